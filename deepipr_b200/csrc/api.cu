@@ -1,0 +1,438 @@
+// api.cu — extern "C" entry points of libpassport_sm100.so (declared in include/passport_sm100.h):
+// argument checking, geometry planning (conv -> tap-GEMM instances) and kernel sequencing.
+#include <string.h>
+
+#include "common.h"
+
+namespace pp {
+
+// ---------------------------------------------------------------- error + device
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static int g_sm_count = -1, g_cc_major = -1, g_cc_minor = -1;
+
+static int query_device() {
+  if (g_sm_count >= 0) return PP_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device (libpassport_sm100 has no CPU path)");
+    return PP_ENODEVICE;
+  }
+  int sm = 0, maj = 0, min = 0;
+  if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cannot query CUDA device attributes");
+    return PP_ENODEVICE;
+  }
+  g_sm_count = sm; g_cc_major = maj; g_cc_minor = min;
+  return PP_OK;
+}
+
+int device_sm_count() {
+  if (query_device() != PP_OK) return 0;
+  return g_sm_count;
+}
+
+int check_device() {
+  PP_TRY(query_device());
+  PP_REQUIRE(g_cc_major == 10, PP_ENODEVICE, "device is sm_%d%d; this library is built for sm_100a only", g_cc_major,
+             g_cc_minor);
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------- geometry
+struct Geo {
+  int P, Q, T;
+  size_t rows;  // N*P*Q
+};
+
+static int geo_of(const PPConvDesc* d, Geo* g) {
+  PP_REQUIRE(d != nullptr, PP_EBADARG, "PPConvDesc is NULL");
+  PP_REQUIRE(d->N > 0 && d->C > 0 && d->H > 0 && d->W > 0 && d->O > 0 && d->kh > 0 && d->kw > 0 && d->stride > 0 &&
+                 d->pad >= 0,
+             PP_EBADSHAPE, "bad conv desc N=%d C=%d H=%d W=%d O=%d k=%dx%d s=%d p=%d", d->N, d->C, d->H, d->W, d->O,
+             d->kh, d->kw, d->stride, d->pad);
+  PP_REQUIRE(d->kh * d->kw <= kMaxTaps, PP_EUNSUPPORTED, "filter %dx%d larger than %d taps", d->kh, d->kw, kMaxTaps);
+  PP_REQUIRE(d->H + 2 * d->pad >= d->kh && d->W + 2 * d->pad >= d->kw, PP_EBADSHAPE, "filter larger than padded input");
+  g->P = (d->H + 2 * d->pad - d->kh) / d->stride + 1;
+  g->Q = (d->W + 2 * d->pad - d->kw) / d->stride + 1;
+  g->T = d->kh * d->kw;
+  g->rows = (size_t)d->N * g->P * g->Q;
+  PP_REQUIRE(g->rows < (1ull << 31), PP_EBADSHAPE, "too many output pixels");
+  return PP_OK;
+}
+
+// forward conv as a tap-GEMM over x (models/layers/passportconv2d.py:18,218)
+static void plan_fprop(const PPConvDesc& d, const Geo& geo, TapGemm& g) {
+  memset(&g, 0, sizeof(g));
+  g.N = d.N; g.H = d.H; g.W = d.W; g.C = d.C;
+  g.P = geo.P; g.Q = geo.Q;
+  g.base_h = -d.pad; g.base_w = -d.pad;
+  g.step_h = d.stride; g.step_w = d.stride;
+  g.upper_h = d.pad - (d.kh - 1);
+  g.upper_w = d.pad - (d.kw - 1);
+  g.ntaps = geo.T;
+  for (int r = 0; r < d.kh; ++r)
+    for (int s = 0; s < d.kw; ++s) {
+      const int t = r * d.kw + s;
+      g.tap_dh[t] = (int8_t)r; g.tap_dw[t] = (int8_t)s; g.tap_kofs[t] = t * d.C;
+    }
+  g.Nout = d.O; g.Ktot = geo.T * d.C;
+  g.out_H = geo.P; g.out_W = geo.Q; g.out_sh = 1; g.out_sw = 1; g.out_ph = 0; g.out_pw = 0; g.out_identity = 1;
+}
+
+// data gradient: dx[h] = sum_r dz[(h + pad - r)/s] W[r] over the r with (h + pad - r) % s == 0.
+// One tap-GEMM over dz per output phase (h % s, w % s); returns 0 if the phase has no taps (dx there is 0).
+static int plan_dgrad_phase(const PPConvDesc& d, const Geo& geo, int ph, int pw, TapGemm& g) {
+  memset(&g, 0, sizeof(g));
+  const int s = d.stride;
+  const int Hph = (d.H - ph + s - 1) / s;
+  const int Wpw = (d.W - pw + s - 1) / s;
+  if (Hph <= 0 || Wpw <= 0) return 0;
+  int rs[8], es_h[8], nh = 0, ss[8], es_w[8], nw = 0;
+  for (int r = 0; r < d.kh; ++r) {
+    const int v = ph + d.pad - r;
+    if (((v % s) + s) % s == 0) { rs[nh] = r; es_h[nh] = (v >= 0) ? v / s : -((-v) / s); ++nh; }
+  }
+  for (int c = 0; c < d.kw; ++c) {
+    const int v = pw + d.pad - c;
+    if (((v % s) + s) % s == 0) { ss[nw] = c; es_w[nw] = (v >= 0) ? v / s : -((-v) / s); ++nw; }
+  }
+  if (nh == 0 || nw == 0) return 0;
+  int bh = es_h[0], bw = es_w[0];
+  for (int i = 1; i < nh; ++i) bh = es_h[i] < bh ? es_h[i] : bh;
+  for (int i = 1; i < nw; ++i) bw = es_w[i] < bw ? es_w[i] : bw;
+  g.N = d.N; g.H = geo.P; g.W = geo.Q; g.C = d.O;  // activation of this GEMM is dz
+  g.P = Hph; g.Q = Wpw;
+  g.base_h = bh; g.base_w = bw; g.step_h = 1; g.step_w = 1;
+  g.upper_h = Hph - geo.P + bh;
+  g.upper_w = Wpw - geo.Q + bw;
+  g.ntaps = 0;
+  for (int i = 0; i < nh; ++i)
+    for (int j = 0; j < nw; ++j) {
+      const int t = g.ntaps++;
+      g.tap_dh[t] = (int8_t)(es_h[i] - bh);
+      g.tap_dw[t] = (int8_t)(es_w[j] - bw);
+      g.tap_kofs[t] = (rs[i] * d.kw + ss[j]) * d.O;  // w_dgrad is [C][kh*kw][O]
+    }
+  g.Nout = d.C; g.Ktot = geo.T * d.O;
+  g.out_H = d.H; g.out_W = d.W; g.out_sh = s; g.out_sw = s; g.out_ph = ph; g.out_pw = pw;
+  g.out_identity = (s == 1) ? 1 : 0;
+  return 1;
+}
+
+static bool use_tcgen05(const PPConvDesc& d, bool supported) {
+  if (d.algo == PP_ALGO_SIMT) return false;
+  return supported;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct FwdWs {
+  float* ca; float* cb; float* partial;
+  size_t total;
+};
+static FwdWs carve_fwd(const PPConvDesc& d, void* base) {
+  FwdWs w;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  w.ca = reinterpret_cast<float*>(p + off); off += align256((size_t)d.O * 4);
+  w.cb = reinterpret_cast<float*>(p + off); off += align256((size_t)d.O * 4);
+  const size_t max_part = (size_t)(bwd_reduce_max_partials() > 160 ? bwd_reduce_max_partials() : 160);
+  w.partial = reinterpret_cast<float*>(p + off); off += align256(max_part * 2 * d.O * 4);
+  w.total = off;
+  return w;
+}
+
+struct BwdWs {
+  float* ca; float* cb; float* k1; float* k2; float* k3; float* partial;
+  __nv_bfloat16* dz; float* wpartial;
+  size_t total;
+};
+static BwdWs carve_bwd(const PPConvDesc& d, const Geo& geo, void* base, int wg_splits) {
+  BwdWs w;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  const size_t vec = align256((size_t)d.O * 4);
+  w.ca = reinterpret_cast<float*>(p + off); off += vec;
+  w.cb = reinterpret_cast<float*>(p + off); off += vec;
+  w.k1 = reinterpret_cast<float*>(p + off); off += vec;
+  w.k2 = reinterpret_cast<float*>(p + off); off += vec;
+  w.k3 = reinterpret_cast<float*>(p + off); off += vec;
+  w.partial = reinterpret_cast<float*>(p + off); off += align256((size_t)bwd_reduce_max_partials() * 2 * d.O * 4);
+  w.dz = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * d.O * 2);
+  w.wpartial = reinterpret_cast<float*>(p + off);
+  off += align256((size_t)wg_splits * d.O * geo.T * d.C * 4);
+  w.total = off;
+  return w;
+}
+
+static int wgrad_splits_for(const PPConvDesc& d, const Geo& geo, bool* tc) {
+  TapGemm g;
+  plan_fprop(d, geo, g);
+  *tc = use_tcgen05(d, wgrad_tcgen05_supported(g, d.O));
+  return *tc ? wgrad_pick_splits(g, d.O) : wgrad_simt_pick_splits(g, d.O);
+}
+
+static int run_fprop(const PPConvDesc& d, const Geo& geo, const void* x, const void* wf, const TapEpilogue& e,
+                     bool* used_tc, cudaStream_t s) {
+  TapGemm g;
+  plan_fprop(d, geo, g);
+  const bool tc = use_tcgen05(d, tapgemm_tcgen05_supported(g));
+  PP_REQUIRE(tc || d.algo != PP_ALGO_TCGEN05, PP_EUNSUPPORTED, "PP_ALGO_TCGEN05 requested but C=%d O=%d unsupported",
+             d.C, d.O);
+  if (used_tc) *used_tc = tc;
+  if (tc) return tapgemm_tcgen05(g, x, wf, e, s);
+  TapEpilogue e2 = e;
+  e2.stats_partial = nullptr;
+  return tapgemm_simt(g, x, wf, e2, s);
+}
+
+static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const void* wd, void* dx, cudaStream_t s) {
+  TapGemm phases[64];
+  int nph = 0;
+  bool any_empty = false;
+  PP_REQUIRE(d.stride <= 8, PP_EUNSUPPORTED, "stride %d > 8", d.stride);
+  for (int ph = 0; ph < d.stride; ++ph)
+    for (int pw = 0; pw < d.stride; ++pw) {
+      if (ph >= d.H || pw >= d.W) continue;
+      if (plan_dgrad_phase(d, geo, ph, pw, phases[nph])) ++nph; else any_empty = true;
+    }
+  if (any_empty) PP_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)d.N * d.H * d.W * d.C * 2, s));
+  for (int i = 0; i < nph; ++i) {
+    TapEpilogue e;
+    e.out = dx; e.out_f32 = 0; e.scale = nullptr; e.shift = nullptr; e.relu = 0; e.stats_partial = nullptr;
+    const bool tc = use_tcgen05(d, tapgemm_tcgen05_supported(phases[i]));
+    PP_REQUIRE(tc || d.algo != PP_ALGO_TCGEN05, PP_EUNSUPPORTED, "PP_ALGO_TCGEN05 requested but dgrad unsupported");
+    if (tc) PP_TRY(tapgemm_tcgen05(phases[i], dz, wd, e, s));
+    else PP_TRY(tapgemm_simt(phases[i], dz, wd, e, s));
+  }
+  return PP_OK;
+}
+
+static int run_wgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const void* x, float* dw, float* wpartial,
+                     int splits, bool tc, cudaStream_t s) {
+  TapGemm g;
+  plan_fprop(d, geo, g);
+  if (tc) PP_TRY(wgrad_tcgen05(g, x, dz, d.O, wpartial, splits, s));
+  else PP_TRY(wgrad_simt(g, x, dz, d.O, wpartial, splits, s));
+  return launch_wgrad_finalize(d, wpartial, splits, dw, s);
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+// ================================================================== C ABI
+extern "C" {
+
+int pp_version(void) { return PP_ABI_VERSION; }
+const char* pp_last_error(void) { return get_error(); }
+
+int pp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  PP_TRY(query_device());
+  if (sm_count) *sm_count = g_sm_count;
+  if (cc_major) *cc_major = g_cc_major;
+  if (cc_minor) *cc_minor = g_cc_minor;
+  return PP_OK;
+}
+
+int pp_workspace_bytes(const PPConvDesc* d, int which, size_t* bytes) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_REQUIRE(bytes != nullptr, PP_EBADARG, "bytes is NULL");
+  if (which == PP_WS_FWD) {
+    *bytes = carve_fwd(*d, nullptr).total;
+  } else if (which == PP_WS_BWD) {
+    bool tc;
+    const int splits = wgrad_splits_for(*d, geo, &tc);
+    *bytes = carve_bwd(*d, geo, nullptr, splits).total;
+  } else {
+    set_error("unknown workspace kind %d", which);
+    return PP_EBADARG;
+  }
+  return PP_OK;
+}
+
+int pp_weight_prep(const PPConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  PP_REQUIRE(w_oihw && w_fprop, PP_EBADARG, "weight pointers are NULL");
+  return launch_weight_prep(*d, w_oihw, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad, (cudaStream_t)stream);
+}
+
+int pp_key_pool(const PPConvDesc* d, int Bk, const float* key_nchw, double* S, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  PP_REQUIRE(key_nchw && S && Bk > 0, PP_EBADARG, "key pool: NULL pointer or empty key batch");
+  return launch_key_pool(*d, Bk, key_nchw, S, (cudaStream_t)stream);
+}
+
+int pp_passport_affine_fwd(const PPConvDesc* d, const void* w_fprop, const double* S_skey, const double* S_key,
+                           const float* b_sign, float alpha, float* gamma, float* beta, float* sign_loss,
+                           float* sign_acc, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  PP_REQUIRE(w_fprop && S_skey && S_key && gamma && beta, PP_EBADARG, "passport affine: NULL pointer");
+  return launch_passport_affine_fwd(*d, (const __nv_bfloat16*)w_fprop, S_skey, S_key, b_sign, alpha, gamma, beta,
+                                    sign_loss, sign_acc, (cudaStream_t)stream);
+}
+
+int pp_passport_affine_bwd(const PPConvDesc* d, const double* S_skey, const double* S_key, const float* gamma,
+                           const float* b_sign, float alpha, const float* g_gamma, const float* g_beta,
+                           const float* g_loss, float* dw_oihw, int accumulate, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  PP_REQUIRE(S_skey && S_key && dw_oihw, PP_EBADARG, "passport affine bwd: NULL pointer");
+  PP_REQUIRE(!(g_loss && b_sign) || gamma, PP_EBADARG, "passport affine bwd: gamma needed for the sign-loss term");
+  return launch_passport_affine_bwd(*d, S_skey, S_key, gamma, b_sign, alpha, g_gamma, g_beta, g_loss, dw_oihw,
+                                    accumulate, (cudaStream_t)stream);
+}
+
+int pp_sign_loss_fwd(int O, const float* gamma, const float* b_sign, float alpha, float* sign_loss, float* sign_acc,
+                     void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(O > 0 && gamma && b_sign, PP_EBADARG, "sign loss: bad arguments");
+  return launch_sign_loss_fwd(O, gamma, b_sign, alpha, sign_loss, sign_acc, (cudaStream_t)stream);
+}
+
+int pp_sign_loss_bwd(int O, const float* gamma, const float* b_sign, float alpha, const float* g_loss,
+                     float* g_gamma, void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(O > 0 && gamma && b_sign && g_gamma, PP_EBADARG, "sign loss bwd: bad arguments");
+  return launch_sign_loss_bwd(O, gamma, b_sign, alpha, g_loss, g_gamma, (cudaStream_t)stream);
+}
+
+int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, void* z, void* y, float* save_mean,
+                      float* save_invstd, void* workspace, size_t ws_bytes, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  cudaStream_t s = (cudaStream_t)stream;
+  PP_REQUIRE(x && w_fprop && y, PP_EBADARG, "conv block fwd: NULL pointer");
+  PP_REQUIRE(d->norm == PP_NORM_NONE || d->norm == PP_NORM_BN_TRAIN || d->norm == PP_NORM_BN_EVAL, PP_EBADARG,
+             "unknown norm %d", d->norm);
+  PP_REQUIRE(d->norm != PP_NORM_BN_EVAL || (running_mean && running_var), PP_EBADARG, "BN eval needs running stats");
+  PP_REQUIRE(d->norm != PP_NORM_BN_TRAIN || z, PP_EBADARG, "BN train needs the z buffer");
+  FwdWs ws = carve_fwd(*d, workspace);
+  PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "fwd workspace too small: need %zu, got %zu", ws.total,
+             ws_bytes);
+  if (z == nullptr) {
+    // inference: statistics are known up front, the affine lives in the conv epilogue
+    PP_TRY(launch_bn_finalize(*d, (int)geo.rows, nullptr, 0, gamma, beta, running_mean, running_var, save_mean,
+                              save_invstd, ws.ca, ws.cb, s));
+    TapEpilogue e;
+    e.out = y; e.out_f32 = 0; e.scale = ws.ca; e.shift = ws.cb; e.relu = d->relu; e.stats_partial = nullptr;
+    return run_fprop(*d, geo, x, w_fprop, e, nullptr, s);
+  }
+  TapEpilogue e;
+  e.out = z; e.out_f32 = d->z_f32; e.scale = nullptr; e.shift = nullptr; e.relu = 0;
+  e.stats_partial = (d->norm == PP_NORM_BN_TRAIN) ? ws.partial : nullptr;
+  bool tc = false;
+  PP_TRY(run_fprop(*d, geo, x, w_fprop, e, &tc, s));
+  int num_partials = 0;
+  if (d->norm == PP_NORM_BN_TRAIN) {
+    if (tc) {
+      TapGemm g;
+      plan_fprop(*d, geo, g);
+      num_partials = tapgemm_tcgen05_grid(g);
+    } else {
+      PP_TRY(launch_col_stats(z, d->z_f32, geo.rows, d->O, ws.partial, &num_partials, s));
+    }
+  }
+  PP_TRY(launch_bn_finalize(*d, (int)geo.rows, ws.partial, num_partials, gamma, beta, running_mean, running_var,
+                            save_mean, save_invstd, ws.ca, ws.cb, s));
+  return launch_affine_apply(z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, (__nv_bfloat16*)y, s);
+}
+
+int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad, const void* z,
+                      const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                      void* dx, float* dw_oihw, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
+                      void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  cudaStream_t s = (cudaStream_t)stream;
+  PP_REQUIRE(dy && z && save_mean && save_invstd && dgamma && dbeta, PP_EBADARG, "conv block bwd: NULL pointer");
+  PP_REQUIRE(!dx || w_dgrad, PP_EBADARG, "dx requested without w_dgrad");
+  PP_REQUIRE(!dw_oihw || x, PP_EBADARG, "dw requested without x");
+  bool wg_tc = false;
+  const int splits = wgrad_splits_for(*d, geo, &wg_tc);
+  BwdWs ws = carve_bwd(*d, geo, workspace, splits);
+  PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "bwd workspace too small: need %zu, got %zu", ws.total,
+             ws_bytes);
+  PP_TRY(launch_affine_coef(d->O, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb, s));
+  int num_partials = 0;
+  PP_TRY(launch_bwd_reduce((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.partial,
+                           &num_partials, s));
+  PP_TRY(launch_bwd_coef(*d, geo.rows, ws.partial, num_partials, gamma, save_mean, save_invstd, dgamma, dbeta, ws.k1,
+                         ws.k2, ws.k3, s));
+  if (!dx && !dw_oihw) return PP_OK;
+  PP_TRY(launch_bwd_dz((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.k1, ws.k2,
+                       ws.k3, ws.dz, s));
+  if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));
+  if (dw_oihw) PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, splits, wg_tc, s));
+  return PP_OK;
+}
+
+int pp_conv_fwd_raw(const PPConvDesc* d, const void* x, const void* w_fprop, void* z, void* workspace,
+                    size_t ws_bytes, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  PP_REQUIRE(x && w_fprop && z, PP_EBADARG, "conv fwd raw: NULL pointer");
+  (void)workspace; (void)ws_bytes;
+  TapEpilogue e;
+  e.out = z; e.out_f32 = d->z_f32; e.scale = nullptr; e.shift = nullptr; e.relu = 0; e.stats_partial = nullptr;
+  return run_fprop(*d, geo, x, w_fprop, e, nullptr, (cudaStream_t)stream);
+}
+
+int pp_conv_dgrad(const PPConvDesc* d, const void* dz, const void* w_dgrad, void* dx, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  PP_REQUIRE(dz && w_dgrad && dx, PP_EBADARG, "conv dgrad: NULL pointer");
+  return run_dgrad(*d, geo, dz, w_dgrad, dx, (cudaStream_t)stream);
+}
+
+int pp_conv_wgrad(const PPConvDesc* d, const void* dz, const void* x, float* dw_oihw, void* workspace,
+                  size_t ws_bytes, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  PP_REQUIRE(dz && x && dw_oihw, PP_EBADARG, "conv wgrad: NULL pointer");
+  bool tc = false;
+  const int splits = wgrad_splits_for(*d, geo, &tc);
+  BwdWs ws = carve_bwd(*d, geo, workspace, splits);
+  PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "wgrad workspace too small: need %zu, got %zu",
+             ws.total, ws_bytes);
+  return run_wgrad(*d, geo, dz, x, dw_oihw, ws.wpartial, splits, tc, (cudaStream_t)stream);
+}
+
+int pp_sgd_step(size_t n, float* param, const float* grad, float* momentum_buf, float lr, float momentum,
+                float weight_decay, int first_step, void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(param && grad && (momentum == 0.0f || momentum_buf), PP_EBADARG, "sgd: NULL pointer");
+  if (n == 0) return PP_OK;
+  return launch_sgd(n, param, grad, momentum_buf, lr, momentum, weight_decay, first_step, (cudaStream_t)stream);
+}
+
+int pp_debug_last_timeout(void) { return debug_last_timeout(); }
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// common.h — host-side shared declarations of libpassport_sm100 (error reporting, launch geometry).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/passport_sm100.h"
+
+namespace pp {
+
+// thread-local last error message (pp_last_error)
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define PP_CHECK_CUDA(expr)                                                                     \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      pp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));      \
+      return PP_ELAUNCH;                                                                        \
+    }                                                                                           \
+  } while (0)
+
+#define PP_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      pp::set_error(__VA_ARGS__);    \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+#define PP_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != PP_OK) return _s; \
+  } while (0)
+
+constexpr int kMaxTaps = 49;  // up to 7x7 filters
+
+// "Tap-list implicit GEMM":  D[m, n] = sum_t sum_c act[pixel(m) + (dh_t, dw_t), c] * B[n, kofs_t + c]
+//   m enumerates a traversal grid of P x Q positions per image (q fastest, then p, then image):
+//     act pixel = (base_h + p*step_h + dh, base_w + q*step_w + dw), zero outside the tensor
+//   output row m is written at pixel (p*out_sh + out_ph, q*out_sw + out_pw) of an out_H x out_W image.
+// The forward conv, the stride-1 data gradient and every phase of a strided data gradient are all
+// instances of this (see igemm_sm100.cu: plan_fprop / plan_dgrad).
+struct TapGemm {
+  // activation tensor, NHWC bf16
+  int N, H, W, C;
+  // traversal grid
+  int P, Q;
+  int base_h, base_w, step_h, step_w;
+  int upper_h, upper_w;  // im2col bounding-box upper corner (derived from P,Q; kept for the TMA descriptor)
+  int ntaps;
+  int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
+  int tap_kofs[kMaxTaps];
+  // B operand: [Nout, Ktot] row-major bf16
+  int Nout, Ktot;
+  // output mapping
+  int out_H, out_W, out_sh, out_sw, out_ph, out_pw;
+  int out_identity;  // 1: out pixel == m (plain [M, Nout] matrix)
+};
+
+// Epilogue of the tap GEMM
+struct TapEpilogue {
+  void* out;             // [out pixels, Nout], bf16 or fp32
+  int out_f32;           // 1: fp32
+  const float* scale;    // per-n affine a[n] (NULL => 1)
+  const float* shift;    // per-n affine b[n] (NULL => 0)
+  int relu;
+  float* stats_partial;  // NULL or [tapgemm_tcgen05_grid()][2][Nout]: per-CTA sum z, sum z^2 (fp32 accumulators)
+};
+
+int device_sm_count();
+int check_device();  // PP_OK iff current device is sm_100
+
+// --- igemm_sm100.cu (tcgen05) ---
+int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapEpilogue& e, cudaStream_t s);
+bool tapgemm_tcgen05_supported(const TapGemm& g);
+int tapgemm_tcgen05_grid(const TapGemm& g);  // CTAs launched == rows of stats_partial written
+int debug_last_timeout();
+// wgrad: partial[split][Mo][T*C] (fp32) = sum over a slice of pixels of dz[m, o] * act_tap[m, c]
+int wgrad_tcgen05(const TapGemm& g /*fprop geometry of x*/, const void* x, const void* dz, int O, float* partial,
+                  int splits, cudaStream_t s);
+bool wgrad_tcgen05_supported(const TapGemm& g, int O);
+int wgrad_pick_splits(const TapGemm& g, int O);
+
+// --- direct_conv.cu (SIMT, any shape) ---
+int tapgemm_simt(const TapGemm& g, const void* act, const void* B, const TapEpilogue& e, cudaStream_t s);
+int wgrad_simt(const TapGemm& g, const void* x, const void* dz, int O, float* partial, int splits, cudaStream_t s);
+int wgrad_simt_pick_splits(const TapGemm& g, int O);
+
+// --- pointwise.cu ---
+int launch_weight_prep(const PPConvDesc& d, const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s);
+int launch_key_pool(const PPConvDesc& d, int Bk, const float* key, double* S, cudaStream_t s);
+int launch_passport_affine_fwd(const PPConvDesc& d, const __nv_bfloat16* wf, const double* Ss, const double* Sk,
+                               const float* b, float alpha, float* gamma, float* beta, float* loss, float* acc,
+                               cudaStream_t s);
+int launch_passport_affine_bwd(const PPConvDesc& d, const double* Ss, const double* Sk, const float* gamma,
+                               const float* b, float alpha, const float* gg, const float* gb, const float* gl,
+                               float* dw, int accumulate, cudaStream_t s);
+int launch_sign_loss_fwd(int O, const float* gamma, const float* b, float alpha, float* loss, float* acc,
+                         cudaStream_t s);
+int launch_sign_loss_bwd(int O, const float* gamma, const float* b, float alpha, const float* gl, float* gg,
+                         cudaStream_t s);
+// (a, b) affine coefficient vectors + statistics
+int launch_bn_finalize(const PPConvDesc& d, int n_per_channel, const float* stats_partial, int num_tiles,
+                       const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       float* save_mean, float* save_invstd, float* coef_a, float* coef_b, cudaStream_t s);
+int launch_affine_coef(int O, const float* gamma, const float* beta, const float* mean, const float* invstd,
+                       float* ca, float* cb, cudaStream_t s);
+int launch_affine_apply(const void* z, int z_f32, size_t rows, int O, const float* a, const float* b, int relu,
+                        __nv_bfloat16* y, cudaStream_t s);
+int launch_col_stats(const void* z, int z_f32, size_t rows, int O, float* partial, int* num_partials,
+                     cudaStream_t s);
+int launch_bwd_reduce(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
+                      const float* b, int relu, float* partial, int* num_partials, cudaStream_t s);
+int bwd_reduce_max_partials();
+int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int num_partials, const float* gamma,
+                    const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* k1,
+                    float* k2, float* k3, cudaStream_t s);
+int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
+                  const float* b, int relu, const float* k1, const float* k2, const float* k3, __nv_bfloat16* dz,
+                  cudaStream_t s);
+int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, float* dw_oihw, cudaStream_t s);
+int launch_sgd(size_t n, float* p, const float* g, float* buf, float lr, float mom, float wd, int first,
+               cudaStream_t s);
+
+}  // namespace pp

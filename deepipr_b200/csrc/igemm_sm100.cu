@@ -1,0 +1,694 @@
+// igemm_sm100.cu — the tensor-core kernels of the passport-conv path (sm_100a only).
+//
+//   tapgemm_kernel : persistent, warp-specialised implicit-GEMM convolution
+//                    A (activation patches)  : TMA im2col -> 128B-swizzled smem, K-major
+//                    B (weights)             : TMA tiled  -> 128B-swizzled smem, K-major
+//                    D                       : tcgen05.mma kind::f16 (bf16 x bf16 -> fp32) into TMEM,
+//                                              two accumulator buffers so the epilogue of tile i overlaps
+//                                              the main loop of tile i+1
+//                    epilogue                : tcgen05.ld -> registers -> per-channel sum / sum-of-squares
+//                                              (warp-shuffle transpose-reduce) and/or affine+ReLU -> 128-bit stores
+//                    serves conv fprop (passportconv2d.py:218) and its data gradient.
+//   wgrad_kernel   : weight gradient, both operands MN-major (pixels are the reduction dimension),
+//                    split over pixel ranges; fp32 partial tiles go to a workspace reduced by
+//                    pointwise.cu:wgrad_finalize (deterministic order, no float atomics).
+//
+// ptx.cuh is included by this translation unit only (it defines a __device__ variable).
+#include "common.h"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace pp {
+
+// ------------------------------------------------------------------------------------------------
+// driver entry points for tensor-map encoding (resolved at run time: the library must load on a
+// machine without libcuda.so.1, e.g. the CPU-only CI container)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+static std::once_flag g_encode_once;
+
+static int resolve_encoders() {
+  std::call_once(g_encode_once, [] {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+    cudaDriverGetVersion(&g_driver_version);
+  });
+  if (!g_encode_tiled || !g_encode_im2col) {
+    set_error("cuTensorMapEncode{Tiled,Im2col} not available from the driver");
+    return PP_ENODEVICE;
+  }
+  return PP_OK;
+}
+
+// 2-D row-major bf16 matrix [rows, cols]; box = box_rows x 64 columns (128 B), 128B swizzle.
+static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return PP_ELAUNCH;
+  }
+  return PP_OK;
+}
+
+// NHWC bf16 activation in im2col mode: 64 channels x `pixels` traversal positions per load.
+static int make_map_im2col(CUtensorMap* m, const void* ptr, const TapGemm& g, uint32_t pixels) {
+  cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+  int lower[2] = {g.base_w, g.base_h};
+  int upper[2] = {g.upper_w, g.upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.step_w, (cuuint32_t)g.step_h, 1};
+  CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower,
+                               upper, 64, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (%d) NHWC=%d,%d,%d,%d lower=%d,%d upper=%d,%d step=%d,%d", (int)r,
+              g.N, g.H, g.W, g.C, g.base_w, g.base_h, g.upper_w, g.upper_h, g.step_w, g.step_h);
+    return PP_ELAUNCH;
+  }
+  // Same driver workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): on drivers <= 13.1 an
+  // im2col descriptor of a tensor smaller than 128 KiB must have bit 21 of its second 64-bit word cleared.
+  if (g_driver_version <= 13010) {
+    uint64_t bytes = (uint64_t)g.N * g.H * g.W * g.C * 2;
+    if (bytes < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+  }
+  return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+template <int OFF>
+__device__ __forceinline__ void bfly_step(float (&v)[32], int lane) {
+  const bool upper = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < OFF; ++i) {
+    const float send = upper ? v[i] : v[i + OFF];
+    const float keep = upper ? v[i + OFF] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+// Each lane holds one row of 32 columns; afterwards lane L holds the sum of column L over the 32 rows.
+__device__ __forceinline__ float warp_column_sum(float (&v)[32], int lane) {
+  bfly_step<16>(v, lane);
+  bfly_step<8>(v, lane);
+  bfly_step<4>(v, lane);
+  bfly_step<2>(v, lane);
+  bfly_step<1>(v, lane);
+  return v[0];
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct TapGemmDev {
+  int M;            // N * P * Q
+  int P, Q, PQ;
+  int base_h, base_w, step_h, step_w;
+  int C;            // channels of the activation (K per tap)
+  int ntaps;
+  int Nout;
+  int num_m_tiles, num_n_tiles;
+  int out_H, out_W, out_sh, out_sw, out_ph, out_pw, out_identity;
+  int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
+  int tap_kofs[kMaxTaps];
+  // epilogue
+  void* out;
+  int out_f32;
+  const float* scale;
+  const float* shift;
+  int relu;
+  float* stats_partial;
+};
+
+constexpr int kBM = 128;       // output pixels per tile (UMMA M)
+constexpr int kBK = 64;        // channels per pipeline stage (one 128-byte swizzle row of bf16)
+constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..5 epilogue
+constexpr int kMaxStatsN = 1024;  // widest output for which the fused column statistics are kept in smem
+
+template <int BN>
+struct FwdCfg {
+  static constexpr int kStageA = kBM * kBK * 2;  // 16 KiB
+  static constexpr int kStageB = BN * kBK * 2;
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = (BN == 64) ? 8 : (BN == 128 ? 6 : 4);
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
+  static constexpr int kScratch = 2 * BN * 4 /*a,b*/ + 4 * 2 * BN * 4 /*per-warp column sums*/ +
+                                  2 * kMaxStatsN * 4 /*per-CTA running column sums*/;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kScratch + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TapGemmDev p) {
+  using Cfg = FwdCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* s_a = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  float* s_b = s_a + BN;
+  float* s_red = s_b + BN;            // [4 warps][2][BN]
+  float* s_acc = s_red + 4 * 2 * BN;  // [2][Nout] running per-CTA column sums (sum z, sum z^2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_acc + 2 * kMaxStatsN);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int kchunks = p.C / kBK;
+  const int ksteps = p.ntaps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int m_tile = tile / p.num_n_tiles;
+        const int m0 = m_tile * kBM;
+        const int img = m0 / p.PQ;
+        const int rem = m0 - img * p.PQ;
+        const int p0 = rem / p.Q;
+        const int q0 = rem - p0 * p.Q;
+        const int cw = p.base_w + q0 * p.step_w;
+        const int ch = p.base_h + p0 * p.step_h;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const uint16_t dw = (uint16_t)p.tap_dw[t];
+          const uint16_t dh = (uint16_t)p.tap_dh[t];
+          const int kofs = p.tap_kofs[t];
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
+            uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kStageA;
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            tma_load_im2col_4d(&tmA, &full[stage], sa, kc * kBK, cw, ch, img, dw, dh);
+            tma_load_2d(&tmB, &full[stage], sb, kofs + kc * kBK, n_tile * BN);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kStageA;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            tc_mma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, 128 threads = 128 accumulator rows) =====================
+    const int ew = warp - 2;          // 0..3: slot in the reduction scratch
+    const int quarter = warp & 3;     // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;
+    const int tid_e = ew * 32 + lane;
+    const bool has_affine = (p.scale != nullptr) || (p.shift != nullptr);
+    const bool has_stats = p.stats_partial != nullptr;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (has_stats) {
+      for (int i = tid_e; i < 2 * p.Nout; i += 128) s_acc[i] = 0.0f;
+    }
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n0 = n_tile * BN;
+      const int m = m_tile * kBM + row;
+      const bool valid = m < p.M;
+      if (has_affine || has_stats) {
+        named_bar_sync(1, 128);  // previous tile's readers of s_a / s_red are done
+        if (has_affine) {
+          for (int i = tid_e; i < BN; i += 128) {
+            s_a[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.0f;
+            s_b[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.0f;
+          }
+          named_bar_sync(1, 128);
+        }
+      }
+      size_t out_row = 0;
+      if (valid) {
+        if (p.out_identity) {
+          out_row = (size_t)m;
+        } else {
+          const int img = m / p.PQ;
+          const int rem = m - img * p.PQ;
+          const int pp_ = rem / p.Q;
+          const int qq_ = rem - pp_ * p.Q;
+          out_row = ((size_t)img * p.out_H + (size_t)(pp_ * p.out_sh + p.out_ph)) * p.out_W +
+                    (size_t)(qq_ * p.out_sw + p.out_pw);
+        }
+      }
+      mbar_wait(&tfull[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + j * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(raw[i]) : 0.0f;
+        if (has_stats) {
+          float t1[32], t2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            t1[i] = v[i];
+            t2[i] = v[i] * v[i];
+          }
+          const float s1 = warp_column_sum(t1, lane);
+          const float s2 = warp_column_sum(t2, lane);
+          s_red[(ew * 2 + 0) * BN + j * 32 + lane] = s1;
+          s_red[(ew * 2 + 1) * BN + j * 32 + lane] = s2;
+        }
+        if (has_affine) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], s_a[j * 32 + i], s_b[j * 32 + i]);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        if (valid) {
+          if (p.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.Nout + n0 + j * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.Nout + n0 +
+                                                  j * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+              u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+              u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+              u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+              dst[i] = u;
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (has_stats) {
+        named_bar_sync(1, 128);
+        for (int i = tid_e; i < BN; i += 128) {
+          const float a1 = s_red[(0 * 2 + 0) * BN + i] + s_red[(1 * 2 + 0) * BN + i] + s_red[(2 * 2 + 0) * BN + i] +
+                           s_red[(3 * 2 + 0) * BN + i];
+          const float a2 = s_red[(0 * 2 + 1) * BN + i] + s_red[(1 * 2 + 1) * BN + i] + s_red[(2 * 2 + 1) * BN + i] +
+                           s_red[(3 * 2 + 1) * BN + i];
+          // column n0+i is only ever touched by this thread (i == column % BN), so no race across tiles
+          s_acc[n0 + i] += a1;
+          s_acc[p.Nout + n0 + i] += a2;
+        }
+      }
+    }
+    if (has_stats) {
+      named_bar_sync(1, 128);
+      float* dst = p.stats_partial + (size_t)blockIdx.x * 2 * p.Nout;
+      for (int i = tid_e; i < 2 * p.Nout; i += 128) dst[i] = s_acc[i];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+bool tapgemm_tcgen05_supported(const TapGemm& g) {
+  if (g.C % 64 != 0 || g.Nout % 64 != 0) return false;
+  if (g.ntaps < 1 || g.ntaps > kMaxTaps) return false;
+  if (g.base_h < -128 || g.base_h > 127 || g.base_w < -128 || g.base_w > 127) return false;
+  if (g.upper_h < -128 || g.upper_h > 127 || g.upper_w < -128 || g.upper_w > 127) return false;
+  if (g.step_h < 1 || g.step_h > 8 || g.step_w < 1 || g.step_w > 8) return false;
+  for (int t = 0; t < g.ntaps; ++t)
+    if (g.tap_dh[t] < 0 || g.tap_dw[t] < 0) return false;
+  if ((long long)g.N * g.P * g.Q > 0x7fffffffLL) return false;
+  return true;
+}
+
+int tapgemm_tcgen05_grid(const TapGemm& g) {
+  const int bn = (g.Nout % 128 == 0) ? 128 : 64;
+  const long long M = (long long)g.N * g.P * g.Q;
+  const long long tiles = ((M + kBM - 1) / kBM) * (g.Nout / bn);
+  const int sms = device_sm_count();
+  return (int)(tiles < sms ? tiles : sms);
+}
+
+template <int BN>
+static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, const TapEpilogue& e, cudaStream_t s) {
+  using Cfg = FwdCfg<BN>;
+  CUtensorMap tmA, tmB;
+  PP_TRY(make_map_im2col(&tmA, act, g, kBM));
+  PP_TRY(make_map_2d(&tmB, B, (uint64_t)g.Nout, (uint64_t)g.Ktot, BN));
+  TapGemmDev p;
+  p.M = g.N * g.P * g.Q;
+  p.P = g.P; p.Q = g.Q; p.PQ = g.P * g.Q;
+  p.base_h = g.base_h; p.base_w = g.base_w; p.step_h = g.step_h; p.step_w = g.step_w;
+  p.C = g.C; p.ntaps = g.ntaps; p.Nout = g.Nout;
+  p.num_m_tiles = (p.M + kBM - 1) / kBM;
+  p.num_n_tiles = g.Nout / BN;
+  p.out_H = g.out_H; p.out_W = g.out_W; p.out_sh = g.out_sh; p.out_sw = g.out_sw;
+  p.out_ph = g.out_ph; p.out_pw = g.out_pw; p.out_identity = g.out_identity;
+  for (int t = 0; t < g.ntaps; ++t) {
+    p.tap_dh[t] = g.tap_dh[t]; p.tap_dw[t] = g.tap_dw[t]; p.tap_kofs[t] = g.tap_kofs[t];
+  }
+  p.out = e.out; p.out_f32 = e.out_f32; p.scale = e.scale; p.shift = e.shift; p.relu = e.relu;
+  p.stats_partial = e.stats_partial;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  PP_REQUIRE(e.stats_partial == nullptr || g.Nout <= kMaxStatsN, PP_EUNSUPPORTED,
+             "fused column statistics support Nout <= %d (Nout=%d)", kMaxStatsN, g.Nout);
+  const int grid = tapgemm_tcgen05_grid(g);
+  tapgemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, p);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapEpilogue& e, cudaStream_t s) {
+  PP_TRY(resolve_encoders());
+  PP_REQUIRE(tapgemm_tcgen05_supported(g), PP_EUNSUPPORTED,
+             "tcgen05 tap-GEMM needs C%%64==0 and Nout%%64==0 (C=%d Nout=%d)", g.C, g.Nout);
+  if (g.Nout % 128 == 0) return launch_tapgemm<128>(g, act, B, e, s);
+  return launch_tapgemm<64>(g, act, B, e, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient
+//   D[o, c] (one filter tap) = sum over pixels m of dz[m, o] * x_tap[m, c]
+//   A = dz^T  : MN-major (o contiguous),  2 slabs of [64 pixels x 64 o]
+//   B = x_tap : MN-major (c contiguous),  BNW/64 slabs of [64 pixels x 64 c] loaded in im2col mode
+// ------------------------------------------------------------------------------------------------
+constexpr int kWK = 64;  // pixels per stage
+
+template <int BNW>
+struct WgCfg {
+  static constexpr int kStageA = 2 * kWK * 128;            // 16 KiB: two 64-wide o slabs
+  static constexpr int kStageB = (BNW / 64) * kWK * 128;   // 8 or 16 KiB
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = 6;
+  static constexpr int kTmemCols = BNW;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+};
+
+struct WgradDev {
+  int M, P, Q, PQ;
+  int base_h, base_w, step_h, step_w;
+  int C, O, ntaps, Ktot;
+  int c_tiles, o_tiles;
+  int chunks_total, chunks_per_split;
+  int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
+  float* partial;  // [splits][O][Ktot]
+};
+
+template <int BNW>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX,
+             const __grid_constant__ WgradDev p) {
+  using Cfg = WgCfg<BNW>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile decode: blockIdx.x = (tap, o_tile, c_tile), blockIdx.y = split
+  int id = blockIdx.x;
+  const int c_tile = id % p.c_tiles; id /= p.c_tiles;
+  const int o_tile = id % p.o_tiles; id /= p.o_tiles;
+  const int tap = id;
+  const int split = blockIdx.y;
+  const int chunk_lo = split * p.chunks_per_split;
+  int chunk_hi = chunk_lo + p.chunks_per_split;
+  if (chunk_hi > p.chunks_total) chunk_hi = p.chunks_total;
+  const int nchunks = chunk_hi > chunk_lo ? chunk_hi - chunk_lo : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDz);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint16_t dw = (uint16_t)p.tap_dw[tap];
+      const uint16_t dh = (uint16_t)p.tap_dh[tap];
+      for (int ch = chunk_lo; ch < chunk_lo + nchunks; ++ch) {
+        const int m0 = ch * kWK;
+        const int img = m0 / p.PQ;
+        const int rem = m0 - img * p.PQ;
+        const int p0 = rem / p.Q;
+        const int q0 = rem - p0 * p.Q;
+        const int cw = p.base_w + q0 * p.step_w;
+        const int chh = p.base_h + p0 * p.step_h;
+        mbar_wait(&empty[stage], phase ^ 1, 500 + stage);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kStageA;
+        mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+        tma_load_2d(&tmDz, &full[stage], sa, o_tile * 128, m0);
+        tma_load_2d(&tmDz, &full[stage], sa + kWK * 128, o_tile * 128 + 64, m0);
+#pragma unroll
+        for (int i = 0; i < BNW / 64; ++i)
+          tma_load_im2col_4d(&tmX, &full[stage], sb + i * kWK * 128, c_tile * BNW + i * 64, cw, chh, img, dw, dh);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BNW, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nchunks; ++it) {
+        mbar_wait(&full[stage], phase, 600 + stage);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kStageA;
+#pragma unroll
+        for (int k = 0; k < kWK / 16; ++k) {
+          // 16 pixels (k) per instruction = two 8-row groups of 1024 B; MN slabs are kWK*128 B apart
+          const uint64_t da = make_smem_desc_sw128(sa + k * 2048, kWK * 128, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kWK * 128, 1024);
+          tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(tfull);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int o = o_tile * 128 + row;
+    float* dst_row = p.partial + ((size_t)split * p.O + (size_t)o) * p.Ktot + (size_t)tap * p.C + c_tile * BNW;
+    if (nchunks > 0) {
+      mbar_wait(tfull, 0, 700);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+#pragma unroll 1
+    for (int j = 0; j < BNW / 32; ++j) {
+      uint32_t raw[32];
+      if (nchunks > 0) {
+        tmem_ld_32x32(taddr + j * 32, raw);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = 0u;
+      }
+      if (o < p.O) {
+        float4* dst = reinterpret_cast<float4*>(dst_row + j * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                               __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+bool wgrad_tcgen05_supported(const TapGemm& g, int O) {
+  if (g.C % 64 != 0 || O % 64 != 0) return false;
+  if (g.base_h < -128 || g.base_w < -128 || g.upper_h < -128 || g.upper_w < -128) return false;
+  if (g.base_h > 127 || g.base_w > 127 || g.upper_h > 127 || g.upper_w > 127) return false;
+  for (int t = 0; t < g.ntaps; ++t)
+    if (g.tap_dh[t] < 0 || g.tap_dw[t] < 0) return false;
+  return true;
+}
+
+int wgrad_pick_splits(const TapGemm& g, int O) {
+  const int bnw = (g.C % 128 == 0) ? 128 : 64;
+  const int tiles = ((O + 127) / 128) * (g.C / bnw) * g.ntaps;
+  const long long M = (long long)g.N * g.P * g.Q;
+  const int chunks = (int)((M + kWK - 1) / kWK);
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  int splits = (2 * sms + tiles - 1) / tiles;
+  if (splits > chunks) splits = chunks;
+  if (splits < 1) splits = 1;
+  // keep the fp32 partial workspace bounded (64 MiB)
+  const long long per_split = (long long)O * g.ntaps * g.C * 4;
+  while (splits > 1 && per_split * splits > (64ll << 20)) --splits;
+  return splits;
+}
+
+template <int BNW>
+static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, float* partial, int splits,
+                        cudaStream_t s) {
+  using Cfg = WgCfg<BNW>;
+  CUtensorMap tmDz, tmX;
+  const long long M = (long long)g.N * g.P * g.Q;
+  PP_TRY(make_map_2d(&tmDz, dz, (uint64_t)M, (uint64_t)O, kWK));
+  PP_TRY(make_map_im2col(&tmX, x, g, kWK));
+  WgradDev p;
+  p.M = (int)M; p.P = g.P; p.Q = g.Q; p.PQ = g.P * g.Q;
+  p.base_h = g.base_h; p.base_w = g.base_w; p.step_h = g.step_h; p.step_w = g.step_w;
+  p.C = g.C; p.O = O; p.ntaps = g.ntaps; p.Ktot = g.ntaps * g.C;
+  p.c_tiles = g.C / BNW;
+  p.o_tiles = (O + 127) / 128;
+  p.chunks_total = (int)((M + kWK - 1) / kWK);
+  p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
+  for (int t = 0; t < g.ntaps; ++t) { p.tap_dh[t] = g.tap_dh[t]; p.tap_dw[t] = g.tap_dw[t]; }
+  p.partial = partial;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(p.c_tiles * p.o_tiles * g.ntaps, splits);
+  wgrad_kernel<BNW><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmDz, tmX, p);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+int wgrad_tcgen05(const TapGemm& g, const void* x, const void* dz, int O, float* partial, int splits,
+                  cudaStream_t s) {
+  PP_TRY(resolve_encoders());
+  PP_REQUIRE(wgrad_tcgen05_supported(g, O), PP_EUNSUPPORTED, "tcgen05 wgrad needs C%%64==0 and O%%64==0 (C=%d O=%d)",
+             g.C, O);
+  if (g.C % 128 == 0) return launch_wgrad<128>(g, x, dz, O, partial, splits, s);
+  return launch_wgrad<64>(g, x, dz, O, partial, splits, s);
+}
+
+int debug_last_timeout() {
+  int v = 0;
+  cudaMemcpyFromSymbol(&v, g_pp_timeout_code, sizeof(int));
+  return v;
+}
+
+}  // namespace pp

@@ -1,0 +1,588 @@
+// pointwise.cu — the HBM-bound part of the passport block: layout/precision prep, the key-pooled
+// GEMV that yields gamma/beta (+ SignLoss), BatchNorm statistics finalisation, the affine+ReLU pass,
+// the two backward passes (per-channel reductions, dz), the split-K weight-gradient reduction and SGD.
+// All reductions are fixed-order (no float atomics) so results are run-to-run deterministic.
+#include "common.h"
+
+namespace pp {
+
+static inline int grid_for(size_t work_items, int threads, int max_blocks) {
+  size_t b = (work_items + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > (size_t)max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ---------------------------------------------------------------------------------------------
+// weights: fp32 OIHW -> bf16 [O][T][C] (fprop) and bf16 [C][T][O] (dgrad; taps NOT flipped)
+// ---------------------------------------------------------------------------------------------
+__global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                   __nv_bfloat16* __restrict__ wd, int O, int C, int T) {
+  const size_t total = (size_t)O * C * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    // i enumerates the fprop layout [o][t][c]
+    const int c = (int)(i % C);
+    const int t = (int)((i / C) % T);
+    const int o = (int)(i / ((size_t)C * T));
+    const float v = w[((size_t)o * C + c) * T + t];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    wf[i] = h;
+    if (wd) wd[((size_t)c * T + t) * O + o] = h;
+  }
+}
+
+int launch_weight_prep(const PPConvDesc& d, const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s) {
+  const size_t total = (size_t)d.O * d.C * d.kh * d.kw;
+  weight_prep_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(w, wf, wd, d.O, d.C, d.kh * d.kw);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// key pooling: S[t*C + c] = mean_{b,p,q} key[b, c, p*s - pad + r, q*s - pad + s'] (0 outside)
+// ---------------------------------------------------------------------------------------------
+__global__ void key_pool_kernel(const float* __restrict__ key, double* __restrict__ S, int Bk, int C, int H, int W,
+                                int kh, int kw, int stride, int pad, int P, int Q) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int T = kh * kw;
+  if (idx >= T * C) return;
+  const int c = idx % C;
+  const int t = idx / C;
+  const int r = t / kw, sx = t % kw;
+  double acc = 0.0;
+  for (int b = 0; b < Bk; ++b) {
+    const float* kp = key + ((size_t)b * C + c) * H * W;
+    for (int p = 0; p < P; ++p) {
+      const int h = p * stride - pad + r;
+      if (h < 0 || h >= H) continue;
+      for (int q = 0; q < Q; ++q) {
+        const int w = q * stride - pad + sx;
+        if (w < 0 || w >= W) continue;
+        acc += (double)bf16_round(kp[h * W + w]);
+      }
+    }
+  }
+  S[idx] = acc / ((double)Bk * P * Q);
+}
+
+int launch_key_pool(const PPConvDesc& d, int Bk, const float* key, double* S, cudaStream_t s) {
+  const int P = (d.H + 2 * d.pad - d.kh) / d.stride + 1;
+  const int Q = (d.W + 2 * d.pad - d.kw) / d.stride + 1;
+  const int total = d.kh * d.kw * d.C;
+  key_pool_kernel<<<(total + 127) / 128, 128, 0, s>>>(key, S, Bk, d.C, d.H, d.W, d.kh, d.kw, d.stride, d.pad, P, Q);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gamma/beta GEMV (one warp per output channel, fp64 accumulate, fixed-order shuffle tree)
+// ---------------------------------------------------------------------------------------------
+__global__ void passport_gemv_kernel(const __nv_bfloat16* __restrict__ wf, const double* __restrict__ Ss,
+                                     const double* __restrict__ Sk, float* __restrict__ gamma,
+                                     float* __restrict__ beta, int O, int K) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= O) return;
+  const __nv_bfloat16* row = wf + (size_t)warp * K;
+  double g = 0.0, b = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    const double w = (double)__bfloat162float(row[k]);
+    g = fma(w, Ss[k], g);
+    b = fma(w, Sk[k], b);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    g += __shfl_xor_sync(0xffffffffu, g, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+  }
+  if (lane == 0) {
+    gamma[warp] = (float)g;
+    beta[warp] = (float)b;
+  }
+}
+
+// SignLoss.add (sign_loss.py:25-28, 53-54): one block, fixed-order tree reduction in fp64.
+__global__ void sign_loss_kernel(const float* __restrict__ gamma, const float* __restrict__ b, float alpha,
+                                 float* __restrict__ loss, float* __restrict__ acc, int O) {
+  __shared__ double s_h[256], s_r[256], s_a[256];
+  double h = 0.0, r = 0.0, a = 0.0;
+  for (int o = threadIdx.x; o < O; o += blockDim.x) {
+    const float g = gamma[o];
+    const float bb = b[o];
+    const float hinge = fmaxf(-bb * g + 0.1f, 0.0f);  // F.relu(-b * scale + 0.1)
+    h += (double)(alpha * hinge);
+    r += (double)(g * g);
+    const float sb = (bb > 0.f) - (bb < 0.f);
+    const float sg = (g > 0.f) - (g < 0.f);
+    a += (sb == sg) ? 1.0 : 0.0;
+  }
+  s_h[threadIdx.x] = h; s_r[threadIdx.x] = r; s_a[threadIdx.x] = a;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off >= 1; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      s_h[threadIdx.x] += s_h[threadIdx.x + off];
+      s_r[threadIdx.x] += s_r[threadIdx.x + off];
+      s_a[threadIdx.x] += s_a[threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (loss) *loss = (float)(s_h[0] + 0.00001 * s_r[0]);
+    if (acc) *acc = (float)(s_a[0] / (double)O);
+  }
+}
+
+int launch_sign_loss_fwd(int O, const float* gamma, const float* b, float alpha, float* loss, float* acc,
+                         cudaStream_t s) {
+  sign_loss_kernel<<<1, 256, 0, s>>>(gamma, b, alpha, loss, acc, O);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// d(sign_loss)/d(gamma_o) = -alpha*b_o*[0.1 - b_o*gamma_o > 0] + 2e-5*gamma_o
+__device__ __forceinline__ float sign_loss_grad(float g, float b, float alpha) {
+  const float pre = -b * g + 0.1f;
+  return (pre > 0.0f ? -alpha * b : 0.0f) + 2.0f * 0.00001f * g;
+}
+
+__global__ void sign_loss_bwd_kernel(const float* __restrict__ gamma, const float* __restrict__ b, float alpha,
+                                     const float* __restrict__ gl, float* __restrict__ gg, int O) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  const float up = gl ? *gl : 1.0f;
+  gg[o] = up * sign_loss_grad(gamma[o], b[o], alpha);
+}
+
+int launch_sign_loss_bwd(int O, const float* gamma, const float* b, float alpha, const float* gl, float* gg,
+                         cudaStream_t s) {
+  sign_loss_bwd_kernel<<<(O + 127) / 128, 128, 0, s>>>(gamma, b, alpha, gl, gg, O);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+int launch_passport_affine_fwd(const PPConvDesc& d, const __nv_bfloat16* wf, const double* Ss, const double* Sk,
+                               const float* b, float alpha, float* gamma, float* beta, float* loss, float* acc,
+                               cudaStream_t s) {
+  const int K = d.kh * d.kw * d.C;
+  const int warps_per_block = 8;
+  passport_gemv_kernel<<<(d.O + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
+      wf, Ss, Sk, gamma, beta, d.O, K);
+  PP_CHECK_CUDA(cudaGetLastError());
+  if (b && (loss || acc)) PP_TRY(launch_sign_loss_fwd(d.O, gamma, b, alpha, loss, acc, s));
+  return PP_OK;
+}
+
+// dW[o][c][t] (+)= (gg[o] + gl * dLsign/dgamma[o]) * Ss[t*C+c] + gb[o] * Sk[t*C+c]
+__global__ void passport_affine_bwd_kernel(const double* __restrict__ Ss, const double* __restrict__ Sk,
+                                           const float* __restrict__ gamma, const float* __restrict__ b, float alpha,
+                                           const float* __restrict__ gg, const float* __restrict__ gb,
+                                           const float* __restrict__ gl, float* __restrict__ dw, int accumulate,
+                                           int O, int C, int T) {
+  const size_t total = (size_t)O * C * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    const int c = (int)((i / T) % C);
+    const int o = (int)(i / ((size_t)T * C));
+    float cg = gg ? gg[o] : 0.0f;
+    if (gl && b) cg += (*gl) * sign_loss_grad(gamma[o], b[o], alpha);
+    const float cb = gb ? gb[o] : 0.0f;
+    const int k = t * C + c;
+    const float v = (float)((double)cg * Ss[k] + (double)cb * Sk[k]);
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+int launch_passport_affine_bwd(const PPConvDesc& d, const double* Ss, const double* Sk, const float* gamma,
+                               const float* b, float alpha, const float* gg, const float* gb, const float* gl,
+                               float* dw, int accumulate, cudaStream_t s) {
+  const size_t total = (size_t)d.O * d.C * d.kh * d.kw;
+  passport_affine_bwd_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(Ss, Sk, gamma, b, alpha, gg, gb, gl, dw,
+                                                                         accumulate, d.O, d.C, d.kh * d.kw);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm finalise: partial[num][2][O] -> mean, invstd, running stats, affine coefficients
+//   y = a*z + b,  a = gamma*invstd,  b = beta - a*mean   (gamma*bn(z)+beta, passportconv2d.py:219-220)
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(int norm, int n, const float* __restrict__ partial, int num,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ rmean, float* __restrict__ rvar, float eps, float momentum,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                   float* __restrict__ ca, float* __restrict__ cb, int O) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  float mean = 0.0f, invstd = 1.0f;
+  if (norm == PP_NORM_BN_TRAIN) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = 0; i < num; ++i) {
+      s1 += (double)partial[(size_t)i * 2 * O + o];
+      s2 += (double)partial[(size_t)i * 2 * O + O + o];
+    }
+    const double m = s1 / n;
+    double var = s2 / n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean) {
+      const double unbiased = n > 1 ? var * ((double)n / (n - 1)) : var;
+      rmean[o] = (1.0f - momentum) * rmean[o] + momentum * mean;
+      rvar[o] = (1.0f - momentum) * rvar[o] + momentum * (float)unbiased;
+    }
+  } else if (norm == PP_NORM_BN_EVAL) {
+    mean = rmean[o];
+    invstd = 1.0f / sqrtf(rvar[o] + eps);
+  }
+  if (save_mean) save_mean[o] = mean;
+  if (save_invstd) save_invstd[o] = invstd;
+  const float g = gamma ? gamma[o] : 1.0f;
+  const float bt = beta ? beta[o] : 0.0f;
+  const float a = g * invstd;
+  ca[o] = a;
+  cb[o] = bt - a * mean;
+}
+
+int launch_bn_finalize(const PPConvDesc& d, int n, const float* partial, int num, const float* gamma,
+                       const float* beta, float* rmean, float* rvar, float* save_mean, float* save_invstd, float* ca,
+                       float* cb, cudaStream_t s) {
+  bn_finalize_kernel<<<(d.O + 63) / 64, 64, 0, s>>>(d.norm, n, partial, num, gamma, beta, rmean, rvar, d.eps,
+                                                   d.momentum, save_mean, save_invstd, ca, cb, d.O);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// a = gamma*invstd, b = beta - a*mean from the statistics the forward saved (backward re-derives them)
+__global__ void affine_coef_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                                   float* __restrict__ ca, float* __restrict__ cb, int O) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  const float a = (gamma ? gamma[o] : 1.0f) * invstd[o];
+  ca[o] = a;
+  cb[o] = (beta ? beta[o] : 0.0f) - a * mean[o];
+}
+
+int launch_affine_coef(int O, const float* gamma, const float* beta, const float* mean, const float* invstd,
+                       float* ca, float* cb, cudaStream_t s) {
+  affine_coef_kernel<<<(O + 63) / 64, 64, 0, s>>>(gamma, beta, mean, invstd, ca, cb, O);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// affine + ReLU pass: y[r, o] = relu(a[o]*z[r,o] + b[o]); 8 channels (one 128-bit bf16 vector) per thread
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const void* z, int z_f32, size_t vec_idx, float (&v)[8]) {
+  if (z_f32) {
+    const float4* p = reinterpret_cast<const float4*>(z) + vec_idx * 2;
+    const float4 x0 = p[0], x1 = p[1];
+    v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+    v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+  } else {
+    const uint4 u = reinterpret_cast<const uint4*>(z)[vec_idx];
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, size_t vec_idx, float (&v)[8]) {
+  load8(p, 0, vec_idx, v);
+}
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, size_t vec_idx, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  reinterpret_cast<uint4*>(p)[vec_idx] = u;
+}
+__device__ __forceinline__ void load8_coef(const float* c, int ch, float (&v)[8]) {
+  const float4 x0 = __ldg(reinterpret_cast<const float4*>(c + ch));
+  const float4 x1 = __ldg(reinterpret_cast<const float4*>(c + ch + 4));
+  v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+  v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+}
+
+__global__ void affine_apply_kernel(const void* __restrict__ z, int z_f32, size_t nvec, int O,
+                                    const float* __restrict__ a, const float* __restrict__ b, int relu,
+                                    __nv_bfloat16* __restrict__ y) {
+  const int vec_per_row = O >> 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % vec_per_row) << 3;
+    float v[8], ca[8], cb[8];
+    load8(z, z_f32, i, v);
+    load8_coef(a, ch, ca);
+    load8_coef(b, ch, cb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = fmaf(v[k], ca[k], cb[k]);
+      if (relu) v[k] = fmaxf(v[k], 0.0f);
+    }
+    store8_bf16(y, i, v);
+  }
+}
+
+int launch_affine_apply(const void* z, int z_f32, size_t rows, int O, const float* a, const float* b, int relu,
+                        __nv_bfloat16* y, cudaStream_t s) {
+  PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "affine pass needs O%%8==0 (O=%d)", O);
+  const size_t nvec = rows * (size_t)(O / 8);
+  affine_apply_kernel<<<grid_for(nvec, 256, 148 * 8), 256, 0, s>>>(z, z_f32, nvec, O, a, b, relu, y);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column statistics of a stored z (used after the SIMT conv, which has no fused statistics):
+// partial[block][2][O]
+// ---------------------------------------------------------------------------------------------
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxBlocks = 148 * 4;
+int bwd_reduce_max_partials() { return kRedMaxBlocks; }
+
+// Shared skeleton of the per-channel column reductions: each thread owns one 8-channel vector column
+// and a row lane; rows are strided over (row lanes x blocks); row lanes are combined through shared
+// memory in a fixed order.  MODE 0: (sum z, sum z^2).  MODE 1: (sum dy_m, sum dy_m*z).
+template <int MODE>
+__global__ void column_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ z, int z_f32,
+                                     size_t rows, int O, const float* __restrict__ a, const float* __restrict__ b,
+                                     int relu, float* __restrict__ partial) {
+  extern __shared__ float s_part[];  // [row_lanes][2][O]
+  const int vec_per_row = O >> 3;
+  const int row_lanes = kRedThreads / vec_per_row > 0 ? kRedThreads / vec_per_row : 1;
+  const int col = threadIdx.x % vec_per_row;
+  const int rl = threadIdx.x / vec_per_row;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.0f;
+  if (rl < row_lanes) {
+    float ca[8], cb[8];
+    if (MODE == 1 && relu) {
+      load8_coef(a, col * 8, ca);
+      load8_coef(b, col * 8, cb);
+    }
+    for (size_t r = (size_t)blockIdx.x * row_lanes + rl; r < rows; r += (size_t)gridDim.x * row_lanes) {
+      const size_t vi = r * vec_per_row + col;
+      float zv[8];
+      load8(z, z_f32, vi, zv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s1[k] += zv[k];
+          s2[k] = fmaf(zv[k], zv[k], s2[k]);
+        }
+      } else {
+        float g[8];
+        load8_bf16(dy, vi, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float gm = g[k];
+          if (relu && !(fmaf(zv[k], ca[k], cb[k]) > 0.0f)) gm = 0.0f;
+          s1[k] += gm;
+          s2[k] = fmaf(gm, zv[k], s2[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s_part[(rl * 2 + 0) * O + col * 8 + k] = s1[k];
+      s_part[(rl * 2 + 1) * O + col * 8 + k] = s2[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * O; i += blockDim.x) {
+    float acc = 0.0f;
+    for (int l = 0; l < row_lanes; ++l) acc += s_part[l * 2 * O + i];
+    partial[(size_t)blockIdx.x * 2 * O + i] = acc;
+  }
+}
+
+static int column_reduce_launch(int mode, const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O,
+                                const float* a, const float* b, int relu, float* partial, int* num_partials,
+                                cudaStream_t s) {
+  PP_REQUIRE(O % 8 == 0 && O / 8 <= kRedThreads, PP_EBADSHAPE, "column reduce needs O%%8==0 and O<=2048 (O=%d)", O);
+  const int vec_per_row = O / 8;
+  const int row_lanes = kRedThreads / vec_per_row;
+  size_t blocks = (rows + row_lanes - 1) / row_lanes;
+  if (blocks > (size_t)kRedMaxBlocks) blocks = kRedMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  const size_t smem = (size_t)row_lanes * 2 * O * sizeof(float);
+  if (mode == 0) {
+    static bool attr0 = false;
+    if (!attr0) {
+      cudaFuncSetAttribute(column_reduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      attr0 = true;
+    }
+    column_reduce_kernel<0><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, relu, partial);
+  } else {
+    static bool attr1 = false;
+    if (!attr1) {
+      cudaFuncSetAttribute(column_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      attr1 = true;
+    }
+    column_reduce_kernel<1><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, relu, partial);
+  }
+  PP_CHECK_CUDA(cudaGetLastError());
+  *num_partials = (int)blocks;
+  return PP_OK;
+}
+
+int launch_col_stats(const void* z, int z_f32, size_t rows, int O, float* partial, int* num_partials,
+                     cudaStream_t s) {
+  return column_reduce_launch(0, nullptr, z, z_f32, rows, O, nullptr, nullptr, 0, partial, num_partials, s);
+}
+
+int launch_bwd_reduce(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
+                      const float* b, int relu, float* partial, int* num_partials, cudaStream_t s) {
+  return column_reduce_launch(1, dy, z, z_f32, rows, O, a, b, relu, partial, num_partials, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward coefficients.  With dy_m = dy*[a z + b > 0],  s1 = sum dy_m,  s2 = sum dy_m * z:
+//   dbeta  = s1
+//   dgamma = sum dy_m * zhat = invstd * (s2 - mean*s1)
+//   BN (train): dz = invstd*gamma*(dy_m - s1/n - zhat*dgamma/n) = k1*dy_m + k2*z + k3
+//   none / BN(eval):  dz = a*dy_m
+// ---------------------------------------------------------------------------------------------
+__global__ void bwd_coef_kernel(int norm, double n, const float* __restrict__ partial, int num,
+                                const float* __restrict__ gamma, const float* __restrict__ mean,
+                                const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2,
+                                float* __restrict__ k3, int O) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < num; ++i) {
+    s1 += (double)partial[(size_t)i * 2 * O + o];
+    s2 += (double)partial[(size_t)i * 2 * O + O + o];
+  }
+  const double mu = mean[o], is = invstd[o];
+  const double g = gamma ? (double)gamma[o] : 1.0;
+  const double dg = is * (s2 - mu * s1);
+  dgamma[o] = (float)dg;
+  dbeta[o] = (float)s1;
+  const double a = g * is;
+  if (norm == PP_NORM_BN_TRAIN) {
+    const double c2 = -a * is * dg / n;
+    k1[o] = (float)a;
+    k2[o] = (float)c2;
+    k3[o] = (float)(-a * s1 / n - c2 * mu);
+  } else {
+    k1[o] = (float)a;
+    k2[o] = 0.0f;
+    k3[o] = 0.0f;
+  }
+}
+
+int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int num_partials, const float* gamma,
+                    const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* k1,
+                    float* k2, float* k3, cudaStream_t s) {
+  bwd_coef_kernel<<<(d.O + 63) / 64, 64, 0, s>>>(d.norm, (double)rows, partial, num_partials, gamma, save_mean,
+                                                save_invstd, dgamma, dbeta, k1, k2, k3, d.O);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+__global__ void bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ z, int z_f32,
+                              size_t nvec, int O, const float* __restrict__ a, const float* __restrict__ b, int relu,
+                              const float* __restrict__ k1, const float* __restrict__ k2,
+                              const float* __restrict__ k3, __nv_bfloat16* __restrict__ dz) {
+  const int vec_per_row = O >> 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % vec_per_row) << 3;
+    float zv[8], g[8], ca[8], cb[8], c1[8], c2[8], c3[8], out[8];
+    load8(z, z_f32, i, zv);
+    load8_bf16(dy, i, g);
+    load8_coef(a, ch, ca);
+    load8_coef(b, ch, cb);
+    load8_coef(k1, ch, c1);
+    load8_coef(k2, ch, c2);
+    load8_coef(k3, ch, c3);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float gm = g[k];
+      if (relu && !(fmaf(zv[k], ca[k], cb[k]) > 0.0f)) gm = 0.0f;
+      out[k] = fmaf(c1[k], gm, fmaf(c2[k], zv[k], c3[k]));
+    }
+    store8_bf16(dz, i, out);
+  }
+}
+
+int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
+                  const float* b, int relu, const float* k1, const float* k2, const float* k3, __nv_bfloat16* dz,
+                  cudaStream_t s) {
+  PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "dz pass needs O%%8==0 (O=%d)", O);
+  const size_t nvec = rows * (size_t)(O / 8);
+  bwd_dz_kernel<<<grid_for(nvec, 256, 148 * 8), 256, 0, s>>>(dy, z, z_f32, nvec, O, a, b, relu, k1, k2, k3, dz);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight-gradient finalise: dw[o][c][t] = sum_split partial[split][o][t*C + c]   (one block per o)
+// ---------------------------------------------------------------------------------------------
+__global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dw, int O,
+                                      int C, int T) {
+  extern __shared__ float s_row[];  // [T*C]
+  const int o = blockIdx.x;
+  const int K = T * C;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float acc = 0.0f;
+    for (int sidx = 0; sidx < splits; ++sidx) acc += partial[((size_t)sidx * O + o) * K + k];
+    s_row[k] = acc;
+  }
+  __syncthreads();
+  float* dst = dw + (size_t)o * K;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int t = i % T;
+    const int c = i / T;
+    dst[i] = s_row[t * C + c];
+  }
+}
+
+int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, float* dw_oihw, cudaStream_t s) {
+  const int T = d.kh * d.kw;
+  const size_t smem = (size_t)T * d.C * sizeof(float);
+  PP_REQUIRE(smem <= 160 * 1024, PP_EUNSUPPORTED, "filter row too large for wgrad finalise (%zu B)", smem);
+  static bool attr = false;
+  if (!attr) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       160 * 1024));
+    attr = true;
+  }
+  wgrad_finalize_kernel<<<d.O, 256, smem, s>>>(partial, splits, dw_oihw, d.O, d.C, T);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SGD with momentum and weight decay on a flat fp32 buffer (torch.optim.SGD semantics,
+// dampening 0, no nesterov — experiments/classification.py:47-50)
+// ---------------------------------------------------------------------------------------------
+__global__ void sgd_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                           float lr, float mom, float wd, int first) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float w = p[i];
+    float d = g[i] + wd * w;
+    if (mom != 0.0f) {
+      const float m = first ? d : mom * buf[i] + d;
+      buf[i] = m;
+      d = m;
+    }
+    p[i] = w - lr * d;
+  }
+}
+
+int launch_sgd(size_t n, float* p, const float* g, float* buf, float lr, float mom, float wd, int first,
+               cudaStream_t s) {
+  sgd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(n, p, g, buf, lr, mom, wd, first);
+  PP_CHECK_CUDA(cudaGetLastError());
+  return PP_OK;
+}
+
+}  // namespace pp

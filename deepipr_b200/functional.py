@@ -1,0 +1,341 @@
+"""Autograd bindings of the C ABI: the two differentiable operators the passport blocks are made of.
+
+  conv_block        y = relu?(gamma * norm(conv(x, W)) + beta)           (pp_conv_block_fwd / _bwd)
+  passport_affine   (gamma, beta, sign_loss, sign_acc) from W and the pooled passport keys
+                                                                         (pp_passport_affine_fwd / _bwd)
+
+Tensors cross the boundary as raw device pointers on torch's current stream.  Everything here requires
+CUDA tensors; CPU tensors raise (the package has no CPU path by design).
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"deepipr_b200: {what} is on {t.device}; the passport kernels are sm_100a CUDA only (no CPU fallback)")
+
+
+@dataclass(frozen=True)
+class ConvSpec:
+    """Static geometry of a block (constructor arguments of the reference blocks)."""
+    C: int
+    O: int
+    kh: int
+    kw: int
+    stride: int
+    pad: int
+
+    def out_hw(self, H, W):
+        return ((H + 2 * self.pad - self.kh) // self.stride + 1, (W + 2 * self.pad - self.kw) // self.stride + 1)
+
+
+_desc_cache = {}
+_ws_bytes_cache = {}
+_workspace = {}
+#: PP_ALGO_* used by every call; tests flip it to compare the tensor-core path with the SIMT path
+ALGO = L.PP_ALGO_AUTO
+
+
+def make_desc(spec: ConvSpec, N, H, W, norm=L.PP_NORM_NONE, relu=0, z_f32=0, eps=1e-5, momentum=0.1, algo=None):
+    algo = ALGO if algo is None else algo
+    key = (spec, N, H, W, norm, relu, z_f32, eps, momentum, algo)
+    d = _desc_cache.get(key)
+    if d is None:
+        d = L.PPConvDesc(N=N, C=spec.C, H=H, W=W, O=spec.O, kh=spec.kh, kw=spec.kw, stride=spec.stride, pad=spec.pad,
+                         norm=norm, relu=int(relu), z_f32=int(z_f32), eps=eps, momentum=momentum, algo=algo,
+                         reserved=0)
+        _desc_cache[key] = d
+        if len(_desc_cache) > 4096:
+            _desc_cache.clear()
+    return d, key
+
+
+def workspace(desc, key, which, device):
+    """Grow-only per-device scratch buffer (fwd and bwd share it: they are stream-ordered)."""
+    ck = (key, which)
+    nbytes = _ws_bytes_cache.get(ck)
+    if nbytes is None:
+        out = C.c_size_t(0)
+        L.check(L.load().pp_workspace_bytes(C.byref(desc), which, C.byref(out)), "pp_workspace_bytes")
+        nbytes = int(out.value)
+        _ws_bytes_cache[ck] = nbytes
+    buf = _workspace.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspace[device] = buf
+    return buf, nbytes
+
+
+def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW tensor whose memory is dense NHWC bf16 (no copy if it already is)."""
+    if x.dtype != torch.bfloat16:
+        x = x.to(torch.bfloat16)
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+@dataclass
+class PreparedWeight:
+    wf: torch.Tensor                 # bf16 [O, kh, kw, C]
+    wd: Optional[torch.Tensor]       # bf16 [C, kh, kw, O] or None
+    version: int = -1
+    data_ptr: int = 0
+
+
+def prepare_weight(weight: torch.Tensor, spec: ConvSpec, need_dgrad: bool) -> PreparedWeight:
+    """fp32 OIHW master weight -> bf16 operand copies (pp_weight_prep)."""
+    require_cuda(weight, "conv weight")
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    wf = torch.empty((spec.O, spec.kh, spec.kw, spec.C), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((spec.C, spec.kh, spec.kw, spec.O), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
+    d, _ = make_desc(spec, 1, max(spec.kh, 1), max(spec.kw, 1))
+    L.check(L.load().pp_weight_prep(C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), _stream()), "pp_weight_prep")
+    return PreparedWeight(wf, wd, weight._version, weight.data_ptr())
+
+
+def key_pool(key: torch.Tensor, spec: ConvSpec) -> torch.Tensor:
+    """Pooled passport patch S (fp64 [kh*kw*C]) such that GAP(conv(W, key)) == W.view(O, -1) @ S."""
+    require_cuda(key, "passport key")
+    k = key.detach()
+    if k.dtype != torch.float32 or not k.is_contiguous():
+        k = k.float().contiguous()
+    Bk, Ck, H, W = k.shape
+    if Ck != spec.C:
+        raise RuntimeError(f"passport key has {Ck} channels, block expects {spec.C}")
+    S = torch.empty(spec.kh * spec.kw * spec.C, dtype=torch.float64, device=k.device)
+    d, _ = make_desc(spec, 1, H, W)
+    L.check(L.load().pp_key_pool(C.byref(d), int(Bk), L.ptr(k), L.ptr(S), _stream()), "pp_key_pool")
+    return S
+
+
+@dataclass
+class AffineCtx:
+    spec: ConvSpec
+    prepared: PreparedWeight
+    S_skey: torch.Tensor
+    S_key: torch.Tensor
+    b: Optional[torch.Tensor]
+    alpha: float
+
+
+class _PassportAffineFn(torch.autograd.Function):
+    """gamma = GAP(conv(W, skey)), beta = GAP(conv(W, key)) + SignLoss.add(gamma)
+    (reference: passportconv2d.py:142-175, sign_loss.py:32-54)."""
+
+    @staticmethod
+    def forward(ctx, weight, actx: AffineCtx):
+        dev = weight.device
+        O = actx.spec.O
+        gamma = torch.empty(O, dtype=torch.float32, device=dev)
+        beta = torch.empty(O, dtype=torch.float32, device=dev)
+        has_b = actx.b is not None
+        loss = torch.zeros((), dtype=torch.float32, device=dev) if has_b else None
+        acc = torch.zeros((), dtype=torch.float32, device=dev) if has_b else None
+        d, _ = make_desc(actx.spec, 1, actx.spec.kh, actx.spec.kw)
+        L.check(L.load().pp_passport_affine_fwd(
+            C.byref(d), L.ptr(actx.prepared.wf), L.ptr(actx.S_skey), L.ptr(actx.S_key), L.ptr(actx.b),
+            float(actx.alpha), L.ptr(gamma), L.ptr(beta), L.ptr(loss), L.ptr(acc), _stream()),
+            "pp_passport_affine_fwd")
+        ctx.actx = actx
+        ctx.save_for_backward(gamma)
+        ctx.wshape = weight.shape
+        if has_b:
+            ctx.mark_non_differentiable(acc)
+            return gamma, beta, loss, acc
+        return gamma, beta
+
+    @staticmethod
+    def backward(ctx, g_gamma, g_beta, g_loss=None, g_acc=None):
+        actx = ctx.actx
+        (gamma,) = ctx.saved_tensors
+        dev = gamma.device
+        dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dev)
+
+        def f32(t):
+            return None if t is None else t.contiguous().float()
+
+        g_gamma, g_beta, g_loss = f32(g_gamma), f32(g_beta), f32(g_loss)
+        d, _ = make_desc(actx.spec, 1, actx.spec.kh, actx.spec.kw)
+        L.check(L.load().pp_passport_affine_bwd(
+            C.byref(d), L.ptr(actx.S_skey), L.ptr(actx.S_key), L.ptr(gamma), L.ptr(actx.b), float(actx.alpha),
+            L.ptr(g_gamma), L.ptr(g_beta), L.ptr(g_loss), L.ptr(dw), 0, _stream()), "pp_passport_affine_bwd")
+        return dw, None
+
+
+def passport_affine(weight, actx: AffineCtx):
+    """Returns (gamma[O], beta[O], sign_loss or None, sign_acc or None)."""
+    require_cuda(weight, "conv weight")
+    out = _PassportAffineFn.apply(weight, actx)
+    if len(out) == 2:
+        return out[0], out[1], None, None
+    return out
+
+
+class _SignLossFn(torch.autograd.Function):
+    """SignLoss.add on an arbitrary scale tensor (sign_loss.py:18-54)."""
+
+    @staticmethod
+    def forward(ctx, scale, b, alpha):
+        g = scale.detach().reshape(-1).float().contiguous()
+        bb = b.detach().reshape(-1).float().contiguous()
+        loss = torch.zeros((), dtype=torch.float32, device=g.device)
+        acc = torch.zeros((), dtype=torch.float32, device=g.device)
+        L.check(L.load().pp_sign_loss_fwd(int(g.numel()), L.ptr(g), L.ptr(bb), float(alpha), L.ptr(loss), L.ptr(acc),
+                                          _stream()), "pp_sign_loss_fwd")
+        ctx.save_for_backward(g, bb)
+        ctx.alpha = float(alpha)
+        ctx.shape = scale.shape
+        ctx.dtype = scale.dtype
+        ctx.mark_non_differentiable(acc)
+        return loss, acc
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc=None):
+        g, bb = ctx.saved_tensors
+        gg = torch.empty_like(g)
+        gl = g_loss.contiguous().float()
+        L.check(L.load().pp_sign_loss_bwd(int(g.numel()), L.ptr(g), L.ptr(bb), ctx.alpha, L.ptr(gl), L.ptr(gg),
+                                          _stream()), "pp_sign_loss_bwd")
+        return gg.reshape(ctx.shape).to(ctx.dtype), None, None
+
+
+def sign_loss(scale, b, alpha):
+    require_cuda(scale, "scale")
+    return _SignLossFn.apply(scale, b, alpha)
+
+
+@dataclass
+class BlockOpts:
+    spec: ConvSpec
+    norm: int                 # PP_NORM_*
+    relu: bool
+    z_f32: bool
+    eps: float = 1e-5
+    momentum: float = 0.1
+    running_mean: Optional[torch.Tensor] = None
+    running_var: Optional[torch.Tensor] = None
+    out_dtype: Optional[torch.dtype] = None
+    algo: Optional[int] = None
+
+
+class _ConvBlockFn(torch.autograd.Function):
+    """Fused conv -> (batch-norm) -> per-channel affine -> ReLU and its backward
+    (reference: passportconv2d.py:218-222, passportconv2d_private.py:215-218, conv2d.py:29-36)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, prepared: PreparedWeight, o: BlockOpts):
+        spec = o.spec
+        N, Cx, H, W = x.shape
+        if Cx != spec.C:
+            raise RuntimeError(f"input has {Cx} channels, block expects {spec.C}")
+        P, Q = spec.out_hw(H, W)
+        dev = x.device
+        xc = to_nhwc_bf16(x.detach())
+        need_grad = any(ctx.needs_input_grad[:4])
+        keep_z = need_grad or o.norm == L.PP_NORM_BN_TRAIN
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo)
+        y = torch.empty((N, spec.O, P, Q), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        z = torch.empty((N, P, Q, spec.O), dtype=torch.float32 if o.z_f32 else torch.bfloat16, device=dev) \
+            if keep_z else None
+        save_mean = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        save_invstd = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        g = None if gamma is None else gamma.detach().reshape(-1).float().contiguous()
+        b = None if beta is None else beta.detach().reshape(-1).float().contiguous()
+        ws, nbytes = workspace(d, key, L.PP_WS_FWD, dev)
+        L.check(L.load().pp_conv_block_fwd(
+            C.byref(d), L.ptr(xc), L.ptr(prepared.wf), L.ptr(g), L.ptr(b), L.ptr(o.running_mean),
+            L.ptr(o.running_var), L.ptr(z), L.ptr(y), L.ptr(save_mean), L.ptr(save_invstd), L.ptr(ws),
+            C.c_size_t(nbytes), _stream()), "pp_conv_block_fwd")
+        if need_grad:
+            ctx.save_for_backward(xc, z, g, b, save_mean, save_invstd)
+            ctx.prepared = prepared
+            ctx.o = o
+            ctx.x_dtype = x.dtype
+            ctx.xshape = (N, Cx, H, W)
+            ctx.wshape = weight.shape
+            ctx.gshape = None if gamma is None else gamma.shape
+            ctx.bshape = None if beta is None else beta.shape
+            ctx.gdtype = None if gamma is None else gamma.dtype
+            ctx.bdtype = None if beta is None else beta.dtype
+        out_dtype = o.out_dtype or x.dtype
+        return y if out_dtype == torch.bfloat16 else y.to(out_dtype)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, z, g, b, save_mean, save_invstd = ctx.saved_tensors
+        o, spec = ctx.o, ctx.o.spec
+        N, Cx, H, W = ctx.xshape
+        dev = gy.device
+        gyc = to_nhwc_bf16(gy)
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo)
+        dx = torch.empty((N, Cx, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last) \
+            if need_dx else None
+        dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dev) if need_dw else None
+        dgamma = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        if need_dx and ctx.prepared.wd is None:
+            raise RuntimeError("deepipr_b200: dgrad weights were not prepared")
+        ws, nbytes = workspace(d, key, L.PP_WS_BWD, dev)
+        L.check(L.load().pp_conv_block_bwd(
+            C.byref(d), L.ptr(gyc), L.ptr(xc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(g), L.ptr(b), L.ptr(save_mean),
+            L.ptr(save_invstd), L.ptr(dx), L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), C.c_size_t(nbytes),
+            _stream()), "pp_conv_block_bwd")
+        if dx is not None and ctx.x_dtype != torch.bfloat16:
+            dx = dx.to(ctx.x_dtype)
+        gg = dgamma.reshape(ctx.gshape).to(ctx.gdtype) if (ctx.gshape is not None and ctx.needs_input_grad[2]) else None
+        gb = dbeta.reshape(ctx.bshape).to(ctx.bdtype) if (ctx.bshape is not None and ctx.needs_input_grad[3]) else None
+        return dx, dw, gg, gb, None, None
+
+
+def conv_block(x, weight, gamma, beta, prepared: PreparedWeight, opts: BlockOpts):
+    require_cuda(x, "block input")
+    require_cuda(weight, "conv weight")
+    return _ConvBlockFn.apply(x, weight, gamma, beta, prepared, opts)
+
+
+# ---------------------------------------------------------------- raw building blocks (tests / profiling)
+def conv_fwd_raw(x, prepared: PreparedWeight, spec: ConvSpec, z_f32=False, algo=None):
+    require_cuda(x, "input")
+    N, _, H, W = x.shape
+    P, Q = spec.out_hw(H, W)
+    xc = to_nhwc_bf16(x)
+    d, key = make_desc(spec, N, H, W, z_f32=int(z_f32), algo=algo)
+    z = torch.empty((N, P, Q, spec.O), dtype=torch.float32 if z_f32 else torch.bfloat16, device=x.device)
+    L.check(L.load().pp_conv_fwd_raw(C.byref(d), L.ptr(xc), L.ptr(prepared.wf), L.ptr(z), None, C.c_size_t(0),
+                                     _stream()), "pp_conv_fwd_raw")
+    return z  # NHWC
+
+
+def conv_dgrad(dz_nhwc, prepared: PreparedWeight, spec: ConvSpec, N, H, W, algo=None):
+    require_cuda(dz_nhwc, "dz")
+    d, key = make_desc(spec, N, H, W, algo=algo)
+    dz = dz_nhwc.to(torch.bfloat16).contiguous()
+    dx = torch.empty((N, H, W, spec.C), dtype=torch.bfloat16, device=dz.device)
+    L.check(L.load().pp_conv_dgrad(C.byref(d), L.ptr(dz), L.ptr(prepared.wd), L.ptr(dx), _stream()), "pp_conv_dgrad")
+    return dx  # NHWC
+
+
+def conv_wgrad(dz_nhwc, x, spec: ConvSpec, algo=None):
+    require_cuda(dz_nhwc, "dz")
+    N, _, H, W = x.shape
+    xc = to_nhwc_bf16(x)
+    d, key = make_desc(spec, N, H, W, algo=algo)
+    dz = dz_nhwc.to(torch.bfloat16).contiguous()
+    dw = torch.empty((spec.O, spec.C, spec.kh, spec.kw), dtype=torch.float32, device=dz.device)
+    ws, nbytes = workspace(d, key, L.PP_WS_BWD, dz.device)
+    L.check(L.load().pp_conv_wgrad(C.byref(d), L.ptr(dz), L.ptr(xc), L.ptr(dw), L.ptr(ws), C.c_size_t(nbytes),
+                                   _stream()), "pp_conv_wgrad")
+    return dw

@@ -1,0 +1,218 @@
+"""Network wiring used by the benchmark, smoke test and parity tests when the reference checkout is not
+available (the GPU box has no /root/reference).  Pure module plumbing — no arithmetic of its own — with the
+same attribute names and therefore the same state_dict keys as the reference's
+
+  models/resnet_passport_private.py (ResNetPrivate, :89-182)   models/resnet_passport.py (:88-180)
+  models/resnet_normal.py (:52-119)                            models/alexnet_passport*.py, alexnet_normal.py
+
+so checkpoints interchange.  One parametrised class per family instead of the reference's one file per scheme.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .layers import ConvBlock, PassportBlock, PassportPrivateBlock
+
+SCHEMES = ('normal', 'v1', 'private')
+
+
+def passport_kwargs_from_config(config, norm_type='bn', key_type='random', sign_loss=0.1):
+    """{'layer4': {'0': {'convbnrelu_1': true|false|"signature"}}, '4': true ...} -> per-block kwargs
+    (what experiments/utils.py:6-50 builds from passport_configs/*.json)."""
+    def leaf(flag):
+        kw = {'flag': bool(flag), 'norm_type': norm_type, 'key_type': key_type, 'sign_loss': sign_loss}
+        if isinstance(flag, str):
+            kw['b'] = flag
+        return kw
+
+    def walk(node):
+        return {k: walk(v) for k, v in node.items()} if isinstance(node, dict) else leaf(node)
+
+    return walk(config)
+
+
+def resnet18_passport_config(passport_layers=('layer4',), signature=None):
+    """Same content as passport_configs/resnet18_passport.json: every conv of the listed stages is a passport layer."""
+    cfg = {'convbnrelu_1': False}
+    for li, name in enumerate(('layer1', 'layer2', 'layer3', 'layer4')):
+        flag = name in passport_layers
+        stage = {}
+        for bi in range(2):
+            blk = {'convbnrelu_1': flag, 'convbn_2': flag}
+            if bi == 0 and li > 0:
+                blk['shortcut'] = flag
+            stage[str(bi)] = blk
+        cfg[name] = stage
+    if signature is not None and 'layer4' in passport_layers:
+        cfg['layer4']['1']['convbn_2'] = signature
+    return cfg
+
+
+def alexnet_passport_config(passport_layers=('4', '5', '6')):
+    """Same content as passport_configs/alexnet_passport.json."""
+    return {k: (k in passport_layers) for k in ('0', '2', '4', '5', '6')}
+
+
+class BlockSet:
+    """The three block classes a net is assembled from (the tests' CPU oracle plugs its own set in here)."""
+
+    def __init__(self, conv=ConvBlock, v1=PassportBlock, private=PassportPrivateBlock):
+        self.conv, self.v1, self.private = conv, v1, private
+
+
+_DEFAULT_BLOCKS = BlockSet()
+
+
+def _make_block(blocks, scheme, kw, i, o, ks, s, pd, norm_type, relu=True):
+    if scheme != 'normal' and kw['flag']:
+        if scheme == 'private':
+            return blocks.private(i, o, ks, s, pd, passport_kwargs=kw)
+        return blocks.v1(i, o, ks, s, pd, passport_kwargs=kw, relu=relu)
+    return blocks.conv(i, o, ks, s, pd, bn=kw['norm_type'] if kw else norm_type, relu=relu)
+
+
+def _is_passport(block):
+    return getattr(block, 'KIND', None) in ('v1', 'private')
+
+
+def _call(block, x, force_passport, ind):
+    kind = getattr(block, 'KIND', None)
+    if kind == 'private':
+        return block(x, force_passport, ind)
+    if kind == 'v1':
+        return block(x, force_passport)
+    return block(x)
+
+
+class BasicUnit(nn.Module):
+    """Two 3x3 blocks + (projected) shortcut; attribute names as BasicPrivateBlock / BasicPassportBlock / BasicBlock."""
+    expansion = 1
+
+    def __init__(self, scheme, in_planes, planes, stride, kwargs, norm_type, blocks=_DEFAULT_BLOCKS):
+        super().__init__()
+        kw = kwargs or {}
+        # every block of the reference nets is built with relu=True, convbn_2 and the shortcut included
+        # (resnet_normal.py:15-20, resnet_passport.py:26-30, resnet_passport_private.py:26-30)
+        self.convbnrelu_1 = _make_block(blocks, scheme, kw.get('convbnrelu_1'), in_planes, planes, 3, stride, 1, norm_type)
+        self.convbn_2 = _make_block(blocks, scheme, kw.get('convbn_2'), planes, planes, 3, 1, 1, norm_type)
+        self.shortcut = nn.Sequential()
+        if stride != 1 or in_planes != planes:
+            self.shortcut = _make_block(blocks, scheme, kw.get('shortcut'), in_planes, planes, 1, stride, 0, norm_type)
+
+    def forward(self, x, force_passport=False, ind=0):
+        out = _call(self.convbnrelu_1, x, force_passport, ind)
+        out = _call(self.convbn_2, out, force_passport, ind)
+        if isinstance(self.shortcut, nn.Sequential):
+            out = out + x
+        else:
+            out = out + _call(self.shortcut, x, force_passport, ind)
+        return F.relu(out)
+
+    def set_intermediate_keys(self, pre, x, y=None):
+        def step(mine, theirs, a, b):
+            if _is_passport(mine):
+                mine.set_key(a, b)
+            return theirs(a), (theirs(b) if b is not None else None)
+
+        ox, oy = step(self.convbnrelu_1, pre.convbnrelu_1, x, y)
+        ox, oy = step(self.convbn_2, pre.convbn_2, ox, oy)
+        if isinstance(self.shortcut, nn.Sequential):
+            sx, sy = x, y
+        else:
+            sx, sy = step(self.shortcut, pre.shortcut, x, y)
+        ox = F.relu(ox + sx)
+        oy = F.relu(oy + sy) if y is not None else None
+        return ox, oy
+
+
+class ResNet18(nn.Module):
+    """ResNet-18 in the three reference flavours: scheme='normal' | 'v1' | 'private'."""
+
+    def __init__(self, scheme='private', num_classes=10, passport_kwargs=None, norm_type='bn', imagenet=False,
+                 blocks=_DEFAULT_BLOCKS):
+        super().__init__()
+        assert scheme in SCHEMES
+        self.scheme = scheme
+        pk = passport_kwargs if scheme != 'normal' else None
+        if pk is None:
+            pk = passport_kwargs_from_config(resnet18_passport_config(()), norm_type=norm_type)
+        stem_kw = pk['convbnrelu_1']
+        if num_classes == 1000 or imagenet:
+            self.convbnrelu_1 = nn.Sequential(_make_block(blocks, scheme, stem_kw, 3, 64, 7, 2, 3, norm_type),
+                                              nn.MaxPool2d(3, 2, 1))
+        else:
+            self.convbnrelu_1 = _make_block(blocks, scheme, stem_kw, 3, 64, 3, 1, 1, norm_type)
+        in_planes = 64
+        for li, (planes, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), start=1):
+            units = []
+            for bi, st in enumerate((stride, 1)):
+                units.append(BasicUnit(scheme, in_planes, planes, st, pk[f'layer{li}'][str(bi)], norm_type, blocks))
+                in_planes = planes
+            setattr(self, f'layer{li}', nn.Sequential(*units))
+        self.linear = nn.Linear(512, num_classes)
+
+    def _stages(self):
+        return (self.layer1, self.layer2, self.layer3, self.layer4)
+
+    def forward(self, x, force_passport=False, ind=0):
+        if isinstance(self.convbnrelu_1, nn.Sequential):
+            out = self.convbnrelu_1[1](_call(self.convbnrelu_1[0], x, force_passport, ind))
+        else:
+            out = _call(self.convbnrelu_1, x, force_passport, ind)
+        for stage in self._stages():
+            for unit in stage:
+                out = unit(out, force_passport, ind)
+        out = F.adaptive_avg_pool2d(out, (1, 1)).flatten(1)
+        return self.linear(out)
+
+    def set_intermediate_keys(self, pretrained_model, x, y=None):
+        """Push passport candidates through a (normal) pretrained net, handing each passport layer its input
+        activations as keys (reference resnet_passport_private.py:146-162)."""
+        with torch.no_grad():
+            stem = self.convbnrelu_1[0] if isinstance(self.convbnrelu_1, nn.Sequential) else self.convbnrelu_1
+            if _is_passport(stem):
+                stem.set_key(x, y)
+            x = pretrained_model.convbnrelu_1(x)
+            y = pretrained_model.convbnrelu_1(y) if y is not None else None
+            for mine, theirs in zip(self._stages(), pretrained_model._stages()):
+                for unit, pre in zip(mine, theirs):
+                    x, y = unit.set_intermediate_keys(pre, x, y)
+
+
+_ALEX_OUT = {0: 64, 2: 192, 4: 384, 5: 256, 6: 256}
+_ALEX_KP = {0: (5, 2), 2: (5, 2), 4: (3, 1), 5: (3, 1), 6: (3, 1)}
+
+
+class AlexNetCifar(nn.Module):
+    """CIFAR AlexNet (features idx 0..7, max-pool at 1,3,7, Linear(4096->classes)); scheme as above."""
+
+    def __init__(self, scheme='v1', in_channels=3, num_classes=10, passport_kwargs=None, norm_type='bn',
+                 blocks=_DEFAULT_BLOCKS):
+        super().__init__()
+        assert scheme in SCHEMES
+        self.scheme = scheme
+        if passport_kwargs is None or scheme == 'normal':
+            passport_kwargs = passport_kwargs_from_config(alexnet_passport_config(()), norm_type=norm_type)
+        layers, inp = [], in_channels
+        for idx in range(8):
+            if idx in (1, 3, 7):
+                layers.append(nn.MaxPool2d(2, 2))
+                continue
+            k, p = _ALEX_KP[idx]
+            layers.append(_make_block(blocks, scheme, passport_kwargs[str(idx)], inp, _ALEX_OUT[idx], k, 1, p, norm_type))
+            inp = _ALEX_OUT[idx]
+        self.features = nn.Sequential(*layers)
+        self.classifier = nn.Linear(4 * 4 * 256, num_classes)
+
+    def forward(self, x, force_passport=False, ind=0):
+        for m in self.features:
+            x = _call(m, x, force_passport, ind)
+        return self.classifier(x.reshape(x.size(0), -1))
+
+    def set_intermediate_keys(self, pretrained_model, x, y=None):
+        with torch.no_grad():
+            for theirs, mine in zip(pretrained_model.features, self.features):
+                if _is_passport(mine):
+                    mine.set_key(x, y)
+                x = theirs(x)
+                y = theirs(y) if y is not None else None

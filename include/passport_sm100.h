@@ -1,0 +1,154 @@
+/*
+ * passport_sm100.h — C ABI of libpassport_sm100.so (B200 / sm_100a only).
+ *
+ * This is the drop-in boundary for the passport-layer hot path of kamwoh/DeepIPR.
+ * The reference has no FFI of its own (it is pure PyTorch); each entry point below
+ * replaces a group of ATen/cuDNN calls made by the reference's nn.Modules and names
+ * the reference lines it stands in for.  The Python mirror of the reference's module
+ * surface (deepipr_b200/layers.py) binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the
+ *     caller unless stated otherwise; nothing is allocated or freed by the library;
+ *   - activations are NHWC bf16 ("channels_last"); weights enter as fp32 OIHW (the
+ *     layout of nn.Conv2d.weight) and are re-laid-out by pp_weight_prep();
+ *   - per-channel vectors (gamma, beta, statistics, gradients of them) are fp32;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry
+ *     point synchronises the device;
+ *   - return value 0 = success, negative = PPStatus; pp_last_error() returns a
+ *     thread-local message for the last non-zero return.
+ *   - there is NO CPU path: every compute entry point fails with PP_ENODEVICE when no
+ *     sm_100 device is present.
+ */
+#ifndef PASSPORT_SM100_H_
+#define PASSPORT_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 3
+
+typedef enum PPStatus {
+  PP_OK = 0,
+  PP_EBADSHAPE = -1,    /* inconsistent / unsupported dimensions            */
+  PP_EUNSUPPORTED = -2, /* valid request this build has no kernel for       */
+  PP_ELAUNCH = -3,      /* CUDA launch or driver error (message has detail) */
+  PP_EWORKSPACE = -4,   /* workspace pointer NULL or too small              */
+  PP_ENODEVICE = -5,    /* no CUDA device / not sm_100                      */
+  PP_EBADARG = -6       /* NULL where a pointer is required                 */
+} PPStatus;
+
+enum { PP_NORM_NONE = 0, PP_NORM_BN_TRAIN = 1, PP_NORM_BN_EVAL = 2 };
+enum { PP_ALGO_AUTO = 0, PP_ALGO_TCGEN05 = 1, PP_ALGO_SIMT = 2 };
+enum { PP_WS_FWD = 0, PP_WS_BWD = 1 };
+
+/* Geometry + mode of one conv block.  Mirrors the constructor arguments of the
+ * reference blocks: PassportBlock(i, o, ks, s, pd, ...) models/layers/passportconv2d.py:12-18,
+ * ConvBlock(i, o, ks, s, pd, bn, relu) models/layers/conv2d.py:6-9. */
+typedef struct PPConvDesc {
+  int32_t N, C, H, W; /* input activation, logical NCHW = [N,C,H,W], memory NHWC */
+  int32_t O;          /* output channels                                         */
+  int32_t kh, kw;     /* filter size                                             */
+  int32_t stride;     /* same in h and w (reference passes one int)              */
+  int32_t pad;        /* same in h and w                                         */
+  int32_t norm;       /* PP_NORM_*  (bn in train / eval mode, or no norm)        */
+  int32_t relu;       /* 1: ReLU after the affine                                */
+  int32_t z_f32;      /* 1: conv output z kept in fp32, 0: bf16                  */
+  float eps;          /* BatchNorm eps (1e-5)                                    */
+  float momentum;     /* BatchNorm momentum (0.1)                                */
+  int32_t algo;       /* PP_ALGO_*; AUTO picks tcgen05 when C%64==0 && O%64==0   */
+  int32_t reserved;
+} PPConvDesc;
+
+int pp_version(void);
+const char* pp_last_error(void);
+
+/* Number of SMs / compute capability of the current device (for tests & bench). */
+int pp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Bytes of scratch pp_conv_block_fwd (which=PP_WS_FWD) / _bwd (PP_WS_BWD) need. */
+int pp_workspace_bytes(const PPConvDesc* d, int which, size_t* bytes);
+
+/* fp32 OIHW master weight -> bf16 operand copies.
+ *   w_fprop: [O, kh, kw, C]           (K-major B operand of the forward implicit GEMM)
+ *   w_dgrad: [C, kh, kw, O] flipped   (B operand of the data-gradient GEMM; may be NULL)
+ * Replaces the implicit weight read of nn.Conv2d (passportconv2d.py:18,218). */
+int pp_weight_prep(const PPConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream);
+
+/* S[t*C + c] = mean over key batch and output positions of the (zero padded) key patch
+ * element (tap t, channel c), key rounded to bf16, accumulated in fp64.
+ * With it  GAP(conv(W, key)) == W[O, kh*kw*C] @ S  (SURVEY 7.3), which replaces the two
+ * batch-1 cuDNN convs + means of get_scale / get_bias (passportconv2d.py:146-152,167-173).
+ * key_nchw: fp32 [Bk, C, H, W] exactly as the module's `key` / `skey` buffers store it. */
+int pp_key_pool(const PPConvDesc* d, int Bk, const float* key_nchw, double* S, void* stream);
+
+/* gamma = Wf @ S_skey, beta = Wf @ S_key (fp64 accumulate, fp32 out), plus
+ * SignLoss.add (models/losses/sign_loss.py:25-28,32-54):
+ *   sign_loss = alpha * sum(relu(0.1 - b*gamma)) + 1e-5 * sum(gamma^2)
+ *   sign_acc  = mean(sign(b) == sign(gamma))
+ * b_sign may be NULL (then sign_loss/sign_acc are not written). */
+int pp_passport_affine_fwd(const PPConvDesc* d, const void* w_fprop, const double* S_skey,
+                           const double* S_key, const float* b_sign, float alpha, float* gamma,
+                           float* beta, float* sign_loss, float* sign_acc, void* stream);
+
+/* Gradient of the above w.r.t. the fp32 OIHW weight (rank-1 update):
+ *   dW[o,c,r,s] = (g_gamma[o] + g_loss * dLsign/dgamma[o]) * S_skey[(r,s),c] + g_beta[o] * S_key[(r,s),c]
+ * g_gamma / g_beta / g_loss may each be NULL (treated as 0); g_loss is a device scalar.
+ * accumulate != 0 adds into dw_oihw instead of overwriting it. */
+int pp_passport_affine_bwd(const PPConvDesc* d, const double* S_skey, const double* S_key,
+                           const float* gamma, const float* b_sign, float alpha,
+                           const float* g_gamma, const float* g_beta, const float* g_loss,
+                           float* dw_oihw, int accumulate, void* stream);
+
+/* Stand-alone SignLoss.add on an arbitrary scale vector (sign_loss.py:18-54). */
+int pp_sign_loss_fwd(int O, const float* gamma, const float* b_sign, float alpha, float* sign_loss,
+                     float* sign_acc, void* stream);
+int pp_sign_loss_bwd(int O, const float* gamma, const float* b_sign, float alpha, const float* g_loss,
+                     float* g_gamma, void* stream);
+
+/* y = relu?( gamma * norm(conv(x, W)) + beta )   — PassportBlock.forward
+ * (passportconv2d.py:218-222), PassportPrivateBlock.forward (passportconv2d_private.py:215-218)
+ * and ConvBlock.forward (conv2d.py:29-36, gamma/beta = BatchNorm affine).
+ *   x        bf16 [N,H,W,C]          w_fprop   bf16 [O,kh,kw,C]
+ *   gamma/beta fp32 [O]              running_* fp32 [O]  (updated in BN_TRAIN, read in BN_EVAL, may be NULL for NONE)
+ *   z        conv output [N,P,Q,O] (bf16 or fp32 per d->z_f32); NULL => not kept (inference;
+ *            then norm must not be BN_TRAIN and the affine is fused into the conv epilogue)
+ *   y        bf16 [N,P,Q,O]
+ *   save_mean / save_invstd fp32 [O]: statistics the backward needs (batch stats, running
+ *            stats, or 0/1 for NONE). */
+int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var, void* z, void* y,
+                      float* save_mean, float* save_invstd, void* workspace, size_t ws_bytes,
+                      void* stream);
+
+/* Backward of pp_conv_block_fwd (autograd of the same reference lines).
+ *   dy bf16 [N,P,Q,O];  dx bf16 [N,H,W,C] or NULL;  dw_oihw fp32 [O,C,kh,kw] or NULL
+ *   dgamma / dbeta fp32 [O] (always written). */
+int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad,
+                      const void* z, const float* gamma, const float* beta, const float* save_mean,
+                      const float* save_invstd, void* dx, float* dw_oihw, float* dgamma,
+                      float* dbeta, void* workspace, size_t ws_bytes, void* stream);
+
+/* Building blocks exposed for tests / profiling (same kernels the two calls above use). */
+int pp_conv_fwd_raw(const PPConvDesc* d, const void* x, const void* w_fprop, void* z, void* workspace,
+                    size_t ws_bytes, void* stream); /* z = conv(x,W), dtype per z_f32 */
+int pp_conv_dgrad(const PPConvDesc* d, const void* dz, const void* w_dgrad, void* dx, void* stream);
+int pp_conv_wgrad(const PPConvDesc* d, const void* dz, const void* x, float* dw_oihw, void* workspace,
+                  size_t ws_bytes, void* stream);
+
+/* Fused SGD(momentum, weight decay) step on one flat fp32 buffer (classification.py:47-50):
+ *   g' = g + wd*p;  buf = mom*buf + g' (buf = g' on the first step);  p -= lr*buf */
+int pp_sgd_step(size_t n, float* param, const float* grad, float* momentum_buf, float lr, float momentum,
+                float weight_decay, int first_step, void* stream);
+
+/* Debug: after a kernel-side pipeline timeout the offending barrier id is recorded here. */
+int pp_debug_last_timeout(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PASSPORT_SM100_H_ */
