@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the passport-layer training path (contract: see the task brief / DESIGN.md "Measurement").
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1        # CPU arm: the oracle port of the reference trainer
+
+Workload: one TrainerPrivate-style optimisation step (public + private forward, one backward, SGD) of ResNet-18 with
+passport layers in layer4 (passport_configs/resnet18_passport.json) on synthetic CIFAR-10-shaped tensors, bf16
+activations, per-GPU batch 1024 (weak scaling).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec ResNet18-passport CIFAR10 train"
+UNIT = "images/s"
+WORKLOAD = "ResNet18 V2 private-passport (layer4 x5 passport convs) CIFAR10-shaped TrainerPrivate step"
+PER_GPU_BATCH = 1024
+CPU_BATCH = 64                     # reference default batch (train_v1.py:15); bounded CPU sample
+GFLOP_PER_IMAGE_STEP = 6.665       # 2 forwards, 3x fwd FLOPs each
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", 1409.4), hbm=d.get("hbm_gbs", 6437.3), src="measured")
+    return dict(tflops=1590.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(num_classes=10, seed=0, blocks=None):
+    import contextlib
+    import io
+    import random
+    import numpy as np
+    import torch
+    from deepipr_b200 import nets
+    torch.manual_seed(seed); random.seed(seed); np.random.seed(seed)
+    pk = nets.passport_kwargs_from_config(nets.resnet18_passport_config(), "bn", "random", 0.1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = nets.ResNet18("private", num_classes, pk)
+    # fixed passports (key_type='random' semantics: U(-1,1), passportconv2d.py:198-207), set up front so the
+    # lazily-created-key branch is not part of the timed region
+    for m in model.modules():
+        if getattr(m, "KIND", None) == "private":
+            c = m.conv.in_channels
+            h = 8 if m.conv.stride[0] == 2 else 4
+            m.set_key(torch.tensor(np.random.uniform(-1, 1, (1, c, h, h)), dtype=torch.float32),
+                      torch.tensor(np.random.uniform(-1, 1, (1, c, h, h)), dtype=torch.float32))
+    return model
+
+
+def cpu_reference_run(steps, warmup, batch=CPU_BATCH):
+    """The reference's CPU trainer for this path, as restated by the oracle (oracle/passport_oracle.py):
+    TrainerPrivate.train step on the box's host cores, all threads."""
+    import torch
+    from oracle import passport_oracle as po
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = po.mirror(build_model(), round_bf16=False).train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, 3, 32, 32, generator=g)
+    t = torch.randint(0, 10, (batch,), generator=g)
+    for _ in range(warmup):
+        po.train_step(model, opt, x, t, private=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        po.train_step(model, opt, x, t, private=True)
+    dt = time.perf_counter() - t0
+    return dict(value=steps * batch / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"{steps} TrainerPrivate steps at batch {batch} (reference default), fp32, "
+                       f"{warmup} warm-up, oracle port of experiments/trainer_private.py:148-177"), dt / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1),
+              "parallelism": f"dp{max(world, 1)}", "passport_layers": "layer4 (5 convs)", "norm": "bn",
+              "optimizer": "SGD(0.01, momentum 0.9, wd 1e-4), fused flat step",
+              "l2": "per-step working set (~6 GB of activations at batch 1024) >> 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 5))
+        cb, sec_per_step = cpu_reference_run(steps, max(1, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": steps, "warmup": 1, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config, per_gpu_batch=CPU_BATCH, global_batch=CPU_BATCH, parallelism="cpu"),
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from deepipr_b200 import _lib as L
+    from deepipr_b200.parallel import FlatParams, FlatSGD, GradBuckets, broadcast_state
+    from deepipr_b200.trainer import StepRunner, accuracy, test_signature
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+
+    model = build_model().to(dev).train()
+    broadcast_state(model)
+    flat = FlatParams(model.parameters())
+    opt = FlatSGD(flat, lr=0.01, momentum=0.9, weight_decay=1e-4)
+    buckets = GradBuckets(flat) if world > 1 else None
+    runner = StepRunner(model, opt, private=True, buckets=buckets, autocast=True)
+
+    B = args.batch
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    dev_batches = [(torch.randn(B, 3, 32, 32, device=dev, generator=g),
+                    torch.randint(0, 10, (B,), device=dev, generator=g)) for _ in range(4)]
+    host_batches = [(x.cpu().pin_memory(), t.cpu().pin_memory()) for x, t in dev_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    # ---------------- leg 1: inputs resident in HBM
+    for i in range(args.warmup):
+        runner.step(*dev_batches[i % 4])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.pp_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        runner.step(*dev_batches[i % 4])
+    e1.record()
+    barrier()
+    launches = int(lib.pp_launch_count(0))
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = args.steps * B * world / (ms_total * 1e-3)
+
+    # ---------------- leg 2: end to end through the public step API with host (pinned) buffers
+    def e2e_step(i):
+        x, t = host_batches[i % 4]
+        xd = x.to(dev, non_blocking=True)
+        td = t.to(dev, non_blocking=True)
+        loss, sign_loss, preds = runner.step(xd, td)
+        # the reference loop's host reads: two accuracies + loss + sign loss (trainer_private.py:163-177)
+        return (accuracy(preds[0], td)[0].item(), accuracy(preds[1], td)[0].item(), sign_loss.item(), loss.item())
+
+    for i in range(max(3, args.warmup // 2)):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        last = e2e_step(i)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = args.steps * B * world / (ms_e2e * 1e-3)
+    h2d = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 8
+    d2h = 4 * 4
+
+    # ---------------- leg 3: per-kernel roofline of the dominant kernel (CUDA events on its stream)
+    roof = None
+    roof_w = None
+    if rank == 0:
+        pk = peaks()
+        lib.pp_profile_enable(1)
+        for i in range(3):
+            runner.step(*dev_batches[i % 4])
+        torch.cuda.synchronize()
+        lib.pp_profile_enable(0)
+        out = []
+        for kind in (0, 1):
+            ms, fl, n = C.c_double(0), C.c_double(0), C.c_int(0)
+            lib.pp_profile_read(kind, C.byref(ms), C.byref(fl), C.byref(n))
+            out.append((ms.value, fl.value, n.value))
+        (ms0, fl0, n0), (ms1, fl1, n1) = out
+        if ms0 > 0:
+            ach = fl0 / (ms0 * 1e-3) / 1e12
+            roof = {"kernel": "tapgemm_kernel (tcgen05 implicit-GEMM conv fprop+dgrad)", "bound": "tensor",
+                    "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                    "peak_source": pk["src"] + " bf16 sustained", "traffic": None,
+                    "launches_per_step": n0 // 3, "avg_launch_us": ms0 * 1e3 / max(n0, 1),
+                    "share_of_step": (ms0 / 3) / (ms_total / args.steps)}
+        if ms1 > 0:
+            ach = fl1 / (ms1 * 1e-3) / 1e12
+            roof_w = {"kernel": "wgrad_kernel (tcgen05, MN-major)", "bound": "tensor", "achieved": ach,
+                      "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                      "launches_per_step": n1 // 3, "avg_launch_us": ms1 * 1e3 / max(n1, 1),
+                      "share_of_step": (ms1 / 3) / (ms_total / args.steps)}
+
+    sig = test_signature(model) if rank == 0 else {}
+    model.train()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_run(args.cpu_steps, 1)
+
+    if rank == 0:
+        pk = peaks()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches,
+                "roofline": roof, "roofline_wgrad": roof_w,
+                "conv_roofline_frac_whole_step": (value / world) * GFLOP_PER_IMAGE_STEP * 1e9 / (pk["tflops"] * 1e12),
+                "cpu_baseline": cpu_baseline,
+                "sign_bit_accuracy": (sum(sig.values()) / len(sig)) if sig else None,
+                "last_step": {"acc_public": last[0], "acc_private": last[1], "sign_loss": last[2], "loss": last[3]}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -2,6 +2,10 @@
 // argument checking, geometry planning (conv -> tap-GEMM instances) and kernel sequencing.
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.h"
 
 namespace pp {
@@ -18,6 +22,31 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 static int g_sm_count = -1, g_cc_major = -1, g_cc_minor = -1;
+
+// ---------------------------------------------------------------- launch counter + kernel profiling
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { cudaEvent_t start, stop; double flops; };
+static bool g_prof_on = false;
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof[PROF_KINDS];
+
+void prof_begin(int kind, double flops, cudaStream_t s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.flops = flops;
+  cudaEventCreate(&r.start);
+  cudaEventCreate(&r.stop);
+  cudaEventRecord(r.start, s);
+  g_prof[kind].push_back(r);
+}
+void prof_end(int kind, cudaStream_t s) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof[kind].empty()) cudaEventRecord(g_prof[kind].back().stop, s);
+}
 
 static int query_device() {
   if (g_sm_count >= 0) return PP_OK;
@@ -434,5 +463,38 @@ int pp_sgd_step(size_t n, float* param, const float* grad, float* momentum_buf, 
 }
 
 int pp_debug_last_timeout(void) { return debug_last_timeout(); }
+
+long long pp_launch_count(int reset) {
+  const long long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
+
+int pp_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return PP_OK;
+}
+
+int pp_profile_read(int kind, double* total_ms, double* total_flops, int* launches) {
+  PP_REQUIRE(kind >= 0 && kind < PROF_KINDS, PP_EBADARG, "unknown profile kind %d", kind);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double ms = 0.0, fl = 0.0;
+  int n = 0;
+  for (auto& r : g_prof[kind]) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&t, r.start, r.stop) == cudaSuccess) {
+      ms += t; fl += r.flops; ++n;
+    }
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  g_prof[kind].clear();
+  cudaGetLastError();
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = n;
+  return PP_OK;
+}
 
 }  // extern "C"

@@ -23,6 +23,13 @@ const char* get_error();
     }                                                                                           \
   } while (0)
 
+// after every kernel launch: count it (pp_launch_count) and surface launch errors
+#define PP_POST_LAUNCH()                  \
+  do {                                    \
+    pp::count_launch();                   \
+    PP_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
+
 #define PP_REQUIRE(cond, code, ...)  \
   do {                               \
     if (!(cond)) {                   \
@@ -71,6 +78,12 @@ struct TapEpilogue {
   int relu;
   float* stats_partial;  // NULL or [tapgemm_tcgen05_grid()][2][Nout]: per-CTA sum z, sum z^2 (fp32 accumulators)
 };
+
+void count_launch();
+// optional per-kernel CUDA-event timing of the two tensor-core kernels (bench.py roofline leg)
+enum { PROF_TAPGEMM = 0, PROF_WGRAD = 1, PROF_KINDS = 2 };
+void prof_begin(int kind, double flops, cudaStream_t s);
+void prof_end(int kind, cudaStream_t s);
 
 int device_sm_count();
 int check_device();  // PP_OK iff current device is sm_100

@@ -90,7 +90,7 @@ int tapgemm_simt(const TapGemm& g, const void* act, const void* B, const TapEpil
   } else {
     tapgemm_simt_kernel<false><<<(int)blocks, 256, 0, s>>>(p, (const __nv_bfloat16*)act, (const __nv_bfloat16*)B);
   }
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -148,7 +148,7 @@ int wgrad_simt(const TapGemm& g, const void* x, const void* dz, int O, float* pa
   dim3 grid(bx, splits);
   wgrad_simt_kernel<<<grid, 128, 0, s>>>(p, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, O, partial,
                                         pixels_per_split);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 

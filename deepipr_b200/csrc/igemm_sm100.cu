@@ -448,8 +448,10 @@ static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, cons
   PP_REQUIRE(e.stats_partial == nullptr || g.Nout <= kMaxStatsN, PP_EUNSUPPORTED,
              "fused column statistics support Nout <= %d (Nout=%d)", kMaxStatsN, g.Nout);
   const int grid = tapgemm_tcgen05_grid(g);
+  prof_begin(PROF_TAPGEMM, 2.0 * (double)p.M * g.Nout * g.ntaps * g.C, s);
   tapgemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, p);
-  PP_CHECK_CUDA(cudaGetLastError());
+  prof_end(PROF_TAPGEMM, s);
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -671,8 +673,10 @@ static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, 
     attr_set = true;
   }
   dim3 grid(p.c_tiles * p.o_tiles * g.ntaps, splits);
+  prof_begin(PROF_WGRAD, 2.0 * (double)M * O * g.ntaps * g.C, s);
   wgrad_kernel<BNW><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmDz, tmX, p);
-  PP_CHECK_CUDA(cudaGetLastError());
+  prof_end(PROF_WGRAD, s);
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 

@@ -36,7 +36,7 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
 int launch_weight_prep(const PPConvDesc& d, const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s) {
   const size_t total = (size_t)d.O * d.C * d.kh * d.kw;
   weight_prep_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(w, wf, wd, d.O, d.C, d.kh * d.kw);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -72,7 +72,7 @@ int launch_key_pool(const PPConvDesc& d, int Bk, const float* key, double* S, cu
   const int Q = (d.W + 2 * d.pad - d.kw) / d.stride + 1;
   const int total = d.kh * d.kw * d.C;
   key_pool_kernel<<<(total + 127) / 128, 128, 0, s>>>(key, S, Bk, d.C, d.H, d.W, d.kh, d.kw, d.stride, d.pad, P, Q);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -137,7 +137,7 @@ __global__ void sign_loss_kernel(const float* __restrict__ gamma, const float* _
 int launch_sign_loss_fwd(int O, const float* gamma, const float* b, float alpha, float* loss, float* acc,
                          cudaStream_t s) {
   sign_loss_kernel<<<1, 256, 0, s>>>(gamma, b, alpha, loss, acc, O);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -158,7 +158,7 @@ __global__ void sign_loss_bwd_kernel(const float* __restrict__ gamma, const floa
 int launch_sign_loss_bwd(int O, const float* gamma, const float* b, float alpha, const float* gl, float* gg,
                          cudaStream_t s) {
   sign_loss_bwd_kernel<<<(O + 127) / 128, 128, 0, s>>>(gamma, b, alpha, gl, gg, O);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -169,7 +169,7 @@ int launch_passport_affine_fwd(const PPConvDesc& d, const __nv_bfloat16* wf, con
   const int warps_per_block = 8;
   passport_gemv_kernel<<<(d.O + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
       wf, Ss, Sk, gamma, beta, d.O, K);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   if (b && (loss || acc)) PP_TRY(launch_sign_loss_fwd(d.O, gamma, b, alpha, loss, acc, s));
   return PP_OK;
 }
@@ -200,7 +200,7 @@ int launch_passport_affine_bwd(const PPConvDesc& d, const double* Ss, const doub
   const size_t total = (size_t)d.O * d.C * d.kh * d.kw;
   passport_affine_bwd_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(Ss, Sk, gamma, b, alpha, gg, gb, gl, dw,
                                                                          accumulate, d.O, d.C, d.kh * d.kw);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -250,7 +250,7 @@ int launch_bn_finalize(const PPConvDesc& d, int n, const float* partial, int num
                        float* cb, cudaStream_t s) {
   bn_finalize_kernel<<<(d.O + 63) / 64, 64, 0, s>>>(d.norm, n, partial, num, gamma, beta, rmean, rvar, d.eps,
                                                    d.momentum, save_mean, save_invstd, ca, cb, d.O);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -268,7 +268,7 @@ __global__ void affine_coef_kernel(const float* __restrict__ gamma, const float*
 int launch_affine_coef(int O, const float* gamma, const float* beta, const float* mean, const float* invstd,
                        float* ca, float* cb, cudaStream_t s) {
   affine_coef_kernel<<<(O + 63) / 64, 64, 0, s>>>(gamma, beta, mean, invstd, ca, cb, O);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -333,7 +333,7 @@ int launch_affine_apply(const void* z, int z_f32, size_t rows, int O, const floa
   PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "affine pass needs O%%8==0 (O=%d)", O);
   const size_t nvec = rows * (size_t)(O / 8);
   affine_apply_kernel<<<grid_for(nvec, 256, 148 * 8), 256, 0, s>>>(z, z_f32, nvec, O, a, b, relu, y);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -427,7 +427,7 @@ static int column_reduce_launch(int mode, const __nv_bfloat16* dy, const void* z
     }
     column_reduce_kernel<1><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, relu, partial);
   }
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   *num_partials = (int)blocks;
   return PP_OK;
 }
@@ -484,7 +484,7 @@ int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int 
                     float* k2, float* k3, cudaStream_t s) {
   bwd_coef_kernel<<<(d.O + 63) / 64, 64, 0, s>>>(d.norm, (double)rows, partial, num_partials, gamma, save_mean,
                                                 save_invstd, dgamma, dbeta, k1, k2, k3, d.O);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -519,7 +519,7 @@ int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows
   PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "dz pass needs O%%8==0 (O=%d)", O);
   const size_t nvec = rows * (size_t)(O / 8);
   bwd_dz_kernel<<<grid_for(nvec, 256, 148 * 8), 256, 0, s>>>(dy, z, z_f32, nvec, O, a, b, relu, k1, k2, k3, dz);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -556,7 +556,7 @@ int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits,
     attr = true;
   }
   wgrad_finalize_kernel<<<d.O, 256, smem, s>>>(partial, splits, dw_oihw, d.O, d.C, T);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 
@@ -581,7 +581,7 @@ __global__ void sgd_kernel(size_t n, float* __restrict__ p, const float* __restr
 int launch_sgd(size_t n, float* p, const float* g, float* buf, float lr, float mom, float wd, int first,
                cudaStream_t s) {
   sgd_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(n, p, g, buf, lr, mom, wd, first);
-  PP_CHECK_CUDA(cudaGetLastError());
+  PP_POST_LAUNCH();
   return PP_OK;
 }
 

@@ -45,6 +45,18 @@ _ws_bytes_cache = {}
 _workspace = {}
 #: PP_ALGO_* used by every call; tests flip it to compare the tensor-core path with the SIMT path
 ALGO = L.PP_ALGO_AUTO
+#: bumped whenever parameters are rewritten behind autograd's back (FlatSGD / FlatParams), so that cached bf16
+#: weight operands keyed on Tensor._version are refreshed
+_weight_epoch = 0
+
+
+def bump_weight_epoch():
+    global _weight_epoch
+    _weight_epoch += 1
+
+
+def weight_epoch():
+    return _weight_epoch
 
 
 def make_desc(spec: ConvSpec, N, H, W, norm=L.PP_NORM_NONE, relu=0, z_f32=0, eps=1e-5, momentum=0.1, algo=None):
@@ -90,6 +102,7 @@ class PreparedWeight:
     wd: Optional[torch.Tensor]       # bf16 [C, kh, kw, O] or None
     version: int = -1
     data_ptr: int = 0
+    epoch: int = -1
 
 
 def prepare_weight(weight: torch.Tensor, spec: ConvSpec, need_dgrad: bool) -> PreparedWeight:
@@ -102,7 +115,7 @@ def prepare_weight(weight: torch.Tensor, spec: ConvSpec, need_dgrad: bool) -> Pr
     wd = torch.empty((spec.C, spec.kh, spec.kw, spec.O), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
     d, _ = make_desc(spec, 1, max(spec.kh, 1), max(spec.kw, 1))
     L.check(L.load().pp_weight_prep(C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), _stream()), "pp_weight_prep")
-    return PreparedWeight(wf, wd, weight._version, weight.data_ptr())
+    return PreparedWeight(wf, wd, weight._version, weight.data_ptr(), _weight_epoch)
 
 
 def key_pool(key: torch.Tensor, spec: ConvSpec) -> torch.Tensor:

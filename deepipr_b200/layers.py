@@ -85,6 +85,10 @@ def _norm_mode(bn_module):
 class _FusedConvMixin:
     """Weight-operand cache + dispatch shared by the three block types."""
 
+    #: keep the conv output z (saved for backward, re-read by the affine pass) in fp32.  bf16 halves that
+    #: traffic but adds a second rounding in front of the bf16 output (DESIGN.md "Precision").
+    z_f32 = True
+
     def _spec(self):
         conv = self.conv
         return F_.ConvSpec(C=conv.in_channels, O=conv.out_channels, kh=conv.kernel_size[0], kw=conv.kernel_size[1],
@@ -106,7 +110,8 @@ class _FusedConvMixin:
         cached = self.__dict__.get('_pp_prepared')
         # In no-grad mode (evaluation / attack scripts that edit weight.data) always refresh: it is one tiny kernel.
         if (cached is not None and torch.is_grad_enabled() and cached.version == w._version
-                and cached.data_ptr == w.data_ptr() and cached.wf.device == w.device):
+                and cached.data_ptr == w.data_ptr() and cached.epoch == F_.weight_epoch()
+                and cached.wf.device == w.device):
             return cached
         prepared = F_.prepare_weight(w, self._spec(), need_dgrad=True)
         self.__dict__['_pp_prepared'] = prepared
@@ -167,7 +172,7 @@ class ConvBlock(nn.Module, _FusedConvMixin):
             gamma, beta = None, self.conv.bias
         else:
             gamma, beta = self.bn.weight, self.bn.bias
-        o = self._bn_opts(norm, self.relu is not None, False, x)
+        o = self._bn_opts(norm, self.relu is not None, self.z_f32, x)
         return F_.conv_block(x, self.conv.weight, gamma, beta, prepared, o)
 
 
@@ -328,7 +333,7 @@ class _PassportBase(nn.Module, _FusedConvMixin):
             y = self.bn(y)
             y = gamma.view(1, -1, 1, 1).to(y.dtype) * y + beta.view(1, -1, 1, 1).to(y.dtype)
             return torch.relu_(y) if relu else y
-        o = self._bn_opts(norm, relu, True, x)   # passport layers keep z in fp32 (precision)
+        o = self._bn_opts(norm, relu, self.z_f32, x)
         return F_.conv_block(x, self.weight, gamma, beta, prepared, o)
 
     def _load_placeholders(self, state_dict, prefix):

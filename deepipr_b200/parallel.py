@@ -1,0 +1,191 @@
+"""Data-parallel plumbing for the passport training loop: one process per GPU, gradients all-reduced over
+NCCL (NVLink 5 / NVSwitch) on flat fp32 buckets only — no activation or buffer traffic per step.
+
+The reference's only multi-GPU mechanism is nn.DataParallel (experiments/trainer.py:92-93,
+experiments/trainer_private.py:110-111), which replicates the module every forward and silently drops the
+SignLoss of the replicas.  Here every rank owns a full replica; the passport-derived
+gamma/beta and the sign loss depend on the weights and keys only, so they are computed redundantly and
+identically on every rank and their gradient survives the averaging unchanged.  BatchNorm statistics stay
+per-rank (what DataParallel does too).
+
+  FlatParams      parameters and gradients re-homed as views of two flat fp32 buffers
+  GradBuckets     bucketed (size-bounded, reverse order) asynchronous all-reduce launched from
+                  post-accumulate-grad hooks so communication overlaps the rest of backward
+  FlatSGD         torch.optim.Optimizer whose step is ONE pp_sgd_step launch per param group on the flat buffers
+                  (momentum, weight decay: experiments/classification.py:47-50)
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import functional as F_
+
+
+class FlatParams:
+    """Re-home `params` (fp32, same device) into one flat buffer; same for their gradients."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        seen, uniq = set(), []
+        for p in self.params:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.params = uniq
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        if any(p.device != dev or p.dtype != dt for p in self.params):
+            raise ValueError("FlatParams needs all parameters on one device with one dtype")
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 63) // 64 * 64          # keep every view 256-byte aligned
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=dt, device=dev)
+        self.flat_grad = torch.zeros(off, dtype=dt, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                view = self.flat[o:o + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+        F_.bump_weight_epoch()
+
+    def grad_view(self, i):
+        p, o = self.params[i], self.offsets[i]
+        return self.flat_grad[o:o + p.numel()].view_as(p)
+
+    def ensure_grad_views(self):
+        """After an external zero_grad(set_to_none=True) the views are gone: restore them (copying any grad in)."""
+        for i, p in enumerate(self.params):
+            view = self.grad_view(i)
+            if p.grad is None:
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        self.ensure_grad_views()
+
+
+class GradBuckets:
+    """Size-bounded buckets over FlatParams.flat_grad, all-reduced (mean) asynchronously as they fill."""
+
+    def __init__(self, flat: FlatParams, bucket_bytes=25 << 20, process_group=None, overlap=True):
+        self.flat = flat
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.overlap = overlap
+        # buckets in reverse parameter order (gradients become ready roughly back to front)
+        self.buckets = []            # (start, end) element ranges of flat_grad
+        self.bucket_of = [0] * len(flat.params)
+        cur_end = flat.numel
+        cur_start = cur_end
+        members = []
+        elem_bytes = flat.flat_grad.element_size()
+        for i in reversed(range(len(flat.params))):
+            start = flat.offsets[i]
+            if members and (cur_end - start) * elem_bytes > bucket_bytes:
+                self._close(cur_start, cur_end, members)
+                cur_end, members = cur_start, []
+            cur_start = start
+            members.append(i)
+        if members:
+            self._close(cur_start, cur_end, members)
+        self._pending = [len(m) for (_, _, m) in self.buckets]
+        self._works = []
+        self._hooks = []
+        if overlap and self.world > 1:
+            for i, p in enumerate(flat.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+
+    def _close(self, start, end, members):
+        idx = len(self.buckets)
+        for i in members:
+            self.bucket_of[i] = idx
+        self.buckets.append((start, end, list(members)))
+
+    def _make_hook(self, i):
+        def hook(p):
+            view = self.flat.grad_view(i)
+            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+            b = self.bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        start, end, _ = self.buckets[b]
+        chunk = self.flat.flat_grad[start:end]
+        if self.world > 1:
+            chunk.div_(self.world)   # pre-scale: SUM of pre-divided grads == mean (gloo has no AVG)
+            self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Call after backward(): reduce whatever the hooks have not launched yet and wait for everything."""
+        if self.world > 1:
+            self.flat.ensure_grad_views()
+            for b, pending in enumerate(self._pending):
+                if pending != 0 or not self.overlap:
+                    if not (self.overlap and pending == 0):
+                        self._launch(b)
+            for w in self._works:
+                w.wait()
+        self._works = []
+        self._pending = [len(m) for (_, _, m) in self.buckets]
+
+    def remove_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def broadcast_state(module, src=0, group=None):
+    """Make every rank start from rank `src`'s parameters and buffers (keys, signatures, BN statistics)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + [b for b in module.buffers() if b is not None]:
+            dist.broadcast(t, src=src, group=group)
+    for m in module.modules():
+        if hasattr(m, 'invalidate_cache'):
+            m.invalidate_cache()
+
+
+class FlatSGD(torch.optim.Optimizer):
+    """SGD(momentum, weight_decay) over FlatParams: one fused kernel launch per step (pp_sgd_step)."""
+
+    def __init__(self, flat: FlatParams, lr=0.01, momentum=0.9, weight_decay=1e-4):
+        self.flat = flat
+        defaults = dict(lr=lr, momentum=momentum, weight_decay=weight_decay)
+        super().__init__(flat.params, defaults)
+        self._buf = torch.zeros_like(flat.flat)
+        self._steps = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        F_.require_cuda(self.flat.flat, "FlatSGD parameters")
+        self.flat.ensure_grad_views()
+        g = self.param_groups[0]
+        L.check(L.load().pp_sgd_step(
+            C.c_size_t(self.flat.numel), L.ptr(self.flat.flat), L.ptr(self.flat.flat_grad), L.ptr(self._buf),
+            float(g['lr']), float(g['momentum']), float(g['weight_decay']), int(self._steps == 0),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pp_sgd_step")
+        self._steps += 1
+        F_.bump_weight_epoch()   # parameters changed behind autograd's back: invalidate bf16 operand caches
+        return loss

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 3
+#define PP_ABI_VERSION 4
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -147,6 +147,15 @@ int pp_sgd_step(size_t n, float* param, const float* grad, float* momentum_buf, 
 
 /* Debug: after a kernel-side pipeline timeout the offending barrier id is recorded here. */
 int pp_debug_last_timeout(void);
+
+/* Instrumentation used by bench.py.
+ *   pp_launch_count   kernels launched by this library since the last reset (the "gpu_launches" claim)
+ *   pp_profile_*      when enabled, every tensor-core kernel launch is bracketed by CUDA events on its stream;
+ *                     pp_profile_read(kind) sums durations and algorithmic FLOPs (kind 0: implicit-GEMM
+ *                     conv / dgrad kernel, kind 1: weight-gradient kernel) and clears the records. */
+long long pp_launch_count(int reset);
+int pp_profile_enable(int on);
+int pp_profile_read(int kind, double* total_ms, double* total_flops, int* launches);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,365 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden vectors and with the CPU oracle.
+
+Tolerances (DESIGN.md "Precision and parity"):
+  ACT_TOL   1e-3  rel-L2 on bf16 activations: the block output, compared on the bf16 grid with the oracle's /
+                  the reference's fp32 output rounded to bf16 (north_star: "within 1e-3 relative on bf16
+                  activations/logits"); the unrounded distance is bounded by the bf16 rounding floor (1.7e-3)
+  VEC_TOL   1e-5  gamma, beta, sign loss, BN statistics (fp32/fp64 arithmetic on both sides)
+  GRAD_TOL  4e-3  gradients: dz and dx are bf16 tensors (operands of the tensor-core GEMMs), one bf16 rounding
+                  each on top of fp32 accumulation
+  sign(gamma) must be bit-exact.
+"""
+import pytest
+import torch
+
+from deepipr_b200 import _lib as L
+from deepipr_b200 import functional as F_
+from deepipr_b200 import layers, nets
+from oracle import passport_oracle as po
+from tests.helpers import (BLOCK_FIXTURES, bf16r, load_golden, product_block_from_fixture, quiet, rel_l2, run_block,
+                           seed_all)
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL, VEC_TOL, GRAD_TOL = 1e-3, 1e-5, 4e-3
+
+
+def _grad(out, key):
+    g = out["grads"].get(key)
+    if g is None and key == "weight":
+        g = out["grads"].get("conv.weight")
+    if g is None and key == "conv.weight":
+        g = out["grads"].get("weight")
+    return g
+
+
+@pytest.mark.parametrize("name", BLOCK_FIXTURES)
+def test_block_matches_reference_golden(name):
+    g = load_golden(name)
+    m = product_block_from_fixture(g).cuda()
+    out = run_block(m, g, "cuda")
+    gn = "gn" in name  # GroupNorm runs as a torch module on the bf16 conv output: one more rounding
+    for k, y in enumerate(g["y"]):
+        assert rel_l2(out["y"][k], bf16r(y)) < (3e-3 if gn else ACT_TOL), f"y[{k}]"
+        assert rel_l2(out["y"][k], y) < 4e-3
+    assert abs(float(out["sign_loss"]) - float(g["sign_loss"])) <= VEC_TOL * max(1.0, abs(float(g["sign_loss"])))
+    assert abs(float(out["sign_acc"]) - float(g["sign_acc"])) < 1e-6
+    assert rel_l2(out["dx"], g["dx"]) < (6e-3 if gn else GRAD_TOL)
+    for key, ref in g["grads"].items():
+        mine = _grad(out, key)
+        assert mine is not None, key
+        assert rel_l2(mine, ref) < (6e-3 if gn else GRAD_TOL), key
+    sd = m.state_dict()
+    for key, ref in g["state_after"].items():
+        if ref.dtype.is_floating_point:
+            assert rel_l2(sd[key].cpu(), ref) < VEC_TOL, key
+        else:
+            assert torch.equal(sd[key].cpu(), ref), key
+    if "gamma" in g:
+        m.eval()
+        with torch.no_grad():
+            if g["cfg"]["kind"] == "private":
+                gamma, beta = m.get_scale(ind=1).reshape(-1).cpu(), m.get_bias(ind=1).reshape(-1).cpu()
+            else:
+                gamma, beta = m.get_scale(True).reshape(-1).cpu(), m.get_bias(True).reshape(-1).cpu()
+        assert rel_l2(gamma, g["gamma"]) < VEC_TOL and rel_l2(beta, g["beta"]) < VEC_TOL
+        assert torch.equal(torch.sign(gamma), torch.sign(g["gamma"])), "signature bits differ from the reference"
+
+
+GEOMS = [  # N, C, H, O, k, s, p
+    (2, 64, 8, 64, 1, 1, 0), (3, 64, 4, 64, 3, 1, 1), (9, 64, 4, 128, 3, 1, 1), (4, 192, 8, 384, 3, 1, 1),
+    (16, 512, 4, 512, 3, 1, 1), (8, 256, 8, 512, 3, 2, 1), (8, 256, 8, 512, 1, 2, 0), (2, 64, 32, 64, 3, 1, 1),
+    (5, 256, 7, 256, 3, 1, 1), (3, 128, 14, 256, 3, 2, 1), (1, 64, 4, 64, 3, 1, 1),
+]
+
+
+def _case(N, C, H, O, k, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = bf16r(torch.randn(N, C, H, H, generator=g))
+    w = bf16r(torch.randn(O, C, k, k, generator=g) * (2.0 / (C * k * k)) ** 0.5)
+    return x, w
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_conv_kernels_match_oracle_and_each_other(geom):
+    """tcgen05 fprop / dgrad / wgrad vs the CPU operator the reference calls, and vs the SIMT kernels."""
+    N, C, H, O, k, s, p = geom
+    spec = F_.ConvSpec(C, O, k, k, s, p)
+    x, w = _case(N, C, H, O, k)
+    P, Q = spec.out_hw(H, H)
+    dzc = bf16r(torch.randn(N, O, P, Q, generator=torch.Generator().manual_seed(1)))
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    z_ref = torch.nn.functional.conv2d(xr, wr, None, s, p)
+    z_ref.backward(dzc)
+    prep = F_.prepare_weight(w.cuda(), spec, True)
+    dz = dzc.permute(0, 2, 3, 1).contiguous().cuda()
+    res = {}
+    for tag, algo in (("tc", L.PP_ALGO_TCGEN05), ("simt", L.PP_ALGO_SIMT)):
+        z = F_.conv_fwd_raw(x.cuda(), prep, spec, z_f32=True, algo=algo).permute(0, 3, 1, 2)
+        dx = F_.conv_dgrad(dz, prep, spec, N, H, H, algo=algo).float().permute(0, 3, 1, 2)
+        dw = F_.conv_wgrad(dz, x.cuda(), spec, algo=algo)
+        res[tag] = (z, dx, dw)
+        assert rel_l2(z, z_ref) < 2e-5, tag
+        assert rel_l2(dx, bf16r(xr.grad)) < ACT_TOL, tag     # dx is a bf16 tensor: compare on the bf16 grid
+        assert rel_l2(dw, wr.grad) < 2e-5, tag
+    assert rel_l2(res["tc"][0], res["simt"][0]) < 1e-5
+    assert rel_l2(res["tc"][2], res["simt"][2]) < 1e-5
+
+
+def _make_block(kind, i, o, ks, s, pd, norm, H, seed=0, relu=True):
+    seed_all(seed)
+    kw = {"norm_type": norm, "key_type": "random", "sign_loss": 0.1}
+    if kind == "v1":
+        m = quiet(layers.PassportBlock, i, o, ks, s, pd, kw, relu)
+    elif kind == "private":
+        m = quiet(layers.PassportPrivateBlock, i, o, ks, s, pd, kw)
+    else:
+        m = layers.ConvBlock(i, o, ks, s, pd, bn=norm, relu=relu)
+    with torch.no_grad():
+        m.conv.weight.copy_(bf16r(m.conv.weight))
+        if kind == "private":
+            m.scale.copy_(torch.rand(o) + 0.5)
+            m.bias.copy_(torch.randn(o) * 0.1)
+    if kind != "conv":
+        m.set_key(bf16r(torch.rand(1, i, H, H) * 2 - 1), bf16r(torch.rand(1, i, H, H) * 2 - 1))
+    return m
+
+
+def _fwd_bwd(mod, kind, x, dev, inds):
+    mod.train()
+    xx = x.to(dev).clone().requires_grad_(True)
+    for sl in mod.modules():
+        if hasattr(sl, "scale_cache"):
+            sl.reset()
+    tot, ys = 0, []
+    gen = torch.Generator().manual_seed(5)
+    for ind in inds:
+        y = mod(xx, False, ind) if kind == "private" else (mod(xx) if kind == "conv" else mod(xx, False))
+        r = bf16r(torch.randn(y.shape, generator=gen)).to(dev)
+        tot = tot + (y.float() * r).sum()
+        ys.append(y.detach().float().cpu())
+    sl_tot = 0
+    for sl in mod.modules():
+        if hasattr(sl, "scale_cache"):
+            sl_tot = sl_tot + sl.loss
+    (tot + sl_tot).backward()
+    grads = {k: p.grad.detach().float().cpu() for k, p in mod.named_parameters() if p.grad is not None}
+    return dict(y=ys, dx=xx.grad.detach().float().cpu(), sl=float(sl_tot), grads=grads)
+
+
+BLOCKS = [  # name, kind, i, o, ks, s, pd, norm, N, H   — the passport layers of the BASELINE configs
+    ("resnet_layer4.0.convbnrelu_1", "private", 256, 512, 3, 2, 1, "bn", 32, 8),
+    ("resnet_layer4.0.convbn_2", "private", 512, 512, 3, 1, 1, "bn", 32, 4),
+    ("resnet_layer4.0.shortcut", "private", 256, 512, 1, 2, 0, "bn", 32, 8),
+    ("alexnet_features.4", "v1", 192, 384, 3, 1, 1, "bn", 16, 8),
+    ("alexnet_features.5", "v1", 384, 256, 3, 1, 1, "bn", 16, 8),
+    ("v1_none_norelu", "v1", 256, 256, 3, 1, 1, "none", 8, 8),
+    ("imagenet_layer4", "v1", 512, 512, 3, 1, 1, "bn", 4, 7),
+    ("conv_layer1", "conv", 64, 64, 3, 1, 1, "bn", 4, 32),
+    ("conv_stem", "conv", 3, 64, 3, 1, 1, "bn", 4, 32),
+]
+
+
+@pytest.mark.parametrize("case", BLOCKS, ids=[c[0] for c in BLOCKS])
+def test_block_matches_oracle(case):
+    name, kind, i, o, ks, s, pd, norm, N, H = case
+    m = _make_block(kind, i, o, ks, s, pd, norm, H, relu=(name != "v1_none_norelu"))
+    x = bf16r(torch.randn(N, i, H, H, generator=torch.Generator().manual_seed(3)))
+    oracle = po.mirror(m, round_bf16=True)
+    inds = (0, 1) if kind == "private" else (0,)
+    ref = _fwd_bwd(oracle, kind, x, "cpu", inds)
+    got = _fwd_bwd(m.cuda(), kind, x, "cuda", inds)
+    for k in range(len(inds)):
+        assert rel_l2(got["y"][k], bf16r(ref["y"][k])) < ACT_TOL, f"y{k}"
+    assert abs(got["sl"] - ref["sl"]) <= VEC_TOL * max(1.0, abs(ref["sl"]))
+    if i != 3:
+        assert rel_l2(got["dx"], ref["dx"]) < GRAD_TOL
+    for key, gref in ref["grads"].items():
+        gk = got["grads"].get(key, got["grads"].get("weight" if key == "conv.weight" else "conv.weight"))
+        assert rel_l2(gk, gref) < GRAD_TOL, key
+    if kind != "conv":
+        with torch.no_grad():
+            gg = m.get_scale(True, 1) if kind == "private" else m.get_scale(True)
+            go = oracle.get_scale(True, 1)
+        assert torch.equal(torch.sign(gg.reshape(-1).cpu()), torch.sign(go.reshape(-1)))
+        assert rel_l2(gg.reshape(-1).cpu(), go.reshape(-1)) < VEC_TOL
+
+
+def test_eval_mode_fused_epilogue_matches_training_path_kernels():
+    """no-grad eval (affine folded into the conv epilogue, z never written) == oracle in eval mode."""
+    m = _make_block("private", 256, 512, 3, 2, 1, "bn", 8)
+    with torch.no_grad():
+        m.bn.running_mean.copy_(torch.randn(512) * 0.1)
+        m.bn.running_var.copy_(torch.rand(512) + 0.5)
+    x = bf16r(torch.randn(16, 256, 8, 8, generator=torch.Generator().manual_seed(3)))
+    oracle = po.mirror(m, round_bf16=True).eval()
+    m = m.cuda().eval()
+    with torch.no_grad():
+        for ind in (0, 1):
+            y = m(x.cuda(), False, ind).float().cpu()
+            yr = oracle(x, False, ind)
+            assert rel_l2(y, bf16r(yr)) < ACT_TOL
+
+
+def test_signature_bits_bit_exact_full_size_layer():
+    """sign(gamma) of a full-size passport layer equals the fp64 evaluation of the reference formula."""
+    for (i, o, ks, s, pd, H) in ((512, 512, 3, 1, 1, 4), (256, 512, 3, 2, 1, 8), (256, 512, 1, 2, 0, 8)):
+        m = _make_block("private", i, o, ks, s, pd, "bn", H, seed=7)
+        w64 = m.weight.detach().double()
+        ref = po.key_affine(w64, m.skey_private.double(), s, pd)
+        m = m.cuda().eval()
+        with torch.no_grad():
+            gamma = m.get_scale(ind=1).reshape(-1).cpu()
+        assert torch.equal(torch.sign(gamma), torch.sign(ref).float())
+        assert rel_l2(gamma, ref) < 1e-6
+        assert abs(float(m.sign_loss_private.acc) - (torch.sign(ref).float() == m.b.cpu()).float().mean().item()) < 1e-6
+
+
+def test_full_size_properties_layer4_batch_1024():
+    """BASELINE-size checks that need no CPU oracle: exact integer arithmetic, linearity, BN moments."""
+    N, C, H, O = 1024, 512, 4, 512
+    spec = F_.ConvSpec(C, O, 3, 3, 1, 1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x1 = torch.randint(-2, 3, (N, C, H, H), generator=g, device="cuda").float()
+    x2 = torch.randint(-2, 3, (N, C, H, H), generator=g, device="cuda").float()
+    w = torch.randint(-1, 2, (O, C, 3, 3), generator=g, device="cuda").float()
+    prep = F_.prepare_weight(w, spec, True)
+    z1 = F_.conv_fwd_raw(x1, prep, spec, z_f32=True, algo=L.PP_ALGO_TCGEN05)
+    z2 = F_.conv_fwd_raw(x2, prep, spec, z_f32=True, algo=L.PP_ALGO_TCGEN05)
+    z12 = F_.conv_fwd_raw(x1 + x2, prep, spec, z_f32=True, algo=L.PP_ALGO_TCGEN05)
+    assert torch.equal(z12, z1 + z2)                       # small integers: every product and sum is exact
+    zs = F_.conv_fwd_raw(x1[:64], prep, spec, z_f32=True, algo=L.PP_ALGO_SIMT)
+    assert torch.equal(z1[:64], zs)                        # tensor-core result == SIMT result, bit for bit
+    # <dz, conv(x)> == <dgrad(dz), x> == <wgrad(dz, x), w>  (adjointness of the three kernels), integers -> exact
+    dz = torch.randint(-1, 2, (N, H, H, O), generator=g, device="cuda").float()
+    lhs = (dz.double() * z1.double()).sum()
+    dx = F_.conv_dgrad(dz, prep, spec, N, H, H).double().permute(0, 3, 1, 2)
+    dw = F_.conv_wgrad(dz, x1, spec).double()
+    scale = dz.double().norm().item() * z1.double().norm().item()
+    assert abs(lhs.item() - (dx * x1.double()).sum().item()) <= 1e-3 * scale     # dx is stored in bf16
+    assert abs(lhs.item() - (dw * w.double()).sum().item()) <= 1e-6 * scale      # dw is fp32 (integers: exact sums)
+    # BN(train) moments of the block output before ReLU: mean == beta, var == gamma^2
+    m = _make_block("v1", C, O, 3, 1, 1, "bn", H, relu=False).cuda().train()
+    xr = torch.randn(N, C, H, H, generator=g, device="cuda")
+    y = m(xr).float()
+    with torch.no_grad():
+        gamma, beta = m.get_scale(True).reshape(-1), m.get_bias(True).reshape(-1)
+    mean = y.mean(dim=(0, 2, 3))
+    var = y.var(dim=(0, 2, 3), unbiased=False)
+    assert (mean - beta).abs().max().item() < 2e-3 * (1 + beta.abs().max().item())
+    assert rel_l2(var, gamma * gamma) < 5e-3
+
+
+def _resnet(scheme="private", seed=0, num_classes=10):
+    seed_all(seed)
+    pk = nets.passport_kwargs_from_config(nets.resnet18_passport_config(), "bn", "random", 0.1)
+    return quiet(nets.ResNet18, scheme, num_classes, pk)
+
+
+def test_resnet18_private_step_matches_reference_golden_and_oracle():
+    """Whole ResNet18 V2 step: logits / loss / sign loss / gradients / signature against the reference's own run
+    (golden, fp32) and the bf16-operand oracle."""
+    gm = load_golden("resnet18_private_model")
+    model = _resnet()
+    x, t = gm["x"], gm["t"]
+    # random keys are created lazily by the first forward from numpy's RNG: replay the reference's seeds
+    seed_all(1)
+    torch.randn(8, 3, 32, 32); torch.randint(0, 10, (8,))
+    model = model.cuda().train()
+    from deepipr_b200.trainer import StepRunner
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    runner = StepRunner(model, opt, private=True, autocast=False)
+    loss, sign_loss, preds = runner.forward_backward(x.cuda(), t.cuda())
+    key_name = next(iter(gm["keys"]))
+    assert torch.equal(model.state_dict()[key_name].cpu(), gm["keys"][key_name]), "lazy random key differs"
+    # against the reference's fp32 run: bf16 operands in 20 layers => percent-level agreement on logits
+    for ind in range(2):
+        assert rel_l2(preds[ind].float().cpu(), gm["logits"][ind]) < 3e-2
+    assert abs(loss.item() - gm["loss"].item()) < 2e-2 * gm["loss"].item()
+    assert abs(sign_loss.item() - gm["sign_loss"].item()) < 1e-3 * gm["sign_loss"].item()
+    gn = {k: p.grad.double().norm().item() for k, p in model.named_parameters()}
+    for k in ("linear.weight", "layer4.1.convbn_2.weight", "layer4.0.convbnrelu_1.scale", "convbnrelu_1.conv.weight"):
+        assert abs(gn[k] - gm["grad_norms"][k]) < 6e-2 * gm["grad_norms"][k], k
+    sig = __import__("deepipr_b200.trainer", fromlist=["x"]).test_signature(model)
+    # the reference ran on fp32 keys/weights, this path rounds them to bf16: a few near-zero gammas may flip
+    assert sig == pytest.approx(gm["signature"], abs=0.01), "signature detection differs from the reference"
+
+
+def test_resnet18_private_trajectory_and_signature_vs_oracle():
+    """5 SGD steps on the GPU vs the same 5 steps of the bf16-operand oracle on the CPU."""
+    model = _resnet(seed=2)
+    seed_all(3)
+    xs = [bf16r(torch.randn(16, 3, 32, 32)) for _ in range(5)]
+    ts = [torch.randint(0, 10, (16,)) for _ in range(5)]
+    with torch.no_grad():  # fix the lazily created keys so both sides share them
+        for mod in model.modules():
+            if getattr(mod, "KIND", None) == "private":
+                c = mod.conv.in_channels
+                h = 8 if mod.conv.stride[0] == 2 else 4
+                mod.set_key(bf16r(torch.rand(1, c, h, h) * 2 - 1), bf16r(torch.rand(1, c, h, h) * 2 - 1))
+    oracle = po.mirror(model, round_bf16=True).train()
+    model = model.cuda().train()
+    from deepipr_b200.trainer import StepRunner, test_signature
+    opt_g = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    opt_o = torch.optim.SGD(oracle.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    runner = StepRunner(model, opt_g, private=True, autocast=False)
+    for x, t in zip(xs, ts):
+        loss, sl, _ = runner.step(x.cuda(), t.cuda())
+        ref = po.train_step(oracle, opt_o, x, t, private=True)
+        assert abs(loss.item() - ref["loss"]) < 3e-2 * abs(ref["loss"])
+        assert abs(sl.item() - ref["sign_loss"]) < 2e-3 * abs(ref["sign_loss"])
+    sig_g = test_signature(model)
+    sig_o = po.test_signature(oracle.eval())
+    assert sig_g.keys() == sig_o.keys()
+    for k in sig_g:
+        assert sig_g[k] == pytest.approx(sig_o[k], abs=1e-9), k
+    for (ng, mg), (no, mo) in zip([(n, m) for n, m in model.named_modules() if getattr(m, "KIND", "") == "private"],
+                                  [(n, m) for n, m in oracle.named_modules() if getattr(m, "KIND", "") == "private"]):
+        with torch.no_grad():
+            bits_g = mg.get_scale(ind=1).reshape(-1).sign().cpu()
+            bits_o = mo.get_scale(ind=1).reshape(-1).sign()
+        assert torch.equal(bits_g, bits_o), f"extracted signature bits differ in {ng}"
+
+
+def test_alexnet_v1_step_vs_oracle():
+    seed_all(0)
+    pk = nets.passport_kwargs_from_config(nets.alexnet_passport_config(), "bn", "random", 0.1)
+    model = quiet(nets.AlexNetCifar, "v1", 3, 10, pk)
+    with torch.no_grad():
+        for mod in model.modules():
+            if getattr(mod, "KIND", None) == "v1":
+                c = mod.conv.in_channels
+                mod.set_key(bf16r(torch.rand(1, c, 8, 8) * 2 - 1), bf16r(torch.rand(1, c, 8, 8) * 2 - 1))
+    x = bf16r(torch.randn(16, 3, 32, 32))
+    t = torch.randint(0, 10, (16,))
+    oracle = po.mirror(model, round_bf16=True).train()
+    model = model.cuda().train()
+    from deepipr_b200.trainer import StepRunner
+    opt_g = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    opt_o = torch.optim.SGD(oracle.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    loss, sl, preds = StepRunner(model, opt_g, private=False, autocast=False).step(x.cuda(), t.cuda())
+    ref = po.train_step(oracle, opt_o, x, t, private=False)
+    assert abs(loss.item() - ref["loss"]) < 2e-2 * abs(ref["loss"])
+    assert abs(sl.item() - ref["sign_loss"]) < 1e-3 * abs(ref["sign_loss"])
+
+
+def test_flat_sgd_matches_torch_sgd():
+    from deepipr_b200.parallel import FlatParams, FlatSGD
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in ((7, 5), (64,), (3, 3, 3, 3))]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    flat = FlatParams(ps)
+    opt = FlatSGD(flat, lr=0.1, momentum=0.9, weight_decay=1e-4)
+    opt_ref = torch.optim.SGD(ref, lr=0.1, momentum=0.9, weight_decay=1e-4)
+    for step in range(4):
+        opt.zero_grad()
+        opt_ref.zero_grad()
+        gs = [torch.randn_like(p) for p in ps]
+        for p, r, g in zip(ps, ref, gs):
+            p.grad.copy_(g)
+            r.grad = g.clone()
+        opt.step()
+        opt_ref.step()
+        for p, r in zip(ps, ref):
+            assert torch.allclose(p, r, rtol=1e-6, atol=1e-7)
