@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--legs", default="value,e2e,roofline", help="comma list of legs to run (profiling runs: value)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -216,6 +217,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = args.steps * B * world / (ms_total * 1e-3)
 
+    legs = set(args.legs.split(","))
+
     # ---------------- leg 2: end to end through the public step API with host (pinned) buffers
     def e2e_step(i):
         x, t = host_batches[i % 4]
@@ -225,23 +228,26 @@ def main():
         # the reference loop's host reads: two accuracies + loss + sign loss (trainer_private.py:163-177)
         return (accuracy(preds[0], td)[0].item(), accuracy(preds[1], td)[0].item(), sign_loss.item(), loss.item())
 
-    for i in range(max(3, args.warmup // 2)):
-        e2e_step(i)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        last = e2e_step(i)
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = args.steps * B * world / (ms_e2e * 1e-3)
+    last = (None,) * 4
+    ms_e2e, e2e_value = None, None
+    if "e2e" in legs:
+        for i in range(max(3, args.warmup // 2)):
+            e2e_step(i)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            last = e2e_step(i)
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e_value = args.steps * B * world / (ms_e2e * 1e-3)
     h2d = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 8
     d2h = 4 * 4
 
     # ---------------- leg 3: per-kernel roofline of the dominant kernel (CUDA events on its stream)
     roof = None
     roof_w = None
-    if rank == 0:
+    if rank == 0 and "roofline" in legs:
         pk = peaks()
         lib.pp_profile_enable(1)
         for i in range(3):
@@ -272,7 +278,7 @@ def main():
     model.train()
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and "e2e" in legs:
         cpu_baseline, _ = cpu_reference_run(args.cpu_steps, 1)
 
     if rank == 0:
@@ -282,7 +288,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": (ms_e2e / args.steps) if ms_e2e else None},
                 "gpu_launches": launches,
                 "roofline": roof, "roofline_wgrad": roof_w,
                 "conv_roofline_frac_whole_step": (value / world) * GFLOP_PER_IMAGE_STEP * 1e9 / (pk["tflops"] * 1e12),

@@ -168,11 +168,32 @@ static bool use_tcgen05(const PPConvDesc& d, bool supported) {
 
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
+// Small-C convolutions (C*kh*kw padded to Kpad, e.g. the 3-channel stem): explicit im2col + 1x1 tap-GEMM.
+static int col_kpad(const PPConvDesc& d, const Geo& geo) {
+  if (d.algo == PP_ALGO_SIMT) return 0;
+  if (d.C % 64 == 0 || d.O % 64 != 0) return 0;
+  const int K = d.C * geo.T;
+  if (K > 1024) return 0;
+  return (K + 63) / 64 * 64;
+}
+
+// the explicitly im2col'ed matrix col[rows][Kpad] viewed as a 1 x rows image with Kpad channels
+static void plan_col(const PPConvDesc& d, const Geo& geo, int Kpad, TapGemm& g) {
+  memset(&g, 0, sizeof(g));
+  g.N = 1; g.H = 1; g.W = (int)geo.rows; g.C = Kpad;
+  g.P = 1; g.Q = (int)geo.rows;
+  g.base_h = 0; g.base_w = 0; g.step_h = 1; g.step_w = 1; g.upper_h = 0; g.upper_w = 0;
+  g.ntaps = 1; g.tap_dh[0] = 0; g.tap_dw[0] = 0; g.tap_kofs[0] = 0;
+  g.Nout = d.O; g.Ktot = Kpad;
+  g.out_H = 1; g.out_W = (int)geo.rows; g.out_sh = 1; g.out_sw = 1; g.out_ph = 0; g.out_pw = 0; g.out_identity = 1;
+}
+
 struct FwdWs {
   float* ca; float* cb; float* partial;
+  __nv_bfloat16* col; __nv_bfloat16* wpad;
   size_t total;
 };
-static FwdWs carve_fwd(const PPConvDesc& d, void* base) {
+static FwdWs carve_fwd(const PPConvDesc& d, const Geo& geo, void* base) {
   FwdWs w;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;
@@ -180,13 +201,16 @@ static FwdWs carve_fwd(const PPConvDesc& d, void* base) {
   w.cb = reinterpret_cast<float*>(p + off); off += align256((size_t)d.O * 4);
   const size_t max_part = (size_t)(bwd_reduce_max_partials() > 160 ? bwd_reduce_max_partials() : 160);
   w.partial = reinterpret_cast<float*>(p + off); off += align256(max_part * 2 * d.O * 4);
+  const int Kpad = col_kpad(d, geo);
+  w.col = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * (size_t)Kpad * 2);
+  w.wpad = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256((size_t)d.O * Kpad * 2);
   w.total = off;
   return w;
 }
 
 struct BwdWs {
   float* ca; float* cb; float* k1; float* k2; float* k3; float* partial;
-  __nv_bfloat16* dz; float* wpartial;
+  __nv_bfloat16* dz; __nv_bfloat16* col; float* wpartial;
   size_t total;
 };
 static BwdWs carve_bwd(const PPConvDesc& d, const Geo& geo, void* base, int wg_splits) {
@@ -201,22 +225,40 @@ static BwdWs carve_bwd(const PPConvDesc& d, const Geo& geo, void* base, int wg_s
   w.k3 = reinterpret_cast<float*>(p + off); off += vec;
   w.partial = reinterpret_cast<float*>(p + off); off += align256((size_t)bwd_reduce_max_partials() * 2 * d.O * 4);
   w.dz = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * d.O * 2);
+  const int Kpad = col_kpad(d, geo);
+  w.col = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * (size_t)Kpad * 2);
+  const size_t krow = Kpad ? (size_t)Kpad : (size_t)geo.T * d.C;
   w.wpartial = reinterpret_cast<float*>(p + off);
-  off += align256((size_t)wg_splits * d.O * geo.T * d.C * 4);
+  off += align256((size_t)wg_splits * d.O * krow * 4);
   w.total = off;
   return w;
 }
 
 static int wgrad_splits_for(const PPConvDesc& d, const Geo& geo, bool* tc) {
   TapGemm g;
+  const int Kpad = col_kpad(d, geo);
+  if (Kpad) {
+    plan_col(d, geo, Kpad, g);
+    *tc = true;
+    return wgrad_pick_splits(g, d.O);
+  }
   plan_fprop(d, geo, g);
   *tc = use_tcgen05(d, wgrad_tcgen05_supported(g, d.O));
   return *tc ? wgrad_pick_splits(g, d.O) : wgrad_simt_pick_splits(g, d.O);
 }
 
+// scratch: col / wpad are only touched on the small-C im2col path (may be NULL otherwise)
 static int run_fprop(const PPConvDesc& d, const Geo& geo, const void* x, const void* wf, const TapEpilogue& e,
-                     bool* used_tc, cudaStream_t s) {
+                     bool* used_tc, __nv_bfloat16* col, __nv_bfloat16* wpad, cudaStream_t s) {
   TapGemm g;
+  const int Kpad = col_kpad(d, geo);
+  if (Kpad && col && wpad) {
+    PP_TRY(launch_im2col_small(d, (const __nv_bfloat16*)x, col, geo.rows, geo.P, geo.Q, Kpad, s));
+    PP_TRY(launch_pad_rows((const __nv_bfloat16*)wf, wpad, d.O, geo.T * d.C, Kpad, s));
+    plan_col(d, geo, Kpad, g);
+    if (used_tc) *used_tc = true;
+    return tapgemm_tcgen05(g, col, wpad, e, s);
+  }
   plan_fprop(d, geo, g);
   const bool tc = use_tcgen05(d, tapgemm_tcgen05_supported(g));
   PP_REQUIRE(tc || d.algo != PP_ALGO_TCGEN05, PP_EUNSUPPORTED, "PP_ALGO_TCGEN05 requested but C=%d O=%d unsupported",
@@ -243,7 +285,8 @@ static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
     TapEpilogue e;
     e.out = dx; e.out_f32 = 0; e.scale = nullptr; e.shift = nullptr; e.relu = 0; e.stats_partial = nullptr;
     const bool tc = use_tcgen05(d, tapgemm_tcgen05_supported(phases[i]));
-    PP_REQUIRE(tc || d.algo != PP_ALGO_TCGEN05, PP_EUNSUPPORTED, "PP_ALGO_TCGEN05 requested but dgrad unsupported");
+    PP_REQUIRE(tc || d.algo != PP_ALGO_TCGEN05 || d.C % 64 != 0, PP_EUNSUPPORTED,
+               "PP_ALGO_TCGEN05 requested but dgrad unsupported");
     if (tc) PP_TRY(tapgemm_tcgen05(phases[i], dz, wd, e, s));
     else PP_TRY(tapgemm_simt(phases[i], dz, wd, e, s));
   }
@@ -251,12 +294,19 @@ static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
 }
 
 static int run_wgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const void* x, float* dw, float* wpartial,
-                     int splits, bool tc, cudaStream_t s) {
+                     __nv_bfloat16* col, int splits, bool tc, cudaStream_t s) {
   TapGemm g;
+  const int Kpad = col_kpad(d, geo);
+  if (Kpad && col) {
+    PP_TRY(launch_im2col_small(d, (const __nv_bfloat16*)x, col, geo.rows, geo.P, geo.Q, Kpad, s));
+    plan_col(d, geo, Kpad, g);
+    PP_TRY(wgrad_tcgen05(g, col, dz, d.O, wpartial, splits, s));
+    return launch_wgrad_finalize(d, wpartial, splits, Kpad, dw, s);
+  }
   plan_fprop(d, geo, g);
   if (tc) PP_TRY(wgrad_tcgen05(g, x, dz, d.O, wpartial, splits, s));
   else PP_TRY(wgrad_simt(g, x, dz, d.O, wpartial, splits, s));
-  return launch_wgrad_finalize(d, wpartial, splits, dw, s);
+  return launch_wgrad_finalize(d, wpartial, splits, geo.T * d.C, dw, s);
 }
 
 }  // namespace pp
@@ -282,7 +332,7 @@ int pp_workspace_bytes(const PPConvDesc* d, int which, size_t* bytes) {
   PP_TRY(geo_of(d, &geo));
   PP_REQUIRE(bytes != nullptr, PP_EBADARG, "bytes is NULL");
   if (which == PP_WS_FWD) {
-    *bytes = carve_fwd(*d, nullptr).total;
+    *bytes = carve_fwd(*d, geo, nullptr).total;
   } else if (which == PP_WS_BWD) {
     bool tc;
     const int splits = wgrad_splits_for(*d, geo, &tc);
@@ -359,7 +409,7 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
              "unknown norm %d", d->norm);
   PP_REQUIRE(d->norm != PP_NORM_BN_EVAL || (running_mean && running_var), PP_EBADARG, "BN eval needs running stats");
   PP_REQUIRE(d->norm != PP_NORM_BN_TRAIN || z, PP_EBADARG, "BN train needs the z buffer");
-  FwdWs ws = carve_fwd(*d, workspace);
+  FwdWs ws = carve_fwd(*d, geo, workspace);
   PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "fwd workspace too small: need %zu, got %zu", ws.total,
              ws_bytes);
   if (z == nullptr) {
@@ -368,13 +418,13 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
                               save_invstd, ws.ca, ws.cb, s));
     TapEpilogue e;
     e.out = y; e.out_f32 = 0; e.scale = ws.ca; e.shift = ws.cb; e.relu = d->relu; e.stats_partial = nullptr;
-    return run_fprop(*d, geo, x, w_fprop, e, nullptr, s);
+    return run_fprop(*d, geo, x, w_fprop, e, nullptr, ws.col, ws.wpad, s);
   }
   TapEpilogue e;
   e.out = z; e.out_f32 = d->z_f32; e.scale = nullptr; e.shift = nullptr; e.relu = 0;
   e.stats_partial = (d->norm == PP_NORM_BN_TRAIN) ? ws.partial : nullptr;
   bool tc = false;
-  PP_TRY(run_fprop(*d, geo, x, w_fprop, e, &tc, s));
+  PP_TRY(run_fprop(*d, geo, x, w_fprop, e, &tc, ws.col, ws.wpad, s));
   int num_partials = 0;
   if (d->norm == PP_NORM_BN_TRAIN) {
     if (tc) {
@@ -416,7 +466,7 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
   PP_TRY(launch_bwd_dz((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.k1, ws.k2,
                        ws.k3, ws.dz, s));
   if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));
-  if (dw_oihw) PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, splits, wg_tc, s));
+  if (dw_oihw) PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s));
   return PP_OK;
 }
 
@@ -426,10 +476,12 @@ int pp_conv_fwd_raw(const PPConvDesc* d, const void* x, const void* w_fprop, voi
   PP_TRY(geo_of(d, &geo));
   PP_TRY(check_device());
   PP_REQUIRE(x && w_fprop && z, PP_EBADARG, "conv fwd raw: NULL pointer");
-  (void)workspace; (void)ws_bytes;
+  FwdWs ws = carve_fwd(*d, geo, workspace);
+  const bool have_ws = workspace != nullptr && ws_bytes >= ws.total;
   TapEpilogue e;
   e.out = z; e.out_f32 = d->z_f32; e.scale = nullptr; e.shift = nullptr; e.relu = 0; e.stats_partial = nullptr;
-  return run_fprop(*d, geo, x, w_fprop, e, nullptr, (cudaStream_t)stream);
+  return run_fprop(*d, geo, x, w_fprop, e, nullptr, have_ws ? ws.col : nullptr, have_ws ? ws.wpad : nullptr,
+                   (cudaStream_t)stream);
 }
 
 int pp_conv_dgrad(const PPConvDesc* d, const void* dz, const void* w_dgrad, void* dx, void* stream) {
@@ -451,7 +503,7 @@ int pp_conv_wgrad(const PPConvDesc* d, const void* dz, const void* x, float* dw_
   BwdWs ws = carve_bwd(*d, geo, workspace, splits);
   PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "wgrad workspace too small: need %zu, got %zu",
              ws.total, ws_bytes);
-  return run_wgrad(*d, geo, dz, x, dw_oihw, ws.wpartial, splits, tc, (cudaStream_t)stream);
+  return run_wgrad(*d, geo, dz, x, dw_oihw, ws.wpartial, ws.col, splits, tc, (cudaStream_t)stream);
 }
 
 int pp_sgd_step(size_t n, float* param, const float* grad, float* momentum_buf, float lr, float momentum,

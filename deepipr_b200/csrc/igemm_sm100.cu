@@ -9,9 +9,10 @@
 //                    epilogue                : tcgen05.ld -> registers -> per-channel sum / sum-of-squares
 //                                              (warp-shuffle transpose-reduce) and/or affine+ReLU -> 128-bit stores
 //                    serves conv fprop (passportconv2d.py:218) and its data gradient.
-//   wgrad_kernel   : weight gradient, both operands MN-major (pixels are the reduction dimension),
-//                    split over pixel ranges; fp32 partial tiles go to a workspace reduced by
-//                    pointwise.cu:wgrad_finalize (deterministic order, no float atomics).
+//   wgrad_kernel   : weight gradient computed transposed (rows = (tap, channel), columns = output channel),
+//                    both operands MN-major (pixels are the reduction dimension), split over pixel ranges;
+//                    fp32 partial tiles go to a workspace reduced by pointwise.cu:wgrad_finalize
+//                    (deterministic order, no float atomics).
 //
 // ptx.cuh is included by this translation unit only (it defines a __device__ variable).
 #include "common.h"
@@ -410,8 +411,20 @@ bool tapgemm_tcgen05_supported(const TapGemm& g) {
   return true;
 }
 
+// Output-channel tile: 256 halves the smem bytes read per MAC (an SS-mode 128x128 MMA already needs the full
+// 128 B/clk of shared-memory bandwidth); it is used whenever it still yields at least one tile per SM.
+static int pick_bn(const TapGemm& g) {
+  const long long M = (long long)g.N * g.P * g.Q;
+  const long long m_tiles = (M + kBM - 1) / kBM;
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  if (g.Nout % 256 == 0 && m_tiles * (g.Nout / 256) >= sms) return 256;
+  if (g.Nout % 128 == 0) return 128;
+  return 64;
+}
+
 int tapgemm_tcgen05_grid(const TapGemm& g) {
-  const int bn = (g.Nout % 128 == 0) ? 128 : 64;
+  const int bn = pick_bn(g);
   const long long M = (long long)g.N * g.P * g.Q;
   const long long tiles = ((M + kBM - 1) / kBM) * (g.Nout / bn);
   const int sms = device_sm_count();
@@ -459,43 +472,49 @@ int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapE
   PP_TRY(resolve_encoders());
   PP_REQUIRE(tapgemm_tcgen05_supported(g), PP_EUNSUPPORTED,
              "tcgen05 tap-GEMM needs C%%64==0 and Nout%%64==0 (C=%d Nout=%d)", g.C, g.Nout);
-  if (g.Nout % 128 == 0) return launch_tapgemm<128>(g, act, B, e, s);
-  return launch_tapgemm<64>(g, act, B, e, s);
+  switch (pick_bn(g)) {
+    case 256: return launch_tapgemm<256>(g, act, B, e, s);
+    case 128: return launch_tapgemm<128>(g, act, B, e, s);
+    default: return launch_tapgemm<64>(g, act, B, e, s);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight gradient
-//   D[o, c] (one filter tap) = sum over pixels m of dz[m, o] * x_tap[m, c]
-//   A = dz^T  : MN-major (o contiguous),  2 slabs of [64 pixels x 64 o]
-//   B = x_tap : MN-major (c contiguous),  BNW/64 slabs of [64 pixels x 64 c] loaded in im2col mode
+// weight gradient, computed transposed:  D[(tap, c), o] = sum over pixels m of x_tap[m, c] * dz[m, o]
+//   A = x_tap : MN-major ((tap, c) contiguous per pixel row), two 64-wide slabs per CTA loaded in im2col mode
+//               (a slab is 64 channels of ONE tap, so C % 64 == 0 keeps slabs from straddling taps)
+//   B = dz    : MN-major (o contiguous), BN/64 slabs of [64 pixels x 64 o]
+// Putting (tap, c) on M keeps all 128 MMA rows busy even for 64-channel layers, and BN up to 256 output
+// channels per tile cuts the smem bytes read per MAC.  The reduction (pixels) is split over blockIdx.y;
+// fp32 partial tiles go to partial[split][o][tap*C + c] and are summed by pointwise.cu:wgrad_finalize.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWK = 64;  // pixels per stage
 
-template <int BNW>
+template <int BN>
 struct WgCfg {
-  static constexpr int kStageA = 2 * kWK * 128;            // 16 KiB: two 64-wide o slabs
-  static constexpr int kStageB = (BNW / 64) * kWK * 128;   // 8 or 16 KiB
+  static constexpr int kStageA = 2 * kWK * 128;          // 16 KiB: two 64-wide (tap, c) slabs
+  static constexpr int kStageB = (BN / 64) * kWK * 128;  // 8 / 16 / 32 KiB
   static constexpr int kStageBytes = kStageA + kStageB;
-  static constexpr int kStages = 6;
-  static constexpr int kTmemCols = BNW;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = BN;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
 };
 
 struct WgradDev {
   int M, P, Q, PQ;
   int base_h, base_w, step_h, step_w;
-  int C, O, ntaps, Ktot;
-  int c_tiles, o_tiles;
+  int C, O, ntaps, Ktot;   // Ktot = ntaps * C = rows of the transposed gradient
+  int n_tiles;             // O / BN
   int chunks_total, chunks_per_split;
   int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
   float* partial;  // [splits][O][Ktot]
 };
 
-template <int BNW>
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX,
+wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDz,
              const __grid_constant__ WgradDev p) {
-  using Cfg = WgCfg<BNW>;
+  using Cfg = WgCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -507,11 +526,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile decode: blockIdx.x = (tap, o_tile, c_tile), blockIdx.y = split
-  int id = blockIdx.x;
-  const int c_tile = id % p.c_tiles; id /= p.c_tiles;
-  const int o_tile = id % p.o_tiles; id /= p.o_tiles;
-  const int tap = id;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_tile = blockIdx.x / p.n_tiles;
   const int split = blockIdx.y;
   const int chunk_lo = split * p.chunks_per_split;
   int chunk_hi = chunk_lo + p.chunks_per_split;
@@ -539,10 +555,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {
+      // the two A slabs of this tile: rows [k0, k0+64) and [k1, k1+64) of the (tap, c) axis
+      int k0 = m_tile * 128, k1 = k0 + 64;
+      if (k1 >= p.Ktot) k1 = k0;  // odd slab count: load slab 0 twice (its rows are not stored)
+      const int tap0 = k0 / p.C, c0 = k0 - tap0 * p.C;
+      const int tap1 = k1 / p.C, c1 = k1 - tap1 * p.C;
+      const uint16_t dw0 = (uint16_t)p.tap_dw[tap0], dh0 = (uint16_t)p.tap_dh[tap0];
+      const uint16_t dw1 = (uint16_t)p.tap_dw[tap1], dh1 = (uint16_t)p.tap_dh[tap1];
       int stage = 0;
       uint32_t phase = 0;
-      const uint16_t dw = (uint16_t)p.tap_dw[tap];
-      const uint16_t dh = (uint16_t)p.tap_dh[tap];
       for (int ch = chunk_lo; ch < chunk_lo + nchunks; ++ch) {
         const int m0 = ch * kWK;
         const int img = m0 / p.PQ;
@@ -555,17 +576,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kStageA;
         mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-        tma_load_2d(&tmDz, &full[stage], sa, o_tile * 128, m0);
-        tma_load_2d(&tmDz, &full[stage], sa + kWK * 128, o_tile * 128 + 64, m0);
+        tma_load_im2col_4d(&tmX, &full[stage], sa, c0, cw, chh, img, dw0, dh0);
+        tma_load_im2col_4d(&tmX, &full[stage], sa + kWK * 128, c1, cw, chh, img, dw1, dh1);
 #pragma unroll
-        for (int i = 0; i < BNW / 64; ++i)
-          tma_load_im2col_4d(&tmX, &full[stage], sb + i * kWK * 128, c_tile * BNW + i * 64, cw, chh, img, dw, dh);
+        for (int i = 0; i < BN / 64; ++i)
+          tma_load_2d(&tmDz, &full[stage], sb + i * kWK * 128, n_tile * BN + i * 64, m0);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BNW, 1, 1);
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nchunks; ++it) {
@@ -588,15 +609,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int o = o_tile * 128 + row;
-    float* dst_row = p.partial + ((size_t)split * p.O + (size_t)o) * p.Ktot + (size_t)tap * p.C + c_tile * BNW;
+    const int k = m_tile * 128 + row;           // (tap, c) index of this accumulator row
+    const bool valid = k < p.Ktot;
     if (nchunks > 0) {
       mbar_wait(tfull, 0, 700);
       tc_fence_after();
     }
     const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+    float* dst0 = p.partial + ((size_t)split * p.O + (size_t)n_tile * BN) * p.Ktot + k;
 #pragma unroll 1
-    for (int j = 0; j < BNW / 32; ++j) {
+    for (int j = 0; j < BN / 32; ++j) {
       uint32_t raw[32];
       if (nchunks > 0) {
         tmem_ld_32x32(taddr + j * 32, raw);
@@ -605,12 +627,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 32; ++i) raw[i] = 0u;
       }
-      if (o < p.O) {
-        float4* dst = reinterpret_cast<float4*>(dst_row + j * 32);
+      if (valid) {
+        // lanes hold consecutive k: every store instruction writes 32 consecutive floats of one o row
+        float* dst = dst0 + (size_t)(j * 32) * p.Ktot;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
-                               __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+        for (int i = 0; i < 32; ++i) dst[(size_t)i * p.Ktot] = __uint_as_float(raw[i]);
       }
     }
   }
@@ -632,26 +653,28 @@ bool wgrad_tcgen05_supported(const TapGemm& g, int O) {
   return true;
 }
 
+static int wgrad_bn(int O) { return (O % 256 == 0) ? 256 : ((O % 128 == 0) ? 128 : 64); }
+
 int wgrad_pick_splits(const TapGemm& g, int O) {
-  const int bnw = (g.C % 128 == 0) ? 128 : 64;
-  const int tiles = ((O + 127) / 128) * (g.C / bnw) * g.ntaps;
+  const int Ktot = g.ntaps * g.C;
+  const int tiles = ((Ktot + 127) / 128) * (O / wgrad_bn(O));
   const long long M = (long long)g.N * g.P * g.Q;
   const int chunks = (int)((M + kWK - 1) / kWK);
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  int splits = (2 * sms + tiles - 1) / tiles;
-  if (splits > chunks) splits = chunks;
+  int splits = (2 * sms) / tiles;          // two full waves when the tile count allows it
+  if (splits > chunks / 4) splits = chunks / 4;   // at least a few pipeline stages of work per CTA
   if (splits < 1) splits = 1;
   // keep the fp32 partial workspace bounded (64 MiB)
-  const long long per_split = (long long)O * g.ntaps * g.C * 4;
+  const long long per_split = (long long)O * Ktot * 4;
   while (splits > 1 && per_split * splits > (64ll << 20)) --splits;
   return splits;
 }
 
-template <int BNW>
+template <int BN>
 static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, float* partial, int splits,
                         cudaStream_t s) {
-  using Cfg = WgCfg<BNW>;
+  using Cfg = WgCfg<BN>;
   CUtensorMap tmDz, tmX;
   const long long M = (long long)g.N * g.P * g.Q;
   PP_TRY(make_map_2d(&tmDz, dz, (uint64_t)M, (uint64_t)O, kWK));
@@ -660,21 +683,21 @@ static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, 
   p.M = (int)M; p.P = g.P; p.Q = g.Q; p.PQ = g.P * g.Q;
   p.base_h = g.base_h; p.base_w = g.base_w; p.step_h = g.step_h; p.step_w = g.step_w;
   p.C = g.C; p.O = O; p.ntaps = g.ntaps; p.Ktot = g.ntaps * g.C;
-  p.c_tiles = g.C / BNW;
-  p.o_tiles = (O + 127) / 128;
+  p.n_tiles = O / BN;
   p.chunks_total = (int)((M + kWK - 1) / kWK);
   p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
   for (int t = 0; t < g.ntaps; ++t) { p.tap_dh[t] = g.tap_dh[t]; p.tap_dw[t] = g.tap_dw[t]; }
   p.partial = partial;
   static bool attr_set = false;
   if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BNW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid(p.c_tiles * p.o_tiles * g.ntaps, splits);
+  const int m_tiles = (p.Ktot + 127) / 128;
+  dim3 grid(m_tiles * p.n_tiles, splits);
   prof_begin(PROF_WGRAD, 2.0 * (double)M * O * g.ntaps * g.C, s);
-  wgrad_kernel<BNW><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmDz, tmX, p);
+  wgrad_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmX, tmDz, p);
   prof_end(PROF_WGRAD, s);
   PP_POST_LAUNCH();
   return PP_OK;
@@ -685,8 +708,11 @@ int wgrad_tcgen05(const TapGemm& g, const void* x, const void* dz, int O, float*
   PP_TRY(resolve_encoders());
   PP_REQUIRE(wgrad_tcgen05_supported(g, O), PP_EUNSUPPORTED, "tcgen05 wgrad needs C%%64==0 and O%%64==0 (C=%d O=%d)",
              g.C, O);
-  if (g.C % 128 == 0) return launch_wgrad<128>(g, x, dz, O, partial, splits, s);
-  return launch_wgrad<64>(g, x, dz, O, partial, splits, s);
+  switch (wgrad_bn(O)) {
+    case 256: return launch_wgrad<256>(g, x, dz, O, partial, splits, s);
+    case 128: return launch_wgrad<128>(g, x, dz, O, partial, splits, s);
+    default: return launch_wgrad<64>(g, x, dz, O, partial, splits, s);
+  }
 }
 
 int debug_last_timeout() {

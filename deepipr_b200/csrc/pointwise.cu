@@ -204,24 +204,46 @@ int launch_passport_affine_bwd(const PPConvDesc& d, const double* Ss, const doub
   return PP_OK;
 }
 
+// Sum partial[num][2][O] over `num` for 32 channels per block: blockDim = (32 channels, 32 slices).
+// Every thread adds the rows i == slice (mod 32) in fp64, slices are combined in a fixed order by slice 0.
+// Returns true (with the totals) for the threads that own a channel.
+__device__ __forceinline__ bool reduce_partials_32x32(const float* __restrict__ partial, int num, int O, int o,
+                                                      double& s1, double& s2) {
+  __shared__ double sh1[32][33], sh2[32][33];
+  const int slice = threadIdx.y;
+  double a1 = 0.0, a2 = 0.0;
+  if (o < O) {
+    for (int i = slice; i < num; i += 32) {
+      a1 += (double)partial[(size_t)i * 2 * O + o];
+      a2 += (double)partial[(size_t)i * 2 * O + O + o];
+    }
+  }
+  sh1[slice][threadIdx.x] = a1;
+  sh2[slice][threadIdx.x] = a2;
+  __syncthreads();
+  if (slice != 0 || o >= O) return false;
+  s1 = 0.0; s2 = 0.0;
+  for (int k = 0; k < 32; ++k) {
+    s1 += sh1[k][threadIdx.x];
+    s2 += sh2[k][threadIdx.x];
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // BatchNorm finalise: partial[num][2][O] -> mean, invstd, running stats, affine coefficients
 //   y = a*z + b,  a = gamma*invstd,  b = beta - a*mean   (gamma*bn(z)+beta, passportconv2d.py:219-220)
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(int norm, int n, const float* __restrict__ partial, int num,
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(int norm, int n, const float* __restrict__ partial, int num,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ rmean, float* __restrict__ rvar, float eps, float momentum,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                    float* __restrict__ ca, float* __restrict__ cb, int O) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= O) return;
+  const int o = blockIdx.x * 32 + threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  if (!reduce_partials_32x32(partial, norm == PP_NORM_BN_TRAIN ? num : 0, O, o, s1, s2)) return;
   float mean = 0.0f, invstd = 1.0f;
   if (norm == PP_NORM_BN_TRAIN) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < num; ++i) {
-      s1 += (double)partial[(size_t)i * 2 * O + o];
-      s2 += (double)partial[(size_t)i * 2 * O + O + o];
-    }
     const double m = s1 / n;
     double var = s2 / n - m * m;
     if (var < 0.0) var = 0.0;
@@ -248,7 +270,7 @@ __global__ void bn_finalize_kernel(int norm, int n, const float* __restrict__ pa
 int launch_bn_finalize(const PPConvDesc& d, int n, const float* partial, int num, const float* gamma,
                        const float* beta, float* rmean, float* rvar, float* save_mean, float* save_invstd, float* ca,
                        float* cb, cudaStream_t s) {
-  bn_finalize_kernel<<<(d.O + 63) / 64, 64, 0, s>>>(d.norm, n, partial, num, gamma, beta, rmean, rvar, d.eps,
+  bn_finalize_kernel<<<(d.O + 31) / 32, dim3(32, 32), 0, s>>>(d.norm, n, partial, num, gamma, beta, rmean, rvar, d.eps,
                                                    d.momentum, save_mean, save_invstd, ca, cb, d.O);
   PP_POST_LAUNCH();
   return PP_OK;
@@ -449,18 +471,14 @@ int launch_bwd_reduce(const __nv_bfloat16* dy, const void* z, int z_f32, size_t 
 //   BN (train): dz = invstd*gamma*(dy_m - s1/n - zhat*dgamma/n) = k1*dy_m + k2*z + k3
 //   none / BN(eval):  dz = a*dy_m
 // ---------------------------------------------------------------------------------------------
-__global__ void bwd_coef_kernel(int norm, double n, const float* __restrict__ partial, int num,
+__global__ void __launch_bounds__(1024) bwd_coef_kernel(int norm, double n, const float* __restrict__ partial, int num,
                                 const float* __restrict__ gamma, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2,
                                 float* __restrict__ k3, int O) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= O) return;
+  const int o = blockIdx.x * 32 + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < num; ++i) {
-    s1 += (double)partial[(size_t)i * 2 * O + o];
-    s2 += (double)partial[(size_t)i * 2 * O + O + o];
-  }
+  if (!reduce_partials_32x32(partial, num, O, o, s1, s2)) return;
   const double mu = mean[o], is = invstd[o];
   const double g = gamma ? (double)gamma[o] : 1.0;
   const double dg = is * (s2 - mu * s1);
@@ -482,7 +500,7 @@ __global__ void bwd_coef_kernel(int norm, double n, const float* __restrict__ pa
 int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int num_partials, const float* gamma,
                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* k1,
                     float* k2, float* k3, cudaStream_t s) {
-  bwd_coef_kernel<<<(d.O + 63) / 64, 64, 0, s>>>(d.norm, (double)rows, partial, num_partials, gamma, save_mean,
+  bwd_coef_kernel<<<(d.O + 31) / 32, dim3(32, 32), 0, s>>>(d.norm, (double)rows, partial, num_partials, gamma, save_mean,
                                                 save_invstd, dgamma, dbeta, k1, k2, k3, d.O);
   PP_POST_LAUNCH();
   return PP_OK;
@@ -527,13 +545,13 @@ int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows
 // weight-gradient finalise: dw[o][c][t] = sum_split partial[split][o][t*C + c]   (one block per o)
 // ---------------------------------------------------------------------------------------------
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dw, int O,
-                                      int C, int T) {
+                                      int C, int T, int kstride) {
   extern __shared__ float s_row[];  // [T*C]
   const int o = blockIdx.x;
   const int K = T * C;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     float acc = 0.0f;
-    for (int sidx = 0; sidx < splits; ++sidx) acc += partial[((size_t)sidx * O + o) * K + k];
+    for (int sidx = 0; sidx < splits; ++sidx) acc += partial[((size_t)sidx * O + o) * kstride + k];
     s_row[k] = acc;
   }
   __syncthreads();
@@ -545,7 +563,8 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int spl
   }
 }
 
-int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, float* dw_oihw, cudaStream_t s) {
+int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, int kstride, float* dw_oihw,
+                          cudaStream_t s) {
   const int T = d.kh * d.kw;
   const size_t smem = (size_t)T * d.C * sizeof(float);
   PP_REQUIRE(smem <= 160 * 1024, PP_EUNSUPPORTED, "filter row too large for wgrad finalise (%zu B)", smem);
@@ -555,7 +574,64 @@ int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits,
                                        160 * 1024));
     attr = true;
   }
-  wgrad_finalize_kernel<<<d.O, 256, smem, s>>>(partial, splits, dw_oihw, d.O, d.C, T);
+  wgrad_finalize_kernel<<<d.O, 256, smem, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small-C convolutions (the 3-channel stem): explicit im2col into col[rows][Kpad] (k = tap*C + c, zero padded
+// to a multiple of 64) so the layer runs as a 1x1 tap-GEMM on the tensor cores; weights padded the same way.
+// ---------------------------------------------------------------------------------------------
+__global__ void im2col_small_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, size_t rows,
+                                    int H, int W, int C, int kh, int kw, int stride, int pad, int P, int Q,
+                                    int Kpad) {
+  const int groups = Kpad >> 3;
+  const size_t total = rows * groups;
+  const int K = kh * kw * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kg = (int)(i % groups);
+    const size_t m = i / groups;
+    const int q = (int)(m % Q);
+    const int p = (int)((m / Q) % P);
+    const size_t img = m / ((size_t)P * Q);
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kg * 8 + j;
+      float val = 0.0f;
+      if (k < K) {
+        const int t = k / C, c = k - t * C;
+        const int r = t / kw, sx = t - r * kw;
+        const int h = p * stride - pad + r, w = q * stride - pad + sx;
+        if (h >= 0 && h < H && w >= 0 && w < W) val = __bfloat162float(x[((img * H + h) * W + w) * C + c]);
+      }
+      v[j] = __float2bfloat16_rn(val);
+    }
+    reinterpret_cast<uint4*>(col)[i] = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+int launch_im2col_small(const PPConvDesc& d, const __nv_bfloat16* x, __nv_bfloat16* col, size_t rows, int P, int Q,
+                        int Kpad, cudaStream_t s) {
+  const size_t total = rows * (size_t)(Kpad / 8);
+  im2col_small_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(x, col, rows, d.H, d.W, d.C, d.kh, d.kw, d.stride,
+                                                                    d.pad, P, Q, Kpad);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
+__global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
+                                int K, int Kpad) {
+  const int total = rows * Kpad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / Kpad, k = i - r * Kpad;
+    dst[i] = k < K ? src[(size_t)r * K + k] : __float2bfloat16_rn(0.0f);
+  }
+}
+
+int launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int K, int Kpad, cudaStream_t s) {
+  pad_rows_kernel<<<grid_for((size_t)rows * Kpad, 256, 1024), 256, 0, s>>>(src, dst, rows, K, Kpad);
   PP_POST_LAUNCH();
   return PP_OK;
 }
