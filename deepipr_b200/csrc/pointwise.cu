@@ -546,35 +546,34 @@ int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows
 // ---------------------------------------------------------------------------------------------
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dw, int O,
                                       int C, int T, int kstride) {
-  extern __shared__ float s_row[];  // [T*C]
-  const int o = blockIdx.x;
   const int K = T * C;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+  const size_t total = (size_t)O * K;
+  const size_t split_stride = (size_t)O * kstride;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int o = (int)(i / K);
+    const float* src = partial + (size_t)o * kstride + k;
     float acc = 0.0f;
-    for (int sidx = 0; sidx < splits; ++sidx) acc += partial[((size_t)sidx * O + o) * kstride + k];
-    s_row[k] = acc;
-  }
-  __syncthreads();
-  float* dst = dw + (size_t)o * K;
-  for (int i = threadIdx.x; i < K; i += blockDim.x) {
-    const int t = i % T;
-    const int c = i / T;
-    dst[i] = s_row[t * C + c];
+    int sidx = 0;
+    for (; sidx + 4 <= splits; sidx += 4) {   // fixed summation order, four loads in flight
+      const float a0 = src[(size_t)(sidx + 0) * split_stride];
+      const float a1 = src[(size_t)(sidx + 1) * split_stride];
+      const float a2 = src[(size_t)(sidx + 2) * split_stride];
+      const float a3 = src[(size_t)(sidx + 3) * split_stride];
+      acc = (((acc + a0) + a1) + a2) + a3;
+    }
+    for (; sidx < splits; ++sidx) acc += src[(size_t)sidx * split_stride];
+    const int t = k / C;
+    const int c = k - t * C;
+    dw[((size_t)o * C + c) * T + t] = acc;
   }
 }
 
 int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, int kstride, float* dw_oihw,
                           cudaStream_t s) {
   const int T = d.kh * d.kw;
-  const size_t smem = (size_t)T * d.C * sizeof(float);
-  PP_REQUIRE(smem <= 160 * 1024, PP_EUNSUPPORTED, "filter row too large for wgrad finalise (%zu B)", smem);
-  static bool attr = false;
-  if (!attr) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       160 * 1024));
-    attr = true;
-  }
-  wgrad_finalize_kernel<<<d.O, 256, smem, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
+  const size_t total = (size_t)d.O * T * d.C;
+  wgrad_finalize_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
   PP_POST_LAUNCH();
   return PP_OK;
 }
@@ -586,29 +585,44 @@ int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits,
 __global__ void im2col_small_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, size_t rows,
                                     int H, int W, int C, int kh, int kw, int stride, int pad, int P, int Q,
                                     int Kpad) {
+  // per-k lookup: (dh, dw, c) of column k, or c = -1 for the zero padding columns
+  __shared__ int s_off[1024];   // packed: (dh << 20) | (dw << 12) | c   (Kpad <= 1024)
+  const int K = kh * kw * C;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int v = -1;
+    if (k < K) {
+      const int t = k / C, c = k - t * C;
+      v = ((t / kw) << 20) | ((t % kw) << 12) | c;
+    }
+    s_off[k] = v;
+  }
+  __syncthreads();
   const int groups = Kpad >> 3;
   const size_t total = rows * groups;
-  const int K = kh * kw * C;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int kg = (int)(i % groups);
     const size_t m = i / groups;
-    const int q = (int)(m % Q);
-    const int p = (int)((m / Q) % P);
-    const size_t img = m / ((size_t)P * Q);
-    __align__(16) __nv_bfloat16 v[8];
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (s_off[kg * 8] >= 0) {   // groups entirely inside the padding are written as zeros without any load
+      const int q = (int)(m % Q);
+      const int p = (int)((m / Q) % P);
+      const size_t img = m / ((size_t)P * Q);
+      const int h0 = p * stride - pad, w0 = q * stride - pad;
+      const __nv_bfloat16* xi = x + img * (size_t)H * W * C;
+      __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = kg * 8 + j;
-      float val = 0.0f;
-      if (k < K) {
-        const int t = k / C, c = k - t * C;
-        const int r = t / kw, sx = t - r * kw;
-        const int h = p * stride - pad + r, w = q * stride - pad + sx;
-        if (h >= 0 && h < H && w >= 0 && w < W) val = __bfloat162float(x[((img * H + h) * W + w) * C + c]);
+      for (int j = 0; j < 8; ++j) {
+        const int e = s_off[kg * 8 + j];
+        float val = 0.0f;
+        if (e >= 0) {
+          const int h = h0 + (e >> 20), w = w0 + ((e >> 12) & 0xff), c = e & 0xfff;
+          if (h >= 0 && h < H && w >= 0 && w < W) val = __bfloat162float(xi[((size_t)h * W + w) * C + c]);
+        }
+        v[j] = __float2bfloat16_rn(val);
       }
-      v[j] = __float2bfloat16_rn(val);
+      out = *reinterpret_cast<const uint4*>(v);
     }
-    reinterpret_cast<uint4*>(col)[i] = *reinterpret_cast<const uint4*>(v);
+    reinterpret_cast<uint4*>(col)[i] = out;
   }
 }
 

@@ -134,9 +134,9 @@ class GradBuckets:
         if self.world > 1:
             self.flat.ensure_grad_views()
             for b, pending in enumerate(self._pending):
-                if pending != 0 or not self.overlap:
-                    if not (self.overlap and pending == 0):
-                        self._launch(b)
+                already_launched = self.overlap and pending == 0
+                if not already_launched:       # no overlap mode, or a parameter that got no gradient this step
+                    self._launch(b)
             for w in self._works:
                 w.wait()
         self._works = []

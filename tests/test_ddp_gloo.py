@@ -1,0 +1,99 @@
+"""World-size-2 data-parallel plumbing on CPU (gloo): flat gradient buckets must reproduce the gradient of the
+concatenated global batch, with and without hook-driven overlap, and state broadcast must align the replicas.
+(The passport kernels themselves are CUDA-only; this covers the host-side N>1 logic.)"""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from deepipr_b200.parallel import FlatParams, GradBuckets, broadcast_state
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _model(seed):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Linear(12, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(),
+                               torch.nn.Linear(32, 5))
+
+
+def _worker(rank, world, port, overlap, bucket_bytes, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _model(seed=100 + rank)            # replicas start different on purpose
+        broadcast_state(model, src=0)
+        flat = FlatParams(model.parameters())
+        buckets = GradBuckets(flat, bucket_bytes=bucket_bytes, overlap=overlap)
+        opt = torch.optim.SGD(flat.params, lr=0.1)
+        g = torch.Generator().manual_seed(7)
+        X = torch.randn(8, 12, generator=g)
+        Y = torch.randint(0, 5, (8,), generator=g)
+        xs, ys = X[rank * 4:(rank + 1) * 4], Y[rank * 4:(rank + 1) * 4]
+        for step in range(2):
+            opt.zero_grad()                        # set_to_none=True: the bucket views must be restored
+            torch.nn.functional.cross_entropy(model(xs), ys).backward()
+            buckets.finish()
+            grads = [p.grad.clone() for p in flat.params]
+            opt.step()
+        out[rank] = dict(grads=grads, params=[p.detach().clone() for p in flat.params],
+                         nbuckets=len(buckets.buckets),
+                         views=all(p.grad.data_ptr() == flat.grad_view(i).data_ptr() for i, p in enumerate(flat.params)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(overlap, bucket_bytes):
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, overlap, bucket_bytes, out), nprocs=2, join=True)
+    # single-process reference on the global batch (mean over 8 == mean of the two per-rank means)
+    model = _model(seed=100)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(8, 12, generator=g)
+    Y = torch.randint(0, 5, (8,), generator=g)
+    for step in range(2):
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(model(X), Y).backward()
+        ref_grads = [p.grad.clone() for p in model.parameters()]
+        opt.step()
+    for rank in (0, 1):
+        r = out[rank]
+        assert r["views"]
+        for a, b in zip(r["grads"], ref_grads):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+        for a, b in zip(r["params"], model.parameters()):
+            assert torch.allclose(a, b.detach(), rtol=1e-5, atol=1e-6)
+    return out[0]["nbuckets"]
+
+
+def test_bucketed_allreduce_overlap_many_buckets():
+    assert _run(overlap=True, bucket_bytes=1024) > 2
+
+
+def test_bucketed_allreduce_no_overlap_single_bucket():
+    assert _run(overlap=False, bucket_bytes=1 << 30) == 1
+
+
+def test_flat_params_keeps_values_and_views():
+    model = _model(seed=1)
+    before = [p.detach().clone() for p in model.parameters()]
+    flat = FlatParams(model.parameters())
+    for p, b in zip(flat.params, before):
+        assert torch.equal(p.detach(), b)
+    flat.flat.mul_(2)
+    for p, b in zip(flat.params, before):
+        assert torch.equal(p.detach(), b * 2)          # parameters are views of the flat buffer
+    model(torch.randn(3, 12)).sum().backward()
+    assert flat.flat_grad.abs().sum() > 0              # gradients landed in the flat gradient buffer
+    flat.zero_grad()
+    assert flat.flat_grad.abs().sum() == 0 and all(p.grad is not None for p in flat.params)
