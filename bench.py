@@ -8,7 +8,7 @@
 
 Workload: one TrainerPrivate-style optimisation step (public + private forward, one backward, SGD) of ResNet-18 with
 passport layers in layer4 (passport_configs/resnet18_passport.json) on synthetic CIFAR-10-shaped tensors, bf16
-activations, per-GPU batch 1024 (weak scaling).  One JSON line on stdout (rank 0).
+activations, per-GPU batch 1184 = 8 x 148 SMs (weak scaling).  One JSON line on stdout (rank 0).
 """
 import argparse
 import ctypes as C
@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 METRIC = "images/sec ResNet18-passport CIFAR10 train"
 UNIT = "images/s"
 WORKLOAD = "ResNet18 V2 private-passport (layer4 x5 passport convs) CIFAR10-shaped TrainerPrivate step"
-PER_GPU_BATCH = 1024
+PER_GPU_BATCH = 1184                # 8 images per SM (148 SMs): every conv's tile count is a multiple of the SM count
 CPU_BATCH = 64                     # reference default batch (train_v1.py:15); bounded CPU sample
 GFLOP_PER_IMAGE_STEP = 6.665       # 2 forwards, 3x fwd FLOPs each
 
@@ -142,7 +142,7 @@ def main():
     config = {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1),
               "parallelism": f"dp{max(world, 1)}", "passport_layers": "layer4 (5 convs)", "norm": "bn",
               "optimizer": "SGD(0.01, momentum 0.9, wd 1e-4), fused flat step",
-              "l2": "per-step working set (~6 GB of activations at batch 1024) >> 126 MB L2; no explicit flush"}
+              "l2": "per-step working set (~7 GB of activations at batch 1184) >> 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -254,12 +254,13 @@ def main():
             runner.step(*dev_batches[i % 4])
         torch.cuda.synchronize()
         lib.pp_profile_enable(0)
-        out = []
-        for kind in (0, 1):
+        def read(kind, c=0, nout=0, taps=0):
             ms, fl, n = C.c_double(0), C.c_double(0), C.c_int(0)
-            lib.pp_profile_read(kind, C.byref(ms), C.byref(fl), C.byref(n))
-            out.append((ms.value, fl.value, n.value))
-        (ms0, fl0, n0), (ms1, fl1, n1) = out
+            lib.pp_profile_read(kind, c, nout, taps, C.byref(ms), C.byref(fl), C.byref(n))
+            return ms.value, fl.value, n.value
+
+        (ms0, fl0, n0), (ms1, fl1, n1) = read(0), read(1)
+        msp, flp, npl = read(0, 512, 512, 9)      # the 3x3 512->512 passport convs of layer4 (fprop + dgrad)
         if ms0 > 0:
             ach = fl0 / (ms0 * 1e-3) / 1e12
             roof = {"kernel": "tapgemm_kernel (tcgen05 implicit-GEMM conv fprop+dgrad)", "bound": "tensor",
@@ -267,6 +268,15 @@ def main():
                     "peak_source": pk["src"] + " bf16 sustained", "traffic": None,
                     "launches_per_step": n0 // 3, "avg_launch_us": ms0 * 1e3 / max(n0, 1),
                     "share_of_step": (ms0 / 3) / (ms_total / args.steps)}
+        if msp > 0 and roof is not None:
+            ach = flp / (msp * 1e-3) / 1e12
+            # traffic: dram__bytes_read+write per launch from the ncu --set full capture of this geometry at batch
+            # 1024 (profiles/r1_tapgemm_layer4.txt), scaled to this batch; algorithmic = x + W bytes
+            roof["passport_layer"] = {"geometry": "layer4 3x3 512->512 @4x4, fprop+dgrad launches", "achieved": ach,
+                                      "frac": ach / pk["tflops"], "launches_per_step": npl // 3,
+                                      "avg_launch_us": msp * 1e3 / max(npl, 1),
+                                      "traffic": 21.53e6 * B / 1024.0,
+                                      "algorithmic_bytes": 2.0 * (B * 16 * 512 + 512 * 4608)}
         if ms1 > 0:
             ach = fl1 / (ms1 * 1e-3) / 1e12
             roof_w = {"kernel": "wgrad_kernel (tcgen05, MN-major)", "bound": "tensor", "achieved": ach,

@@ -10,7 +10,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpassport_sm100.so")
 
-PP_ABI_VERSION = 4
+PP_ABI_VERSION = 5
 PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL = 0, 1, 2
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1
@@ -60,7 +60,7 @@ _PROTOS = {
     "pp_debug_last_timeout": (C.c_int, []),
     "pp_launch_count": (C.c_longlong, [_i]),
     "pp_profile_enable": (C.c_int, [_i]),
-    "pp_profile_read": (C.c_int, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "pp_profile_read": (C.c_int, [_i, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
 }
 
 

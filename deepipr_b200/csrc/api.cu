@@ -27,16 +27,16 @@ static int g_sm_count = -1, g_cc_major = -1, g_cc_minor = -1;
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-struct ProfRec { cudaEvent_t start, stop; double flops; };
+struct ProfRec { cudaEvent_t start, stop; double flops; int c, nout, taps; };
 static bool g_prof_on = false;
 static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof[PROF_KINDS];
 
-void prof_begin(int kind, double flops, cudaStream_t s) {
+void prof_begin(int kind, double flops, int c, int nout, int taps, cudaStream_t s) {
   if (!g_prof_on) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec r;
-  r.flops = flops;
+  r.flops = flops; r.c = c; r.nout = nout; r.taps = taps;
   cudaEventCreate(&r.start);
   cudaEventCreate(&r.stop);
   cudaEventRecord(r.start, s);
@@ -525,23 +525,30 @@ long long pp_launch_count(int reset) {
 int pp_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof_on = on != 0;
+  if (g_prof_on) {  // a new recording session starts empty
+    for (int k = 0; k < PROF_KINDS; ++k) {
+      for (auto& r : g_prof[k]) { cudaEventDestroy(r.start); cudaEventDestroy(r.stop); }
+      g_prof[k].clear();
+    }
+  }
   return PP_OK;
 }
 
-int pp_profile_read(int kind, double* total_ms, double* total_flops, int* launches) {
+int pp_profile_read(int kind, int filter_c, int filter_nout, int filter_taps, double* total_ms,
+                    double* total_flops, int* launches) {
   PP_REQUIRE(kind >= 0 && kind < PROF_KINDS, PP_EBADARG, "unknown profile kind %d", kind);
   std::lock_guard<std::mutex> lk(g_prof_mu);
   double ms = 0.0, fl = 0.0;
   int n = 0;
   for (auto& r : g_prof[kind]) {
     float t = 0.f;
-    if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&t, r.start, r.stop) == cudaSuccess) {
+    const bool match = (filter_c <= 0 || r.c == filter_c) && (filter_nout <= 0 || r.nout == filter_nout) &&
+                       (filter_taps <= 0 || r.taps == filter_taps);
+    if (match && cudaEventSynchronize(r.stop) == cudaSuccess &&
+        cudaEventElapsedTime(&t, r.start, r.stop) == cudaSuccess) {
       ms += t; fl += r.flops; ++n;
     }
-    cudaEventDestroy(r.start);
-    cudaEventDestroy(r.stop);
   }
-  g_prof[kind].clear();
   cudaGetLastError();
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;

@@ -82,7 +82,7 @@ struct TapEpilogue {
 void count_launch();
 // optional per-kernel CUDA-event timing of the two tensor-core kernels (bench.py roofline leg)
 enum { PROF_TAPGEMM = 0, PROF_WGRAD = 1, PROF_KINDS = 2 };
-void prof_begin(int kind, double flops, cudaStream_t s);
+void prof_begin(int kind, double flops, int c, int nout, int taps, cudaStream_t s);
 void prof_end(int kind, cudaStream_t s);
 
 int device_sm_count();

@@ -461,7 +461,7 @@ static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, cons
   PP_REQUIRE(e.stats_partial == nullptr || g.Nout <= kMaxStatsN, PP_EUNSUPPORTED,
              "fused column statistics support Nout <= %d (Nout=%d)", kMaxStatsN, g.Nout);
   const int grid = tapgemm_tcgen05_grid(g);
-  prof_begin(PROF_TAPGEMM, 2.0 * (double)p.M * g.Nout * g.ntaps * g.C, s);
+  prof_begin(PROF_TAPGEMM, 2.0 * (double)p.M * g.Nout * g.ntaps * g.C, g.C, g.Nout, g.ntaps, s);
   tapgemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, p);
   prof_end(PROF_TAPGEMM, s);
   PP_POST_LAUNCH();
@@ -696,7 +696,7 @@ static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, 
   }
   const int m_tiles = (p.Ktot + 127) / 128;
   dim3 grid(m_tiles * p.n_tiles, splits);
-  prof_begin(PROF_WGRAD, 2.0 * (double)M * O * g.ntaps * g.C, s);
+  prof_begin(PROF_WGRAD, 2.0 * (double)M * O * g.ntaps * g.C, g.C, O, g.ntaps, s);
   wgrad_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmX, tmDz, p);
   prof_end(PROF_WGRAD, s);
   PP_POST_LAUNCH();

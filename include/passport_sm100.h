@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 4
+#define PP_ABI_VERSION 5
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -75,7 +75,7 @@ int pp_workspace_bytes(const PPConvDesc* d, int which, size_t* bytes);
 
 /* fp32 OIHW master weight -> bf16 operand copies.
  *   w_fprop: [O, kh, kw, C]           (K-major B operand of the forward implicit GEMM)
- *   w_dgrad: [C, kh, kw, O] flipped   (B operand of the data-gradient GEMM; may be NULL)
+ *   w_dgrad: [C, kh, kw, O]           (B operand of the data-gradient GEMM, taps not flipped; may be NULL)
  * Replaces the implicit weight read of nn.Conv2d (passportconv2d.py:18,218). */
 int pp_weight_prep(const PPConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream);
 
@@ -151,11 +151,14 @@ int pp_debug_last_timeout(void);
 /* Instrumentation used by bench.py.
  *   pp_launch_count   kernels launched by this library since the last reset (the "gpu_launches" claim)
  *   pp_profile_*      when enabled, every tensor-core kernel launch is bracketed by CUDA events on its stream;
- *                     pp_profile_read(kind) sums durations and algorithmic FLOPs (kind 0: implicit-GEMM
- *                     conv / dgrad kernel, kind 1: weight-gradient kernel) and clears the records. */
+ *                     pp_profile_read(kind, ...) sums durations and algorithmic FLOPs of the recorded launches
+ *                     (kind 0: implicit-GEMM conv / dgrad kernel, kind 1: weight-gradient kernel), optionally
+ *                     only those whose GEMM has `filter_c` input channels, `filter_nout` output columns and
+ *                     `filter_taps` taps (<= 0: any).  Enabling starts a fresh recording. */
 long long pp_launch_count(int reset);
 int pp_profile_enable(int on);
-int pp_profile_read(int kind, double* total_ms, double* total_flops, int* launches);
+int pp_profile_read(int kind, int filter_c, int filter_nout, int filter_taps, double* total_ms,
+                    double* total_flops, int* launches);
 
 #ifdef __cplusplus
 }
