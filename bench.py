@@ -247,13 +247,16 @@ def main():
     # ---------------- leg 3: per-kernel roofline of the dominant kernel (CUDA events on its stream)
     roof = None
     roof_w = None
-    if rank == 0 and "roofline" in legs:
-        pk = peaks()
-        lib.pp_profile_enable(1)
+    if "roofline" in legs:
+        # every rank runs the steps (they contain the gradient all-reduce); only rank 0 records kernel events
+        if rank == 0:
+            lib.pp_profile_enable(1)
         for i in range(3):
             runner.step(*dev_batches[i % 4])
-        torch.cuda.synchronize()
+        barrier()
         lib.pp_profile_enable(0)
+    if rank == 0 and "roofline" in legs:
+        pk = peaks()
         def read(kind, c=0, nout=0, taps=0):
             ms, fl, n = C.c_double(0), C.c_double(0), C.c_int(0)
             lib.pp_profile_read(kind, c, nout, taps, C.byref(ms), C.byref(fl), C.byref(n))

@@ -98,6 +98,7 @@ class GradBuckets:
         if members:
             self._close(cur_start, cur_end, members)
         self._pending = [len(m) for (_, _, m) in self.buckets]
+        self._next = 0               # first bucket not yet handed to the communicator
         self._works = []
         self._hooks = []
         if overlap and self.world > 1:
@@ -118,8 +119,10 @@ class GradBuckets:
                 p.grad = view
             b = self.bucket_of[i]
             self._pending[b] -= 1
-            if self._pending[b] == 0:
-                self._launch(b)
+            # collectives must be issued in the same order on every rank: launch strictly in bucket order
+            while self._next < len(self.buckets) and self._pending[self._next] == 0:
+                self._launch(self._next)
+                self._next += 1
         return hook
 
     def _launch(self, b):
@@ -133,13 +136,13 @@ class GradBuckets:
         """Call after backward(): reduce whatever the hooks have not launched yet and wait for everything."""
         if self.world > 1:
             self.flat.ensure_grad_views()
-            for b, pending in enumerate(self._pending):
-                already_launched = self.overlap and pending == 0
-                if not already_launched:       # no overlap mode, or a parameter that got no gradient this step
-                    self._launch(b)
+            while self._next < len(self.buckets):   # no-overlap mode, or parameters that got no gradient this step
+                self._launch(self._next)
+                self._next += 1
             for w in self._works:
                 w.wait()
         self._works = []
+        self._next = 0
         self._pending = [len(m) for (_, _, m) in self.buckets]
 
     def remove_hooks(self):
