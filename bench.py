@@ -287,6 +287,47 @@ def main():
                       "launches_per_step": n1 // 3, "avg_launch_us": ms1 * 1e3 / max(n1, 1),
                       "share_of_step": (ms1 / 3) / (ms_total / args.steps)}
 
+    # ---------------- optional leg: the same step in stock PyTorch eager (cuDNN/cuBLAS, autocast bf16,
+    # channels_last) on this GPU — the oracle mirror moved to the device.  Informational only ("the honest bar",
+    # BASELINE.md §3a); not part of the default run.
+    torch_eager = None
+    if rank == 0 and "torch_eager" in legs:
+        import torch.nn.functional as TF
+        from oracle import passport_oracle as po
+        torch.backends.cudnn.benchmark = True                      # train_v1.py:8 / train_v23.py:8
+        ref = po.mirror(build_model(), round_bf16=False).to(dev).to(memory_format=torch.channels_last).train()
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        rlosses = po.sign_loss_modules(ref)
+
+        def ref_step(x, t):
+            ropt.zero_grad()
+            for m in rlosses:
+                m.reset()
+            loss = torch.zeros((), device=dev)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                for ind in range(2):
+                    loss = loss + TF.cross_entropy(ref(x, ind=ind).float(), t)
+            sl = torch.zeros((), device=dev)
+            for m in rlosses:
+                sl = sl + m.loss
+            (loss + sl).backward()
+            ropt.step()
+
+        xs = [(x.contiguous(memory_format=torch.channels_last), t) for x, t in dev_batches]
+        for i in range(max(3, args.warmup)):
+            ref_step(*xs[i % 4])
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            ref_step(*xs[i % 4])
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ref = e0.elapsed_time(e1)
+        torch_eager = {"value": args.steps * B / (ms_ref * 1e-3), "unit": UNIT, "ms_per_step": ms_ref / args.steps,
+                       "what": "oracle mirror on cuda: torch eager + cuDNN, autocast bf16, channels_last, "
+                               "cudnn.benchmark, torch.optim.SGD(foreach); same batch, inputs resident"}
+        del ref, ropt
+
     sig = test_signature(model) if rank == 0 else {}
     model.train()
 
@@ -305,7 +346,7 @@ def main():
                 "gpu_launches": launches,
                 "roofline": roof, "roofline_wgrad": roof_w,
                 "conv_roofline_frac_whole_step": (value / world) * GFLOP_PER_IMAGE_STEP * 1e9 / (pk["tflops"] * 1e12),
-                "cpu_baseline": cpu_baseline,
+                "cpu_baseline": cpu_baseline, "torch_eager_gpu": torch_eager,
                 "sign_bit_accuracy": (sum(sig.values()) / len(sig)) if sig else None,
                 "last_step": {"acc_public": last[0], "acc_private": last[1], "sign_loss": last[2], "loss": last[3]}}
         print(json.dumps(line))

@@ -158,6 +158,11 @@ BLOCKS = [  # name, kind, i, o, ks, s, pd, norm, N, H   — the passport layers 
     ("imagenet_layer4", "v1", 512, 512, 3, 1, 1, "bn", 4, 7),
     ("conv_layer1", "conv", 64, 64, 3, 1, 1, "bn", 4, 32),
     ("conv_stem", "conv", 3, 64, 3, 1, 1, "bn", 4, 32),
+    ("alexnet_features.0_5x5_c3", "conv", 3, 64, 5, 1, 2, "bn", 4, 32),
+    ("alexnet_features.2_5x5", "conv", 64, 192, 5, 1, 2, "bn", 4, 16),
+    ("imagenet_stem_7x7_s2", "conv", 3, 64, 7, 2, 3, "bn", 2, 64),
+    ("conv_none_bias", "conv", 64, 128, 3, 1, 1, "none", 4, 8),
+    ("private_none", "private", 128, 128, 3, 1, 1, "none", 8, 8),
 ]
 
 
@@ -370,3 +375,41 @@ def test_flat_sgd_matches_torch_sgd():
         opt_ref.step()
         for p, r in zip(ps, ref):
             assert torch.allclose(p, r, rtol=1e-6, atol=1e-7)
+
+
+def test_imagenet_shaped_resnet18_v1_forward_backward():
+    """BASELINE config 5 shape (224x224, 7x7/s2 stem + max-pool, 1000 classes) at a tiny batch: runs through the
+    im2col stem path, 56/28/14/7 feature maps (tile tails), and matches the bf16-operand oracle."""
+    seed_all(0)
+    pk = nets.passport_kwargs_from_config(nets.resnet18_passport_config(), "bn", "random", 0.1)
+    model = quiet(nets.ResNet18, "v1", 1000, pk)
+    with torch.no_grad():
+        for mod in model.modules():
+            if getattr(mod, "KIND", None) == "v1":
+                c = mod.conv.in_channels
+                h = 14 if mod.conv.stride[0] == 2 else 7
+                mod.set_key(bf16r(torch.rand(1, c, h, h) * 2 - 1), bf16r(torch.rand(1, c, h, h) * 2 - 1))
+    x = bf16r(torch.randn(2, 3, 224, 224))
+    t = torch.randint(0, 1000, (2,))
+    oracle = po.mirror(model, round_bf16=True).train()
+    model = model.cuda().train()
+    from deepipr_b200.trainer import StepRunner
+    opt_g = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    opt_o = torch.optim.SGD(oracle.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    loss, sl, preds = StepRunner(model, opt_g, private=False, autocast=False).step(x.cuda(), t.cuda())
+    ref = po.train_step(oracle, opt_o, x, t, private=False)
+    assert abs(loss.item() - ref["loss"]) < 3e-2 * abs(ref["loss"])
+    assert abs(sl.item() - ref["sign_loss"]) < 2e-3 * abs(ref["sign_loss"])
+
+
+def test_batch_one_and_odd_batches():
+    """Edge cases: a single image (M = 16 rows in a 128-row tile) and a batch that is not a multiple of anything."""
+    for N in (1, 7):
+        m = _make_block("private", 512, 512, 3, 1, 1, "bn", 4)
+        x = bf16r(torch.randn(N, 512, 4, 4, generator=torch.Generator().manual_seed(3)))
+        oracle = po.mirror(m, round_bf16=True)
+        ref = _fwd_bwd(oracle, "private", x, "cpu", (0, 1))
+        got = _fwd_bwd(m.cuda(), "private", x, "cuda", (0, 1))
+        for k in range(2):
+            assert rel_l2(got["y"][k], bf16r(ref["y"][k])) < ACT_TOL
+        assert rel_l2(got["dx"], ref["dx"]) < GRAD_TOL
