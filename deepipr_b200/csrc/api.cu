@@ -422,12 +422,13 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
   }
   TapEpilogue e;
   e.out = z; e.out_f32 = d->z_f32; e.scale = nullptr; e.shift = nullptr; e.relu = 0;
-  e.stats_partial = (d->norm == PP_NORM_BN_TRAIN) ? ws.partial : nullptr;
+  const bool fused_stats = d->norm == PP_NORM_BN_TRAIN && d->O <= tapgemm_tcgen05_max_stats_width();
+  e.stats_partial = fused_stats ? ws.partial : nullptr;
   bool tc = false;
   PP_TRY(run_fprop(*d, geo, x, w_fprop, e, &tc, ws.col, ws.wpad, s));
   int num_partials = 0;
   if (d->norm == PP_NORM_BN_TRAIN) {
-    if (tc) {
+    if (tc && fused_stats) {
       TapGemm g;
       plan_fprop(*d, geo, g);
       num_partials = tapgemm_tcgen05_grid(g);
@@ -512,6 +513,22 @@ int pp_sgd_step(size_t n, float* param, const float* grad, float* momentum_buf, 
   PP_REQUIRE(param && grad && (momentum == 0.0f || momentum_buf), PP_EBADARG, "sgd: NULL pointer");
   if (n == 0) return PP_OK;
   return launch_sgd(n, param, grad, momentum_buf, lr, momentum, weight_decay, first_step, (cudaStream_t)stream);
+}
+
+int pp_add_relu_fwd(size_t n, const void* a, const void* b, void* y, void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(a && b && y, PP_EBADARG, "add_relu: NULL pointer");
+  if (n == 0) return PP_OK;
+  return launch_add_relu_fwd((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, n,
+                             (cudaStream_t)stream);
+}
+
+int pp_add_relu_bwd(size_t n, const void* gy, const void* y, void* gx, void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(gy && y && gx, PP_EBADARG, "add_relu bwd: NULL pointer");
+  if (n == 0) return PP_OK;
+  return launch_add_relu_bwd((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (__nv_bfloat16*)gx, n,
+                             (cudaStream_t)stream);
 }
 
 int pp_debug_last_timeout(void) { return debug_last_timeout(); }

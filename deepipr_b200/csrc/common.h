@@ -92,6 +92,7 @@ int check_device();  // PP_OK iff current device is sm_100
 int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapEpilogue& e, cudaStream_t s);
 bool tapgemm_tcgen05_supported(const TapGemm& g);
 int tapgemm_tcgen05_grid(const TapGemm& g);  // CTAs launched == rows of stats_partial written
+int tapgemm_tcgen05_max_stats_width();       // widest Nout for which the fused column statistics are available
 int debug_last_timeout();
 // wgrad: partial[split][Mo][T*C] (fp32) = sum over a slice of pixels of dz[m, o] * act_tap[m, c]
 int wgrad_tcgen05(const TapGemm& g /*fprop geometry of x*/, const void* x, const void* dz, int O, float* partial,
@@ -141,6 +142,8 @@ int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits,
 int launch_im2col_small(const PPConvDesc& d, const __nv_bfloat16* x, __nv_bfloat16* col, size_t rows, int P, int Q,
                         int Kpad, cudaStream_t s);
 int launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int K, int Kpad, cudaStream_t s);
+int launch_add_relu_fwd(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, size_t n, cudaStream_t s);
+int launch_add_relu_bwd(const __nv_bfloat16* g, const __nv_bfloat16* y, __nv_bfloat16* gx, size_t n, cudaStream_t s);
 int launch_sgd(size_t n, float* p, const float* g, float* buf, float lr, float mom, float wd, int first,
                cudaStream_t s);
 

@@ -18,6 +18,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace pp {
@@ -100,6 +102,51 @@ static int make_map_im2col(CUtensorMap* m, const void* ptr, const TapGemm& g, ui
   return PP_OK;
 }
 
+// When a tile of `pixels` traversal positions is a whole number of image rows / images (stride 1, power-of-two
+// feature maps: every CIFAR-shaped layer), the same shared-memory image is produced by an ordinary TILED 4-D box
+// {64 ch, Q, rows, images} whose start coordinate is shifted by the filter tap; out-of-bound parts (padding,
+// batch tail) are zero-filled exactly as in im2col mode.  Returns false when the geometry does not fit.
+static bool tiled_box_for(const TapGemm& g, int pixels, int* bw, int* bh, int* bn) {
+  if (g.step_h != 1 || g.step_w != 1) return false;
+  const int PQ = g.P * g.Q;
+  if (g.Q > pixels || pixels % g.Q != 0) return false;
+  if (!((PQ % pixels == 0) || (pixels % PQ == 0))) return false;
+  *bw = g.Q;
+  if (PQ >= pixels) { *bh = pixels / g.Q; *bn = 1; }
+  else { *bh = g.P; *bn = pixels / PQ; }
+  if (*bw > 256 || *bh > 256 || *bn > 256) return false;
+  return true;
+}
+
+static int make_map_tiled4d(CUtensorMap* m, const void* ptr, const TapGemm& g, int bw, int bh, int bn) {
+  cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d) NHWC=%d,%d,%d,%d box=%d,%d,%d", (int)r, g.N, g.H, g.W, g.C, bw,
+              bh, bn);
+    return PP_ELAUNCH;
+  }
+  return PP_OK;
+}
+
+static bool g_prefer_tiled = true;   // PP_TMA_IM2COL_ONLY=1 forces the im2col-mode loads (A/B comparison)
+static bool prefer_tiled() {
+  static bool init = false;
+  if (!init) {
+    const char* e = getenv("PP_TMA_IM2COL_ONLY");
+    g_prefer_tiled = !(e && e[0] == '1');
+    const char* t = getenv("PP_TMA_TILED");   // default: im2col mode (validated on every geometry); =1 tries tiled boxes
+    g_prefer_tiled = (t && t[0] == '1');
+    init = true;
+  }
+  return g_prefer_tiled;
+}
+
 // ------------------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------------------
@@ -137,6 +184,9 @@ struct TapGemmDev {
   int Nout;
   int num_m_tiles, num_n_tiles;
   int out_H, out_W, out_sh, out_sw, out_ph, out_pw, out_identity;
+  int a_tiled;      // 1: activation tiles are loaded with a tiled 4-D box instead of im2col mode
+  int dbg;          // bring-up switches (PP_DEBUG env): 1 skip global stores, 2 skip statistics, 4 skip TMEM loads,
+                    // 8 skip the MMA instructions, 16 skip the TMA loads (results are garbage; timing experiments only)
   int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
   int tap_kofs[kMaxTaps];
   // epilogue
@@ -151,38 +201,49 @@ struct TapGemmDev {
 constexpr int kBM = 128;       // output pixels per tile (UMMA M)
 constexpr int kBK = 64;        // channels per pipeline stage (one 128-byte swizzle row of bf16)
 constexpr int kThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM owner, warps 2..5 epilogue
-constexpr int kMaxStatsN = 1024;  // widest output for which the fused column statistics are kept in smem
+constexpr int kMaxStatsN = 512;   // widest output for which the fused column statistics are kept in smem
 
-template <int BN>
+constexpr int kResMaxSteps = 9;   // resident-weight variant: at most 9 (tap, channel-chunk) blocks of BN x 64
+
+// RESB: the whole weight matrix (one n tile, <= 9 k-steps) is loaded into shared memory once per CTA and stays
+// there for all of its tiles; the pipeline stages then carry activation tiles only.  For the 64-channel layers
+// this removes a third of the L2->smem traffic and the 148-way hot spot on the same 72 KiB of weights.
+template <int BN, bool RESB = false>
 struct FwdCfg {
   static constexpr int kStageA = kBM * kBK * 2;  // 16 KiB
   static constexpr int kStageB = BN * kBK * 2;
-  static constexpr int kStageBytes = kStageA + kStageB;
-  static constexpr int kStages = (BN == 64) ? 8 : (BN == 128 ? 6 : 4);
+  static constexpr int kStageBytes = RESB ? kStageA : kStageA + kStageB;
+  static constexpr int kResBytes = RESB ? kResMaxSteps * kStageB : 0;
+  static constexpr int kStages = RESB ? 8 : ((BN == 64) ? 8 : (BN == 128 ? 6 : 4));
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
   static constexpr int kScratch = 2 * BN * 4 /*a,b*/ + 4 * 2 * BN * 4 /*per-warp column sums*/ +
-                                  2 * kMaxStatsN * 4 /*per-CTA running column sums*/;
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kScratch + 256 /*barriers*/;
+                                  2 * kMaxStatsN * 4 /*per-CTA running column sums*/ +
+                                  4 * 4096 /*per-warp store staging tiles*/;
+  static constexpr int kSmemBytes =
+      1024 /*align slack*/ + kResBytes + kStages * kStageBytes + kScratch + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, bool RESB>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TapGemmDev p) {
-  using Cfg = FwdCfg<BN>;
+  using Cfg = FwdCfg<BN, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;
-  float* s_a = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* res_base = smem;                       // [ksteps][BN x 64] resident weight blocks (RESB only)
+  uint8_t* stage_base = smem + Cfg::kResBytes;
+  float* s_a = reinterpret_cast<float*>(stage_base + Cfg::kStages * Cfg::kStageBytes);
   float* s_b = s_a + BN;
   float* s_red = s_b + BN;            // [4 warps][2][BN]
   float* s_acc = s_red + 4 * 2 * BN;  // [2][Nout] running per-CTA column sums (sum z, sum z^2)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_acc + 2 * kMaxStatsN);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_acc + 2 * kMaxStatsN);  // [4 warps][4 KiB], 16-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * 4096);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tempty = tfull + 2;                // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bres = tempty + 2;                 // [1] resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -201,6 +262,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
     }
+    mbar_init(bres, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -215,6 +277,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (RESB) {
+        // all weight blocks once: block ks = (tap t, channel chunk kc) in main-loop order
+        mbar_arrive_expect_tx(bres, (uint32_t)ksteps * Cfg::kStageB);
+        for (int t = 0; t < p.ntaps; ++t)
+          for (int kc = 0; kc < kchunks; ++kc)
+            tma_load_2d(&tmB, bres, res_base + (t * kchunks + kc) * Cfg::kStageB, p.tap_kofs[t] + kc * kBK, 0);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -235,9 +304,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
             uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kStageA;
+            if (p.dbg & 16) {   // bring-up: no loads at all, just hand the (stale) stage to the MMA warp
+              mbar_arrive(&full[stage]);
+              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            tma_load_im2col_4d(&tmA, &full[stage], sa, kc * kBK, cw, ch, img, dw, dh);
-            tma_load_2d(&tmB, &full[stage], sb, kofs + kc * kBK, n_tile * BN);
+            if (p.a_tiled) tma_load_4d(&tmA, &full[stage], sa, kc * kBK, cw + dw, ch + dh, img);
+            else tma_load_im2col_4d(&tmA, &full[stage], sa, kc * kBK, cw, ch, img, dw, dh);
+            if (!RESB) tma_load_2d(&tmB, &full[stage], sb, kofs + kc * kBK, n_tile * BN);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -251,6 +326,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (RESB) mbar_wait(bres, 0, 250);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
@@ -259,12 +335,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full[stage], phase, 300 + stage);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kStageA;
+          const uint32_t sb = RESB ? smem_u32(res_base + ks * Cfg::kStageB) : sa + Cfg::kStageA;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            tc_mma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+            if (!(p.dbg & 8)) tc_mma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
           }
           tc_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -315,18 +391,24 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     (size_t)(qq_ * p.out_sw + p.out_pw);
         }
       }
+      const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
       mbar_wait(&tfull[acc], acc_phase, 400 + acc);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
         uint32_t raw[32];
-        tmem_ld_32x32(taddr + j * 32, raw);
-        tmem_ld_wait();
+        if (p.dbg & 4) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = 0x3f800000u;
+        } else {
+          tmem_ld_32x32(taddr + j * 32, raw);
+          tmem_ld_wait();
+        }
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(raw[i]) : 0.0f;
-        if (has_stats) {
+        if (has_stats && !(p.dbg & 2)) {
           float t1[32], t2[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -346,24 +428,45 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
-        if (valid) {
-          if (p.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_row * p.Nout + n0 + j * 32);
+        // Store through a per-warp staging tile so that every store instruction writes whole 128-byte lines
+        // (a lane owns a ROW of the accumulator; writing it directly would touch 32 different lines per store).
+        if (p.dbg & 1) continue;
+        if (p.out_f32) {
+          float4* st = reinterpret_cast<float4*>(s_stage + ew * 4096);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.Nout + n0 +
-                                                  j * 32);
+          for (int i = 0; i < 8; ++i)
+            st[lane * 8 + (i ^ (lane & 7))] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          __syncwarp();
+          float* obase = reinterpret_cast<float*>(p.out) + n0 + j * 32 + (lane & 7) * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-              u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-              u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-              u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-              dst[i] = u;
-            }
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3);
+            const float4 val = st[r * 8 + ((lane & 7) ^ (r & 7))];
+            const long long orow = __shfl_sync(0xffffffffu, (long long)out_row, r);
+            if ((valid_mask >> r) & 1u) *reinterpret_cast<float4*>(obase + (size_t)orow * p.Nout) = val;
           }
+          __syncwarp();
+        } else {
+          uint4* st = reinterpret_cast<uint4*>(s_stage + ew * 4096);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+            st[lane * 4 + (i ^ ((lane >> 1) & 3))] = u;
+          }
+          __syncwarp();
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + n0 + j * 32 + (lane & 3) * 8;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2);
+            const uint4 val = st[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
+            const long long orow = __shfl_sync(0xffffffffu, (long long)out_row, r);
+            if ((valid_mask >> r) & 1u) *reinterpret_cast<uint4*>(obase + (size_t)orow * p.Nout) = val;
+          }
+          __syncwarp();
         }
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -423,6 +526,8 @@ static int pick_bn(const TapGemm& g) {
   return 64;
 }
 
+int tapgemm_tcgen05_max_stats_width() { return kMaxStatsN; }
+
 int tapgemm_tcgen05_grid(const TapGemm& g) {
   const int bn = pick_bn(g);
   const long long M = (long long)g.N * g.P * g.Q;
@@ -431,13 +536,22 @@ int tapgemm_tcgen05_grid(const TapGemm& g) {
   return (int)(tiles < sms ? tiles : sms);
 }
 
-template <int BN>
+template <int BN, bool RESB>
 static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, const TapEpilogue& e, cudaStream_t s) {
-  using Cfg = FwdCfg<BN>;
+  using Cfg = FwdCfg<BN, RESB>;
   CUtensorMap tmA, tmB;
-  PP_TRY(make_map_im2col(&tmA, act, g, kBM));
+  int bw = 0, bh = 0, bn = 0;
+  const bool a_tiled = prefer_tiled() && tiled_box_for(g, kBM, &bw, &bh, &bn);
+  if (a_tiled) PP_TRY(make_map_tiled4d(&tmA, act, g, bw, bh, bn));
+  else PP_TRY(make_map_im2col(&tmA, act, g, kBM));
   PP_TRY(make_map_2d(&tmB, B, (uint64_t)g.Nout, (uint64_t)g.Ktot, BN));
   TapGemmDev p;
+  p.a_tiled = a_tiled ? 1 : 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("PP_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
   p.M = g.N * g.P * g.Q;
   p.P = g.P; p.Q = g.Q; p.PQ = g.P * g.Q;
   p.base_h = g.base_h; p.base_w = g.base_w; p.step_h = g.step_h; p.step_w = g.step_w;
@@ -454,7 +568,7 @@ static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, cons
 
   static bool attr_set = false;
   if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PP_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -462,7 +576,7 @@ static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, cons
              "fused column statistics support Nout <= %d (Nout=%d)", kMaxStatsN, g.Nout);
   const int grid = tapgemm_tcgen05_grid(g);
   prof_begin(PROF_TAPGEMM, 2.0 * (double)p.M * g.Nout * g.ntaps * g.C, g.C, g.Nout, g.ntaps, s);
-  tapgemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, p);
+  tapgemm_kernel<BN, RESB><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, p);
   prof_end(PROF_TAPGEMM, s);
   PP_POST_LAUNCH();
   return PP_OK;
@@ -473,9 +587,11 @@ int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapE
   PP_REQUIRE(tapgemm_tcgen05_supported(g), PP_EUNSUPPORTED,
              "tcgen05 tap-GEMM needs C%%64==0 and Nout%%64==0 (C=%d Nout=%d)", g.C, g.Nout);
   switch (pick_bn(g)) {
-    case 256: return launch_tapgemm<256>(g, act, B, e, s);
-    case 128: return launch_tapgemm<128>(g, act, B, e, s);
-    default: return launch_tapgemm<64>(g, act, B, e, s);
+    case 256: return launch_tapgemm<256, false>(g, act, B, e, s);
+    case 128: return launch_tapgemm<128, false>(g, act, B, e, s);
+    default:
+      if (g.Nout == 64 && g.ntaps * (g.C / kBK) <= kResMaxSteps) return launch_tapgemm<64, true>(g, act, B, e, s);
+      return launch_tapgemm<64, false>(g, act, B, e, s);
   }
 }
 
@@ -505,6 +621,7 @@ struct WgradDev {
   int base_h, base_w, step_h, step_w;
   int C, O, ntaps, Ktot;   // Ktot = ntaps * C = rows of the transposed gradient
   int n_tiles;             // O / BN
+  int x_tiled;             // 1: x slabs are loaded with a tiled 4-D box instead of im2col mode
   int chunks_total, chunks_per_split;
   int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
   float* partial;  // [splits][O][Ktot]
@@ -576,8 +693,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kStageA;
         mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-        tma_load_im2col_4d(&tmX, &full[stage], sa, c0, cw, chh, img, dw0, dh0);
-        tma_load_im2col_4d(&tmX, &full[stage], sa + kWK * 128, c1, cw, chh, img, dw1, dh1);
+        if (p.x_tiled) {
+          tma_load_4d(&tmX, &full[stage], sa, c0, cw + dw0, chh + dh0, img);
+          tma_load_4d(&tmX, &full[stage], sa + kWK * 128, c1, cw + dw1, chh + dh1, img);
+        } else {
+          tma_load_im2col_4d(&tmX, &full[stage], sa, c0, cw, chh, img, dw0, dh0);
+          tma_load_im2col_4d(&tmX, &full[stage], sa + kWK * 128, c1, cw, chh, img, dw1, dh1);
+        }
 #pragma unroll
         for (int i = 0; i < BN / 64; ++i)
           tma_load_2d(&tmDz, &full[stage], sb + i * kWK * 128, n_tile * BN + i * 64, m0);
@@ -678,8 +800,12 @@ static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, 
   CUtensorMap tmDz, tmX;
   const long long M = (long long)g.N * g.P * g.Q;
   PP_TRY(make_map_2d(&tmDz, dz, (uint64_t)M, (uint64_t)O, kWK));
-  PP_TRY(make_map_im2col(&tmX, x, g, kWK));
+  int bw = 0, bh = 0, bn = 0;
+  const bool x_tiled = prefer_tiled() && tiled_box_for(g, kWK, &bw, &bh, &bn);
+  if (x_tiled) PP_TRY(make_map_tiled4d(&tmX, x, g, bw, bh, bn));
+  else PP_TRY(make_map_im2col(&tmX, x, g, kWK));
   WgradDev p;
+  p.x_tiled = x_tiled ? 1 : 0;
   p.M = (int)M; p.P = g.P; p.Q = g.Q; p.PQ = g.P * g.Q;
   p.base_h = g.base_h; p.base_w = g.base_w; p.step_h = g.step_h; p.step_w = g.step_w;
   p.C = g.C; p.O = O; p.ntaps = g.ntaps; p.Ktot = g.ntaps * g.C;

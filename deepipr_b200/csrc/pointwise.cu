@@ -651,6 +651,57 @@ int launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// residual join of the ResNet basic block: y = relu(a + b), and its backward g * [y > 0] (one gradient tensor
+// serves both inputs).  Replaces the add + relu (+ threshold_backward) ATen launches of
+// models/resnet_passport_private.py:78-85.  bf16 tensors, 8 elements per thread, scalar tail.
+// ---------------------------------------------------------------------------------------------
+__global__ void add_relu_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                    __nv_bfloat16* __restrict__ y, size_t n) {
+  const size_t nvec = n >> 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float va[8], vb[8];
+    load8_bf16(a, i, va);
+    load8_bf16(b, i, vb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) va[k] = fmaxf(va[k] + vb[k], 0.0f);
+    store8_bf16(y, i, va);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (nvec << 3) + threadIdx.x;
+    y[i] = __float2bfloat16_rn(fmaxf(__bfloat162float(a[i]) + __bfloat162float(b[i]), 0.0f));
+  }
+}
+
+__global__ void add_relu_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                    __nv_bfloat16* __restrict__ gx, size_t n) {
+  const size_t nvec = n >> 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float vg[8], vy[8];
+    load8_bf16(g, i, vg);
+    load8_bf16(y, i, vy);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vg[k] = vy[k] > 0.0f ? vg[k] : 0.0f;
+    store8_bf16(gx, i, vg);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (nvec << 3) + threadIdx.x;
+    gx[i] = __bfloat162float(y[i]) > 0.0f ? g[i] : __float2bfloat16_rn(0.0f);
+  }
+}
+
+int launch_add_relu_fwd(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, size_t n, cudaStream_t s) {
+  add_relu_fwd_kernel<<<grid_for(n / 8 + 1, 256, 148 * 8), 256, 0, s>>>(a, b, y, n);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
+int launch_add_relu_bwd(const __nv_bfloat16* g, const __nv_bfloat16* y, __nv_bfloat16* gx, size_t n, cudaStream_t s) {
+  add_relu_bwd_kernel<<<grid_for(n / 8 + 1, 256, 148 * 8), 256, 0, s>>>(g, y, gx, n);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // SGD with momentum and weight decay on a flat fp32 buffer (torch.optim.SGD semantics,
 // dampening 0, no nesterov — experiments/classification.py:47-50)
 // ---------------------------------------------------------------------------------------------

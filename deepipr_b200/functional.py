@@ -319,6 +319,38 @@ def conv_block(x, weight, gamma, beta, prepared: PreparedWeight, opts: BlockOpts
     return _ConvBlockFn.apply(x, weight, gamma, beta, prepared, opts)
 
 
+class _AddReluFn(torch.autograd.Function):
+    """y = relu(a + b) for the residual join of a basic block (resnet_passport_private.py:78-85)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        y = torch.empty_like(a)
+        L.check(L.load().pp_add_relu_fwd(C.c_size_t(a.numel()), L.ptr(a), L.ptr(b), L.ptr(y), _stream()),
+                "pp_add_relu_fwd")
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        if gy.stride() != y.stride() or gy.dtype != y.dtype:
+            gy = gy.to(y.dtype).contiguous(memory_format=torch.channels_last) if y.dim() == 4 and \
+                y.is_contiguous(memory_format=torch.channels_last) else gy.to(y.dtype).contiguous()
+        gx = torch.empty_like(y)
+        L.check(L.load().pp_add_relu_bwd(C.c_size_t(y.numel()), L.ptr(gy), L.ptr(y), L.ptr(gx), _stream()),
+                "pp_add_relu_bwd")
+        return gx, gx
+
+
+def add_relu(a, b):
+    """relu(a + b); fused kernel for dense bf16 tensors of identical layout, torch ops otherwise."""
+    if (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape == b.shape
+            and a.stride() == b.stride()
+            and (a.is_contiguous() or (a.dim() == 4 and a.is_contiguous(memory_format=torch.channels_last)))):
+        return _AddReluFn.apply(a, b)
+    return torch.relu(a + b)
+
+
 # ---------------------------------------------------------------- raw building blocks (tests / profiling)
 def conv_fwd_raw(x, prepared: PreparedWeight, spec: ConvSpec, z_f32=False, algo=None):
     require_cuda(x, "input")

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 5
+#define PP_ABI_VERSION 6
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -139,6 +139,12 @@ int pp_conv_fwd_raw(const PPConvDesc* d, const void* x, const void* w_fprop, voi
 int pp_conv_dgrad(const PPConvDesc* d, const void* dz, const void* w_dgrad, void* dx, void* stream);
 int pp_conv_wgrad(const PPConvDesc* d, const void* dz, const void* x, float* dw_oihw, void* workspace,
                   size_t ws_bytes, void* stream);
+
+/* Residual join of a ResNet basic block (models/resnet_passport_private.py:78-85, resnet_passport.py:77-84,
+ * resnet_normal.py:24-26): y = relu(a + b) on bf16 tensors of n elements, and its backward
+ * gx = gy * [y > 0] (the same gradient flows to both inputs). */
+int pp_add_relu_fwd(size_t n, const void* a, const void* b, void* y, void* stream);
+int pp_add_relu_bwd(size_t n, const void* gy, const void* y, void* gx, void* stream);
 
 /* Fused SGD(momentum, weight decay) step on one flat fp32 buffer (classification.py:47-50):
  *   g' = g + wd*p;  buf = mom*buf + g' (buf = g' on the first step);  p -= lr*buf */
