@@ -10,7 +10,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpassport_sm100.so")
 
-PP_ABI_VERSION = 6
+PP_ABI_VERSION = 7
 PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL = 0, 1, 2
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1
@@ -21,7 +21,7 @@ EXPORTS = (
     "pp_passport_affine_fwd", "pp_passport_affine_bwd", "pp_sign_loss_fwd", "pp_sign_loss_bwd",
     "pp_conv_block_fwd", "pp_conv_block_bwd", "pp_conv_fwd_raw", "pp_conv_dgrad", "pp_conv_wgrad",
     "pp_sgd_step", "pp_debug_last_timeout", "pp_launch_count", "pp_profile_enable", "pp_profile_read",
-    "pp_add_relu_fwd", "pp_add_relu_bwd",
+    "pp_add_relu_fwd", "pp_add_relu_bwd", "pp_passport_key_grad",
 )
 
 
@@ -50,6 +50,7 @@ _PROTOS = {
     "pp_key_pool": (C.c_int, [_desc, _i, _fp, _dp, _vp]),
     "pp_passport_affine_fwd": (C.c_int, [_desc, _vp, _dp, _dp, _fp, _f, _fp, _fp, _fp, _fp, _vp]),
     "pp_passport_affine_bwd": (C.c_int, [_desc, _dp, _dp, _fp, _fp, _f, _fp, _fp, _fp, _fp, _i, _vp]),
+    "pp_passport_key_grad": (C.c_int, [_desc, _i, _vp, _fp, _fp, _f, _fp, _fp, _fp, _dp, _fp, _fp, _vp]),
     "pp_sign_loss_fwd": (C.c_int, [_i, _fp, _fp, _f, _fp, _fp, _vp]),
     "pp_sign_loss_bwd": (C.c_int, [_i, _fp, _fp, _f, _fp, _fp, _vp]),
     "pp_conv_block_fwd": (C.c_int, [_desc, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp, _sz, _vp]),

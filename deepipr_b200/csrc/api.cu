@@ -383,6 +383,19 @@ int pp_passport_affine_bwd(const PPConvDesc* d, const double* S_skey, const doub
                                     accumulate, (cudaStream_t)stream);
 }
 
+int pp_passport_key_grad(const PPConvDesc* d, int Bk, const void* w_fprop, const float* gamma, const float* b_sign,
+                         float alpha, const float* g_gamma, const float* g_beta, const float* g_loss,
+                         double* scratch, float* dskey_nchw, float* dkey_nchw, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  PP_REQUIRE(w_fprop && scratch && Bk > 0, PP_EBADARG, "passport key grad: NULL pointer");
+  PP_REQUIRE(!(g_loss && b_sign) || gamma, PP_EBADARG, "passport key grad: gamma needed for the sign-loss term");
+  const int K = geo.T * d->C;
+  return launch_passport_key_grad(*d, Bk, (const __nv_bfloat16*)w_fprop, gamma, b_sign, alpha, g_gamma, g_beta, g_loss,
+                                  scratch, scratch + K, dskey_nchw, dkey_nchw, (cudaStream_t)stream);
+}
+
 int pp_sign_loss_fwd(int O, const float* gamma, const float* b_sign, float alpha, float* sign_loss, float* sign_acc,
                      void* stream) {
   PP_TRY(check_device());

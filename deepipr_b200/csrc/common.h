@@ -114,6 +114,9 @@ int launch_passport_affine_fwd(const PPConvDesc& d, const __nv_bfloat16* wf, con
 int launch_passport_affine_bwd(const PPConvDesc& d, const double* Ss, const double* Sk, const float* gamma,
                                const float* b, float alpha, const float* gg, const float* gb, const float* gl,
                                float* dw, int accumulate, cudaStream_t s);
+int launch_passport_key_grad(const PPConvDesc& d, int Bk, const __nv_bfloat16* wf, const float* gamma, const float* b,
+                             float alpha, const float* gg, const float* gb, const float* gl, double* dSs, double* dSk,
+                             float* dskey, float* dkey, cudaStream_t s);
 int launch_sign_loss_fwd(int O, const float* gamma, const float* b, float alpha, float* loss, float* acc,
                          cudaStream_t s);
 int launch_sign_loss_bwd(int O, const float* gamma, const float* b, float alpha, const float* gl, float* gg,

@@ -231,6 +231,72 @@ __device__ __forceinline__ bool reduce_partials_32x32(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// gradients w.r.t. the passport keys (passport_attack_3.py:232-270 optimises them as Parameters):
+//   dS_s[k] = sum_o cg[o] * W[o,k],  dS_k[k] = sum_o cb[o] * W[o,k]     (cg includes the sign-loss term)
+//   dkey[b,c,h,w] = 1/(Bk*P*Q) * sum over taps (r,s) that read pixel (h,w) of dS[(r,s), c]
+// ---------------------------------------------------------------------------------------------
+__global__ void passport_key_grad_gemv_kernel(const __nv_bfloat16* __restrict__ wf, const float* __restrict__ gamma,
+                                              const float* __restrict__ b, float alpha,
+                                              const float* __restrict__ gg, const float* __restrict__ gb,
+                                              const float* __restrict__ gl, double* __restrict__ dSs,
+                                              double* __restrict__ dSk, int O, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double as = 0.0, ak = 0.0;
+  for (int o = 0; o < O; ++o) {
+    float cg = gg ? gg[o] : 0.0f;
+    if (gl && b) cg += (*gl) * sign_loss_grad(gamma[o], b[o], alpha);
+    const float cb = gb ? gb[o] : 0.0f;
+    const double w = (double)__bfloat162float(wf[(size_t)o * K + k]);
+    as = fma((double)cg, w, as);
+    ak = fma((double)cb, w, ak);
+  }
+  dSs[k] = as;
+  dSk[k] = ak;
+}
+
+__global__ void key_unpool_kernel(const double* __restrict__ dS, float* __restrict__ dkey, int Bk, int C, int H, int W,
+                                  int kh, int kw, int stride, int pad, int P, int Q) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = Bk * C * H * W;
+  if (idx >= total) return;
+  const int w = idx % W;
+  const int h = (idx / W) % H;
+  const int c = (idx / (W * H)) % C;
+  double acc = 0.0;
+  for (int r = 0; r < kh; ++r) {
+    const int hp = h + pad - r;
+    if (hp < 0 || hp % stride != 0 || hp / stride >= P) continue;
+    for (int sx = 0; sx < kw; ++sx) {
+      const int wp = w + pad - sx;
+      if (wp < 0 || wp % stride != 0 || wp / stride >= Q) continue;
+      acc += dS[(r * kw + sx) * C + c];
+    }
+  }
+  dkey[idx] = (float)(acc / ((double)Bk * P * Q));
+}
+
+int launch_passport_key_grad(const PPConvDesc& d, int Bk, const __nv_bfloat16* wf, const float* gamma, const float* b,
+                             float alpha, const float* gg, const float* gb, const float* gl, double* dSs, double* dSk,
+                             float* dskey, float* dkey, cudaStream_t s) {
+  const int K = d.kh * d.kw * d.C;
+  const int P = (d.H + 2 * d.pad - d.kh) / d.stride + 1;
+  const int Q = (d.W + 2 * d.pad - d.kw) / d.stride + 1;
+  passport_key_grad_gemv_kernel<<<(K + 127) / 128, 128, 0, s>>>(wf, gamma, b, alpha, gg, gb, gl, dSs, dSk, d.O, K);
+  PP_POST_LAUNCH();
+  const int total = Bk * d.C * d.H * d.W;
+  if (dskey) {
+    key_unpool_kernel<<<(total + 127) / 128, 128, 0, s>>>(dSs, dskey, Bk, d.C, d.H, d.W, d.kh, d.kw, d.stride, d.pad, P, Q);
+    PP_POST_LAUNCH();
+  }
+  if (dkey) {
+    key_unpool_kernel<<<(total + 127) / 128, 128, 0, s>>>(dSk, dkey, Bk, d.C, d.H, d.W, d.kh, d.kw, d.stride, d.pad, P, Q);
+    PP_POST_LAUNCH();
+  }
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // BatchNorm finalise: partial[num][2][O] -> mean, invstd, running stats, affine coefficients
 //   y = a*z + b,  a = gamma*invstd,  b = beta - a*mean   (gamma*bn(z)+beta, passportconv2d.py:219-220)
 // ---------------------------------------------------------------------------------------------

@@ -141,6 +141,7 @@ class AffineCtx:
     S_key: torch.Tensor
     b: Optional[torch.Tensor]
     alpha: float
+    key_shape: Optional[tuple] = None      # (Bk, C, H, W) when gradients w.r.t. the keys are wanted
 
 
 class _PassportAffineFn(torch.autograd.Function):
@@ -148,7 +149,7 @@ class _PassportAffineFn(torch.autograd.Function):
     (reference: passportconv2d.py:142-175, sign_loss.py:32-54)."""
 
     @staticmethod
-    def forward(ctx, weight, actx: AffineCtx):
+    def forward(ctx, weight, actx: AffineCtx, skey=None, key=None):
         dev = weight.device
         O = actx.spec.O
         gamma = torch.empty(O, dtype=torch.float32, device=dev)
@@ -181,16 +182,33 @@ class _PassportAffineFn(torch.autograd.Function):
 
         g_gamma, g_beta, g_loss = f32(g_gamma), f32(g_beta), f32(g_loss)
         d, _ = make_desc(actx.spec, 1, actx.spec.kh, actx.spec.kw)
-        L.check(L.load().pp_passport_affine_bwd(
-            C.byref(d), L.ptr(actx.S_skey), L.ptr(actx.S_key), L.ptr(gamma), L.ptr(actx.b), float(actx.alpha),
-            L.ptr(g_gamma), L.ptr(g_beta), L.ptr(g_loss), L.ptr(dw), 0, _stream()), "pp_passport_affine_bwd")
-        return dw, None
+        if ctx.needs_input_grad[0]:
+            L.check(L.load().pp_passport_affine_bwd(
+                C.byref(d), L.ptr(actx.S_skey), L.ptr(actx.S_key), L.ptr(gamma), L.ptr(actx.b), float(actx.alpha),
+                L.ptr(g_gamma), L.ptr(g_beta), L.ptr(g_loss), L.ptr(dw), 0, _stream()), "pp_passport_affine_bwd")
+        else:
+            dw = None
+        dskey = dkey = None
+        want_s = len(ctx.needs_input_grad) > 2 and ctx.needs_input_grad[2]
+        want_k = len(ctx.needs_input_grad) > 3 and ctx.needs_input_grad[3]
+        if want_s or want_k:
+            Bk, Ck, H, W = actx.key_shape
+            dk, _ = make_desc(actx.spec, 1, H, W)
+            scratch = torch.empty(2 * actx.spec.kh * actx.spec.kw * actx.spec.C, dtype=torch.float64, device=dev)
+            dskey = torch.empty(actx.key_shape, dtype=torch.float32, device=dev) if want_s else None
+            dkey = torch.empty(actx.key_shape, dtype=torch.float32, device=dev) if want_k else None
+            L.check(L.load().pp_passport_key_grad(
+                C.byref(dk), int(Bk), L.ptr(actx.prepared.wf), L.ptr(gamma), L.ptr(actx.b), float(actx.alpha),
+                L.ptr(g_gamma), L.ptr(g_beta), L.ptr(g_loss), L.ptr(scratch), L.ptr(dskey), L.ptr(dkey), _stream()),
+                "pp_passport_key_grad")
+        return dw, None, dskey, dkey
 
 
-def passport_affine(weight, actx: AffineCtx):
-    """Returns (gamma[O], beta[O], sign_loss or None, sign_acc or None)."""
+def passport_affine(weight, actx: AffineCtx, skey=None, key=None):
+    """Returns (gamma[O], beta[O], sign_loss or None, sign_acc or None).  Pass `skey` / `key` only when they
+    require grad (they are then differentiated through the pooled-key identity)."""
     require_cuda(weight, "conv weight")
-    out = _PassportAffineFn.apply(weight, actx)
+    out = _PassportAffineFn.apply(weight, actx, skey, key)
     if len(out) == 2:
         return out[0], out[1], None, None
     return out

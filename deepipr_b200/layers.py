@@ -307,15 +307,21 @@ class _PassportBase(nn.Module, _FusedConvMixin):
     def _passport_affine(self, loss_module):
         """(gamma, beta) from the passport; feeds ``loss_module`` exactly as get_scale does in the reference."""
         self._check_conv()
-        key = getattr(self, self._KEY)
-        if isinstance(key, nn.Parameter) and key.requires_grad:
-            raise RuntimeError("deepipr_b200: gradients w.r.t. the passport keys are not built yet (SURVEY 8f-3)")
+        key, skey = getattr(self, self._KEY), getattr(self, self._SKEY)
         S_skey, S_key = self._pooled_keys()
         b = loss_module.b if loss_module is not None else None
         alpha = loss_module.alpha if loss_module is not None else 0.0
+        # passport_attack_3.py turns the keys into Parameters: differentiate through the pooled-key identity
+        keys_need_grad = torch.is_grad_enabled() and (key.requires_grad or skey.requires_grad)
         actx = F_.AffineCtx(self._spec(), self._prepared(), S_skey, S_key,
-                            None if b is None else b.detach().reshape(-1).float().contiguous(), float(alpha))
-        gamma, beta, loss, acc = F_.passport_affine(self.weight, actx)
+                            None if b is None else b.detach().reshape(-1).float().contiguous(), float(alpha),
+                            tuple(key.shape) if keys_need_grad else None)
+        if keys_need_grad:
+            if key.shape != skey.shape:
+                raise RuntimeError("deepipr_b200: key and skey must have the same shape to be optimised")
+            gamma, beta, loss, acc = F_.passport_affine(self.weight, actx, skey, key)
+        else:
+            gamma, beta, loss, acc = F_.passport_affine(self.weight, actx)
         if loss_module is not None:
             loss_module.reset()
             loss_module._add_fused(gamma.view(1, -1, 1, 1), loss, acc)

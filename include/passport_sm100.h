@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 6
+#define PP_ABI_VERSION 7
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -103,6 +103,13 @@ int pp_passport_affine_bwd(const PPConvDesc* d, const double* S_skey, const doub
                            const float* gamma, const float* b_sign, float alpha,
                            const float* g_gamma, const float* g_beta, const float* g_loss,
                            float* dw_oihw, int accumulate, void* stream);
+
+/* Gradient of pp_passport_affine_fwd w.r.t. the passport keys themselves (needed when an attack turns `key` /
+ * `skey` into Parameters: passport_attack_3.py:232-270).  d describes the geometry with H,W = key size.
+ *   scratch: 2 * kh*kw*C doubles;  dskey_nchw / dkey_nchw: fp32 [Bk,C,H,W] (either may be NULL). */
+int pp_passport_key_grad(const PPConvDesc* d, int Bk, const void* w_fprop, const float* gamma, const float* b_sign,
+                         float alpha, const float* g_gamma, const float* g_beta, const float* g_loss,
+                         double* scratch, float* dskey_nchw, float* dkey_nchw, void* stream);
 
 /* Stand-alone SignLoss.add on an arbitrary scale vector (sign_loss.py:18-54). */
 int pp_sign_loss_fwd(int O, const float* gamma, const float* b_sign, float alpha, float* sign_loss,

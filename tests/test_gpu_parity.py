@@ -413,3 +413,31 @@ def test_batch_one_and_odd_batches():
         for k in range(2):
             assert rel_l2(got["y"][k], bf16r(ref["y"][k])) < ACT_TOL
         assert rel_l2(got["dx"], ref["dx"]) < GRAD_TOL
+
+
+def test_gradients_wrt_passport_keys_match_oracle():
+    """passport_attack_3.py:232-270 re-registers key/skey as Parameters and optimises them: dL/dkey, dL/dskey."""
+    for (i, o, ks, s, pd, H, Bk) in ((64, 128, 3, 1, 1, 8, 1), (64, 128, 3, 2, 1, 8, 2), (128, 64, 1, 2, 0, 8, 1)):
+        m = _make_block("v1", i, o, ks, s, pd, "bn", H, seed=5)
+        key = bf16r(torch.rand(Bk, i, H, H) * 2 - 1)
+        skey = bf16r(torch.rand(Bk, i, H, H) * 2 - 1)
+        x = bf16r(torch.randn(4, i, H, H, generator=torch.Generator().manual_seed(3)))
+        res = {}
+        for tag in ("ref", "gpu"):
+            dev = "cpu" if tag == "ref" else "cuda"
+            mod = po.mirror(m, round_bf16=True) if tag == "ref" else m.cuda()
+            for name, val in (("key", key), ("skey", skey)):      # the attack's buffer -> Parameter swap
+                if name in mod._buffers:
+                    del mod._buffers[name]
+                setattr(mod, name, torch.nn.Parameter(val.clone().to(dev)))
+            mod.train()
+            for sl in mod.modules():
+                if hasattr(sl, "scale_cache"):
+                    sl.reset()
+            y = mod(x.to(dev))
+            r = bf16r(torch.randn(y.shape, generator=torch.Generator().manual_seed(9))).to(dev)
+            sl_tot = sum(sl.loss for sl in mod.modules() if hasattr(sl, "scale_cache"))
+            ((y.float() * r).sum() + sl_tot).backward()
+            res[tag] = (mod.key.grad.detach().float().cpu(), mod.skey.grad.detach().float().cpu())
+        assert rel_l2(res["gpu"][0], res["ref"][0]) < GRAD_TOL, "dkey"
+        assert rel_l2(res["gpu"][1], res["ref"][1]) < GRAD_TOL, "dskey"
