@@ -132,7 +132,8 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
-    ap.add_argument("--legs", default="value,e2e,roofline", help="comma list of legs to run (profiling runs: value)")
+    ap.add_argument("--legs", default="value,e2e,roofline,shared",
+                    help="comma list of legs: value (always), e2e, roofline, shared, torch_eager")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -328,6 +329,26 @@ def main():
                                "cudnn.benchmark, torch.optim.SGD(foreach); same batch, inputs resident"}
         del ref, ropt
 
+    # ---------------- optional extra: the same step with the public/private passes sharing the passport-free
+    # trunk (nets.ResNet18.share_trunk, identical results up to summation order).  Reported separately; `value`
+    # above always executes both full passes like the reference does.
+    shared = None
+    if "shared" in legs:
+        model.share_trunk = True
+        for i in range(3):
+            runner.step(*dev_batches[i % 4])
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            runner.step(*dev_batches[i % 4])
+        e1.record()
+        barrier()
+        ms_sh = max_over_ranks(e0.elapsed_time(e1))
+        shared = {"value": args.steps * B * world / (ms_sh * 1e-3), "unit": UNIT, "ms_per_step": ms_sh / args.steps,
+                  "what": "public+private passes share the stem..layer3 forward/backward (common-subexpression "
+                          "elimination across the two model calls of trainer_private.py:159-161)"}
+        model.share_trunk = False
+
     sig = test_signature(model) if rank == 0 else {}
     model.train()
 
@@ -346,7 +367,7 @@ def main():
                 "gpu_launches": launches,
                 "roofline": roof, "roofline_wgrad": roof_w,
                 "conv_roofline_frac_whole_step": (value / world) * GFLOP_PER_IMAGE_STEP * 1e9 / (pk["tflops"] * 1e12),
-                "cpu_baseline": cpu_baseline, "torch_eager_gpu": torch_eager,
+                "cpu_baseline": cpu_baseline, "torch_eager_gpu": torch_eager, "value_shared_trunk": shared,
                 "sign_bit_accuracy": (sum(sig.values()) / len(sig)) if sig else None,
                 "last_step": {"acc_public": last[0], "acc_private": last[1], "sign_loss": last[2], "loss": last[3]}}
         print(json.dumps(line))

@@ -150,18 +150,81 @@ class ResNet18(nn.Module):
                 in_planes = planes
             setattr(self, f'layer{li}', nn.Sequential(*units))
         self.linear = nn.Linear(512, num_classes)
+        #: Opt-in common-subexpression elimination for the V2/V3 step (trainer_private.py:159-161 calls the model
+        #: twice on the SAME batch, ind=0 then ind=1): every block in front of the first passport layer computes
+        #: identical values in both calls, so the second call can reuse the first call's trunk output (and autograd
+        #: then back-propagates the summed gradient through the trunk once).  Results are those of the two full
+        #: passes up to summation order; BatchNorm running statistics receive their second EMA update explicitly.
+        #: Off by default: bench.py reports it separately (value_shared_trunk).
+        self.share_trunk = False
+        self._trunk_cache = None
 
     def _stages(self):
         return (self.layer1, self.layer2, self.layer3, self.layer4)
 
-    def forward(self, x, force_passport=False, ind=0):
+    def _units(self):
+        return [u for stage in self._stages() for u in stage]
+
+    def _trunk_len(self):
+        """Number of leading basic units (after a passport-free stem) that contain no passport block."""
+        stem = self.convbnrelu_1[0] if isinstance(self.convbnrelu_1, nn.Sequential) else self.convbnrelu_1
+        if _is_passport(stem):
+            return -1
+        n = 0
+        for u in self._units():
+            if any(_is_passport(m) for m in u.modules()):
+                break
+            n += 1
+        return n
+
+    def _stem(self, x, force_passport, ind):
         if isinstance(self.convbnrelu_1, nn.Sequential):
-            out = self.convbnrelu_1[1](_call(self.convbnrelu_1[0], x, force_passport, ind))
+            return self.convbnrelu_1[1](_call(self.convbnrelu_1[0], x, force_passport, ind))
+        return _call(self.convbnrelu_1, x, force_passport, ind)
+
+    def _trunk_bns(self, ntrunk):
+        mods = [self.convbnrelu_1] + self._units()[:ntrunk]
+        return [m for root in mods for m in root.modules() if isinstance(m, nn.BatchNorm2d)]
+
+    def _trunk(self, x, ntrunk):
+        """Stem + the first `ntrunk` units, memoised on the identity of the input batch and of the weights."""
+        params = [p for root in [self.convbnrelu_1] + self._units()[:ntrunk] for p in root.parameters()]
+        key = (id(x), x.data_ptr(), x._version, tuple(x.shape), x.dtype, torch.is_grad_enabled(), self.training,
+               torch.is_autocast_enabled(), F_.weight_epoch(), sum(p._version for p in params))
+        cache = self._trunk_cache
+        if cache is not None and cache[0] == key:
+            _, out, bns, before = cache
+            if self.training and bns:
+                # second EMA update with the same batch statistics s:  r1 = (1-m) r0 + m s  =>
+                # r2 = (1-m) r1 + m s = (2-m) r1 - (1-m) r0      (momentum m per BatchNorm, default 0.1)
+                with torch.no_grad():
+                    for bn, (m0, v0) in zip(bns, before):
+                        mom = bn.momentum
+                        # .data: stock BatchNorm (the CPU oracle mirror of this wiring) keeps the running buffers in
+                        # its autograd graph and would reject a version bump before backward
+                        bn.running_mean.data.mul_(2.0 - mom).sub_(m0, alpha=1.0 - mom)
+                        bn.running_var.data.mul_(2.0 - mom).sub_(v0, alpha=1.0 - mom)
+                        bn.num_batches_tracked.data.add_(1)
+            self._trunk_cache = None        # one reuse per batch: public pass -> private pass
+            return out
+        bns = self._trunk_bns(ntrunk) if self.training else []
+        before = [(bn.running_mean.clone(), bn.running_var.clone()) for bn in bns]
+        out = self._stem(x, False, 0)
+        for unit in self._units()[:ntrunk]:
+            out = unit(out, False, 0)
+        self._trunk_cache = (key, out, bns, before)
+        return out
+
+    def forward(self, x, force_passport=False, ind=0):
+        ntrunk = self._trunk_len() if self.share_trunk else -1
+        if ntrunk >= 0:
+            out = self._trunk(x, ntrunk)
+            rest = self._units()[ntrunk:]
         else:
-            out = _call(self.convbnrelu_1, x, force_passport, ind)
-        for stage in self._stages():
-            for unit in stage:
-                out = unit(out, force_passport, ind)
+            out = self._stem(x, force_passport, ind)
+            rest = self._units()
+        for unit in rest:
+            out = unit(out, force_passport, ind)
         out = F.adaptive_avg_pool2d(out, (1, 1)).flatten(1)
         return self.linear(out)
 
