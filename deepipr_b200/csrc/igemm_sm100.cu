@@ -276,78 +276,91 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (RESB) {
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses / descriptors in uniform registers);
+    // one elected lane issues the bulk-tensor copies.
+    if (RESB) {
+      if (elect_one()) {
         // all weight blocks once: block ks = (tap t, channel chunk kc) in main-loop order
         mbar_arrive_expect_tx(bres, (uint32_t)ksteps * Cfg::kStageB);
         for (int t = 0; t < p.ntaps; ++t)
           for (int kc = 0; kc < kchunks; ++kc)
             tma_load_2d(&tmB, bres, res_base + (t * kchunks + kc) * Cfg::kStageB, p.tap_kofs[t] + kc * kBK, 0);
       }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        const int m_tile = tile / p.num_n_tiles;
-        const int m0 = m_tile * kBM;
-        const int img = m0 / p.PQ;
-        const int rem = m0 - img * p.PQ;
-        const int p0 = rem / p.Q;
-        const int q0 = rem - p0 * p.Q;
-        const int cw = p.base_w + q0 * p.step_w;
-        const int ch = p.base_h + p0 * p.step_h;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const uint16_t dw = (uint16_t)p.tap_dw[t];
-          const uint16_t dh = (uint16_t)p.tap_dh[t];
-          const int kofs = p.tap_kofs[t];
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
+      __syncwarp();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    const int dbg = p.dbg;
+    const int a_tiled = p.a_tiled;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = tile / p.num_n_tiles;
+      const int m0 = m_tile * kBM;
+      const int img = m0 / p.PQ;
+      const int rem = m0 - img * p.PQ;
+      const int p0 = rem / p.Q;
+      const int q0 = rem - p0 * p.Q;
+      const int cw = p.base_w + q0 * p.step_w;
+      const int ch = p.base_h + p0 * p.step_h;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int dw = p.tap_dw[t];
+        const int dh = p.tap_dh[t];
+        const int kofs = p.tap_kofs[t];
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
+          if (elect_one()) {
             uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kStageA;
-            if (p.dbg & 16) {   // bring-up: no loads at all, just hand the (stale) stage to the MMA warp
+            if (dbg & 16) {   // bring-up: no loads at all, just hand the (stale) stage to the MMA warp
               mbar_arrive(&full[stage]);
-              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-              continue;
+            } else {
+              mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+              if (a_tiled) tma_load_4d(&tmA, &full[stage], sa, kc * kBK, cw + dw, ch + dh, img);
+              else tma_load_im2col_4d(&tmA, &full[stage], sa, kc * kBK, cw, ch, img, (uint16_t)dw, (uint16_t)dh);
+              if (!RESB) tma_load_2d(&tmB, &full[stage], sb, kofs + kc * kBK, n_tile * BN);
             }
-            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-            if (p.a_tiled) tma_load_4d(&tmA, &full[stage], sa, kc * kBK, cw + dw, ch + dh, img);
-            else tma_load_im2col_4d(&tmA, &full[stage], sa, kc * kBK, cw, ch, img, dw, dh);
-            if (!RESB) tma_load_2d(&tmB, &full[stage], sb, kofs + kc * kBK, n_tile * BN);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      if (RESB) mbar_wait(bres, 0, 250);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
+    // Warp-uniform loop; one elected lane issues tcgen05.mma / tcgen05.commit (descriptors stay in uniform registers,
+    // so the instructions issue back to back instead of through per-instruction election loops).
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int dbg = p.dbg;
+    const uint32_t stage0 = smem_u32(stage_base);
+    const uint32_t res0 = smem_u32(res_base);
+    if (RESB) mbar_wait(bres, 0, 250);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full[stage], phase, 300 + stage);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&full[stage], phase, 300 + stage);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
-          const uint32_t sb = RESB ? smem_u32(res_base + ks * Cfg::kStageB) : sa + Cfg::kStageA;
+        const uint32_t sa = stage0 + stage * Cfg::kStageBytes;
+        const uint32_t sb = RESB ? res0 + ks * Cfg::kStageB : sa + Cfg::kStageA;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            if (!(p.dbg & 8)) tc_mma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+            if (!(dbg & 8)) tc_mma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
           }
           tc_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (ks == ksteps - 1) tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
         }
-        tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (4 warps, 128 threads = 128 accumulator rows) =====================
@@ -671,51 +684,56 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // the two A slabs of this tile: rows [k0, k0+64) and [k1, k1+64) of the (tap, c) axis
-      int k0 = m_tile * 128, k1 = k0 + 64;
-      if (k1 >= p.Ktot) k1 = k0;  // odd slab count: load slab 0 twice (its rows are not stored)
-      const int tap0 = k0 / p.C, c0 = k0 - tap0 * p.C;
-      const int tap1 = k1 / p.C, c1 = k1 - tap1 * p.C;
-      const uint16_t dw0 = (uint16_t)p.tap_dw[tap0], dh0 = (uint16_t)p.tap_dh[tap0];
-      const uint16_t dw1 = (uint16_t)p.tap_dw[tap1], dh1 = (uint16_t)p.tap_dh[tap1];
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int ch = chunk_lo; ch < chunk_lo + nchunks; ++ch) {
-        const int m0 = ch * kWK;
-        const int img = m0 / p.PQ;
-        const int rem = m0 - img * p.PQ;
-        const int p0 = rem / p.Q;
-        const int q0 = rem - p0 * p.Q;
-        const int cw = p.base_w + q0 * p.step_w;
-        const int chh = p.base_h + p0 * p.step_h;
-        mbar_wait(&empty[stage], phase ^ 1, 500 + stage);
+    // TMA producer: warp-uniform loop, one elected lane issues the copies
+    // the two A slabs of this tile: rows [k0, k0+64) and [k1, k1+64) of the (tap, c) axis
+    int k0 = m_tile * 128, k1 = k0 + 64;
+    if (k1 >= p.Ktot) k1 = k0;  // odd slab count: load slab 0 twice (its rows are not stored)
+    const int tap0 = k0 / p.C, c0 = k0 - tap0 * p.C;
+    const int tap1 = k1 / p.C, c1 = k1 - tap1 * p.C;
+    const int dw0 = p.tap_dw[tap0], dh0 = p.tap_dh[tap0];
+    const int dw1 = p.tap_dw[tap1], dh1 = p.tap_dh[tap1];
+    const int x_tiled = p.x_tiled;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ch = chunk_lo; ch < chunk_lo + nchunks; ++ch) {
+      const int m0 = ch * kWK;
+      const int img = m0 / p.PQ;
+      const int rem = m0 - img * p.PQ;
+      const int p0 = rem / p.Q;
+      const int q0 = rem - p0 * p.Q;
+      const int cw = p.base_w + q0 * p.step_w;
+      const int chh = p.base_h + p0 * p.step_h;
+      mbar_wait(&empty[stage], phase ^ 1, 500 + stage);
+      if (elect_one()) {
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kStageA;
         mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-        if (p.x_tiled) {
+        if (x_tiled) {
           tma_load_4d(&tmX, &full[stage], sa, c0, cw + dw0, chh + dh0, img);
           tma_load_4d(&tmX, &full[stage], sa + kWK * 128, c1, cw + dw1, chh + dh1, img);
         } else {
-          tma_load_im2col_4d(&tmX, &full[stage], sa, c0, cw, chh, img, dw0, dh0);
-          tma_load_im2col_4d(&tmX, &full[stage], sa + kWK * 128, c1, cw, chh, img, dw1, dh1);
+          tma_load_im2col_4d(&tmX, &full[stage], sa, c0, cw, chh, img, (uint16_t)dw0, (uint16_t)dh0);
+          tma_load_im2col_4d(&tmX, &full[stage], sa + kWK * 128, c1, cw, chh, img, (uint16_t)dw1, (uint16_t)dh1);
         }
 #pragma unroll
         for (int i = 0; i < BN / 64; ++i)
           tma_load_2d(&tmDz, &full[stage], sb + i * kWK * 128, n_tile * BN + i * 64, m0);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < nchunks; ++it) {
-        mbar_wait(&full[stage], phase, 600 + stage);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kStageA;
+    // MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    const uint32_t smem0 = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      mbar_wait(&full[stage], phase, 600 + stage);
+      tc_fence_after();
+      const uint32_t sa = smem0 + stage * Cfg::kStageBytes;
+      const uint32_t sb = sa + Cfg::kStageA;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kWK / 16; ++k) {
           // 16 pixels (k) per instruction = two 8-row groups of 1024 B; MN slabs are kWK*128 B apart
@@ -724,9 +742,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
         }
         tc_commit(&empty[stage]);
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (it == nchunks - 1) tc_commit(tfull);
       }
-      tc_commit(tfull);
+      __syncwarp();
+      if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
     }
   } else {
     const int quarter = warp & 3;
