@@ -541,14 +541,6 @@ static int pick_bn(const TapGemm& g) {
 
 int tapgemm_tcgen05_max_stats_width() { return kMaxStatsN; }
 
-int tapgemm_tcgen05_grid(const TapGemm& g) {
-  const int bn = pick_bn(g);
-  const long long M = (long long)g.N * g.P * g.Q;
-  const long long tiles = ((M + kBM - 1) / kBM) * (g.Nout / bn);
-  const int sms = device_sm_count();
-  return (int)(tiles < sms ? tiles : sms);
-}
-
 template <int BN, bool RESB>
 static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, const TapEpilogue& e, cudaStream_t s) {
   using Cfg = FwdCfg<BN, RESB>;
@@ -595,10 +587,422 @@ static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, cons
   return PP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// "pixels on N" variant for layers with <= 128 output channels (stride-1 traversal).
+//
+// Measured on B200 (profiles/README.md): a 128-row tcgen05.mma costs ~125 cycles + 0.28*N, i.e. narrow N = 64 / 128
+// tiles pay 2-3.5x per MAC, and the nine taps of a 3x3 filter re-read the activation tile from L2.  Here the roles
+// are swapped and the tap windows share one shared-memory slab:
+//   A = weight tile  [128 out-channel rows (rows >= Nout are don't-care) x 64 k]   K-major, 2-D TMA (or resident)
+//   B = pixel window [npx = R image rows x Q (<= 256) pixels x 64 k]               K-major
+//   D[o, pixel] in TMEM: lane = output channel, column = pixel, two buffers of 256 columns.
+// For each horizontal tap offset dw ONE tiled 4-D box {64 ch, Q, R + max_dh, 1 image} (zero-filled outside the
+// image) is loaded; the vertical taps dh are windows of that slab starting dh*Q rows (a multiple of 1024 B) further
+// down, so they cost no extra L2 traffic.  The epilogue has a channel per thread: BN statistics are plain per-thread
+// sums, and the tile is transposed through shared memory so that stores are full NHWC rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPxnMaxGroups = 8;
+constexpr int kPxnMaxDh = 8;
+
+struct PxnDev {
+  int M, P, Q, PQ;
+  int base_h, base_w;
+  int C, kchunks, Nout;
+  int R, npx, tiles_per_img, num_tiles;
+  int ngroups;
+  int dw_val[kPxnMaxGroups];
+  int ndh[kPxnMaxGroups];
+  int dh_val[kPxnMaxGroups][kPxnMaxDh];
+  int kofs[kPxnMaxGroups][kPxnMaxDh];
+  int wslot[kPxnMaxGroups][kPxnMaxDh];  // resident mode: index of the tap's first weight tile
+  int halo_rows, slab_bytes;            // rows per slab, bytes per slab (multiple of 1024)
+  int wtile_bytes;                      // Nout * 128
+  int max_ndh;
+  int resident, res_bytes;              // weights resident in smem; bytes of that region (incl. slack)
+  int stage_bytes, nstages;
+  int out_H, out_W, out_sh, out_sw, out_ph, out_pw, out_identity;
+  void* out;
+  int out_f32;
+  const float* scale;
+  const float* shift;
+  int relu;
+  float* stats_partial;
+  int dbg;
+};
+
+constexpr int kPxnStageStaging = 32 * 128 * 4;   // 32 pixels x 128 channels fp32
+constexpr int kPxnMaxStages = 8;
+
+__global__ void __launch_bounds__(kThreads, 1)
+pxn_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
+           const __grid_constant__ PxnDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* res_base = smem;
+  uint8_t* stage_base = smem + p.res_bytes;
+  uint8_t* tail = stage_base + (size_t)p.nstages * p.stage_bytes;
+  float* s_stage = reinterpret_cast<float*>(tail);                         // [32 px][128 ch]
+  long long* s_orow = reinterpret_cast<long long*>(tail + kPxnStageStaging);  // [32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + kPxnStageStaging + 256);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kPxnMaxStages;
+  uint64_t* tfull = bars + 2 * kPxnMaxStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bres = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nstages = p.nstages;
+  const int ksteps = p.ngroups * p.kchunks;   // pipeline steps per tile: one slab each
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAct);
+    tma_prefetch_desc(&tmW);
+    for (int i = 0; i < nstages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(bres, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (p.resident) {
+      if (elect_one()) {
+        int ntiles_w = 0;
+        for (int g = 0; g < p.ngroups; ++g) ntiles_w += p.ndh[g] * p.kchunks;
+        mbar_arrive_expect_tx(bres, (uint32_t)(ntiles_w * p.wtile_bytes));
+        for (int g = 0; g < p.ngroups; ++g)
+          for (int j = 0; j < p.ndh[g]; ++j)
+            for (int kc = 0; kc < p.kchunks; ++kc)
+              tma_load_2d(&tmW, bres, res_base + (size_t)(p.wslot[g][j] + kc) * p.wtile_bytes, p.kofs[g][j] + kc * kBK,
+                          0);
+      }
+      __syncwarp();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int img = tile / p.tiles_per_img;
+      const int p0 = (tile - img * p.tiles_per_img) * p.R;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const int cw = p.base_w + p.dw_val[g];
+        const int ch = p.base_h + p0;
+        const int nd = p.ndh[g];
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1, 800 + stage);
+          if (elect_one()) {
+            uint8_t* slab = stage_base + (size_t)stage * p.stage_bytes;
+            const uint32_t bytes = (uint32_t)p.slab_bytes + (p.resident ? 0u : (uint32_t)(nd * p.wtile_bytes));
+            if (p.dbg & 16) {
+              mbar_arrive(&full[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], bytes);
+              tma_load_4d(&tmAct, &full[stage], slab, kc * kBK, cw, ch, img);
+              if (!p.resident) {
+                for (int j = 0; j < nd; ++j)
+                  tma_load_2d(&tmW, &full[stage], slab + p.slab_bytes + (size_t)j * p.wtile_bytes,
+                              p.kofs[g][j] + kc * kBK, 0);
+              }
+            }
+          }
+          __syncwarp();
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_bf16(128, p.npx, 0, 0);
+    const uint32_t stage0 = smem_u32(stage_base);
+    const uint32_t res0 = smem_u32(res_base);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (p.resident) mbar_wait(bres, 0, 850);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1, 900 + acc);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      int step = 0;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const int nd = p.ndh[g];
+        for (int kc = 0; kc < p.kchunks; ++kc, ++step) {
+          mbar_wait(&full[stage], phase, 1000 + stage);
+          tc_fence_after();
+          const uint32_t slab = stage0 + stage * p.stage_bytes;
+          if (elect_one()) {
+            for (int j = 0; j < nd; ++j) {
+              const uint32_t sw = p.resident ? res0 + (p.wslot[g][j] + kc) * p.wtile_bytes
+                                             : slab + p.slab_bytes + j * p.wtile_bytes;
+              const uint32_t sx = slab + p.dh_val[g][j] * p.Q * 128;
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t da = make_smem_desc_sw128(sw + k * 32, 16, 1024);
+                const uint64_t db = make_smem_desc_sw128(sx + k * 32, 16, 1024);
+                if (!(p.dbg & 8)) tc_mma_bf16(d_tmem, da, db, idesc, (step | j | k) != 0 ? 1u : 0u);
+              }
+            }
+            tc_commit(&empty[stage]);
+            if (step == ksteps - 1) tc_commit(&tfull[acc]);
+          }
+          __syncwarp();
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue: one output channel per thread =====================
+    const int quarter = warp & 3;
+    const int o = quarter * 32 + lane;
+    const int tid_e = (warp - 2) * 32 + lane;
+    const bool o_valid = o < p.Nout;
+    const float ca = (o_valid && p.scale) ? __ldg(p.scale + o) : 1.0f;
+    const float cb = (o_valid && p.shift) ? __ldg(p.shift + o) : 0.0f;
+    const bool has_affine = (p.scale != nullptr) || (p.shift != nullptr);
+    float sum1 = 0.0f, sum2 = 0.0f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int nchunks = p.npx / 32;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int img = tile / p.tiles_per_img;
+      const int p0 = (tile - img * p.tiles_per_img) * p.R;
+      const int m0 = img * p.PQ + p0 * p.Q;      // first output pixel (traversal order) of this tile
+      mbar_wait(&tfull[acc], acc_phase, 1100 + acc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * 256;
+#pragma unroll 1
+      for (int j = 0; j < nchunks; ++j) {
+        uint32_t raw[32];
+        if (p.dbg & 4) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = 0x3f800000u;
+        } else {
+          tmem_ld_32x32(taddr + j * 32, raw);
+          tmem_ld_wait();
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        if (p.stats_partial && !(p.dbg & 2)) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {   // pixels past the batch tail were zero-filled: they add nothing
+            sum1 += v[i];
+            sum2 = fmaf(v[i], v[i], sum2);
+          }
+        }
+        if (has_affine) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], ca, cb);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        // A lane owns an output channel, so for a fixed pixel the 32 lanes of a warp write 32 consecutive channels:
+        // every store instruction is one full 128-byte (fp32) / 64-byte (bf16) NHWC segment — no staging needed.
+        // The 32 pixels of a chunk are `32/seg` runs of `seg` consecutive pixels of one image row; inside a run the
+        // output row advances by out_sw, so addresses are formed by pointer increments (warp-uniform, no shuffles).
+        if (o_valid && !(p.dbg & 1)) {
+          const int mc = m0 + j * 32;
+          const size_t step = (size_t)(p.out_identity ? 1 : p.out_sw) * p.Nout;
+          // Q is a multiple of 8, so each group of 8 consecutive pixels lies in one image row: four row lookups per
+          // chunk, pointer increments inside a group.
+          size_t base8[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int m = mc + 8 * k;
+            size_t orow;
+            if (p.out_identity) {
+              orow = (size_t)m;
+            } else {
+              const int rem = m - img * p.PQ;
+              const int pp_ = rem / p.Q;
+              const int qq_ = rem - pp_ * p.Q;
+              orow = ((size_t)img * p.out_H + (size_t)(pp_ * p.out_sh + p.out_ph)) * p.out_W +
+                     (size_t)(qq_ * p.out_sw + p.out_pw);
+            }
+            base8[k] = orow * p.Nout + o;
+          }
+          if (p.out_f32) {
+            float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) out[base8[i >> 3] + (size_t)(i & 7) * step] = v[i];
+          } else {
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) out[base8[i >> 3] + (size_t)(i & 7) * step] = __float2bfloat16_rn(v[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.stats_partial && o_valid) {
+      float* dst = p.stats_partial + (size_t)blockIdx.x * 2 * p.Nout;
+      dst[o] = sum1;
+      dst[p.Nout + o] = sum2;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+struct PxnPlan {
+  bool ok;
+  PxnDev dev;
+  int grid;
+  int smem_bytes;
+};
+
+static bool pxn_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PP_NO_PXN"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
+// Decide whether the pixels-on-N kernel applies and fill its launch parameters.
+static PxnPlan plan_pxn(const TapGemm& g) {
+  PxnPlan pl;
+  pl.ok = false;
+  if (!pxn_enabled()) return pl;
+  if (g.step_h != 1 || g.step_w != 1) return pl;
+  if (g.C % 64 != 0 || (g.Nout != 64 && g.Nout != 128)) return pl;
+  if (g.Q > 256 || g.Q < 1) return pl;
+  int R = 256 / g.Q;
+  if (R > g.P) R = g.P;
+  while (R > 1 && (g.P % R != 0 || (R * g.Q) % 32 != 0)) --R;
+  const int npx = R * g.Q;
+  if (g.P % R != 0 || npx != 256 || R < 2) return pl;   // full-width N = 256 tiles of >= 2 image rows only
+                                                          // (32x32 and 16x16 feature maps)
+  if (g.Q * 128 % 1024 != 0) return pl;   // tap windows must start on a swizzle-atom boundary: Q % 8 == 0
+  PxnDev& d = pl.dev;
+  memset(&d, 0, sizeof(d));
+  d.M = g.N * g.P * g.Q; d.P = g.P; d.Q = g.Q; d.PQ = g.P * g.Q;
+  d.base_h = g.base_h; d.base_w = g.base_w;
+  d.C = g.C; d.kchunks = g.C / 64; d.Nout = g.Nout;
+  d.R = R; d.npx = npx; d.tiles_per_img = g.P / R; d.num_tiles = g.N * d.tiles_per_img;
+  // group the taps by horizontal offset
+  int max_dh = 0, wtiles = 0;
+  for (int t = 0; t < g.ntaps; ++t) {
+    int gi = -1;
+    for (int k = 0; k < d.ngroups; ++k)
+      if (d.dw_val[k] == g.tap_dw[t]) gi = k;
+    if (gi < 0) {
+      if (d.ngroups == kPxnMaxGroups) return pl;
+      gi = d.ngroups++;
+      d.dw_val[gi] = g.tap_dw[t];
+    }
+    if (d.ndh[gi] == kPxnMaxDh) return pl;
+    const int j = d.ndh[gi]++;
+    d.dh_val[gi][j] = g.tap_dh[t];
+    d.kofs[gi][j] = g.tap_kofs[t];
+    d.wslot[gi][j] = wtiles;
+    wtiles += d.kchunks;
+    if (g.tap_dh[t] > max_dh) max_dh = g.tap_dh[t];
+    if (d.ndh[gi] > d.max_ndh) d.max_ndh = d.ndh[gi];
+  }
+  d.halo_rows = R + max_dh;
+  if (d.halo_rows > 256) return pl;
+  d.slab_bytes = d.halo_rows * g.Q * 128;
+  if (d.slab_bytes % 1024 != 0) return pl;
+  d.wtile_bytes = g.Nout * 128;
+  const int tail = kPxnStageStaging + 256 + 256;
+  const int budget = 232448 - 1024 - tail;
+  // resident weights: all (tap, chunk) tiles + one tile of slack (an M=128 MMA reads 128 rows even when Nout = 64)
+  const int res_bytes = (wtiles + 1) * d.wtile_bytes + (g.Nout == 64 ? d.wtile_bytes : 0);
+  const int res_aligned = (res_bytes + 1023) / 1024 * 1024;
+  if (res_aligned + 2 * d.slab_bytes <= budget && res_aligned <= 96 * 1024) {
+    d.resident = 1;
+    d.res_bytes = res_aligned;
+    d.stage_bytes = d.slab_bytes;
+  } else {
+    d.resident = 0;
+    d.res_bytes = 0;
+    // slab + weight tiles of the group (+ slack tile for the 128-row read when Nout = 64)
+    d.stage_bytes = d.slab_bytes + (d.max_ndh + (g.Nout == 64 ? 1 : 0)) * d.wtile_bytes;
+  }
+  d.nstages = (budget - d.res_bytes) / d.stage_bytes;
+  if (d.nstages > kPxnMaxStages) d.nstages = kPxnMaxStages;
+  if (d.nstages < 2) return pl;
+  d.out_H = g.out_H; d.out_W = g.out_W; d.out_sh = g.out_sh; d.out_sw = g.out_sw; d.out_ph = g.out_ph;
+  d.out_pw = g.out_pw; d.out_identity = g.out_identity;
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  pl.grid = d.num_tiles < sms ? d.num_tiles : sms;
+  pl.smem_bytes = 1024 + d.res_bytes + d.nstages * d.stage_bytes + tail;
+  pl.ok = true;
+  return pl;
+}
+
+static int launch_pxn(const TapGemm& g, PxnPlan& pl, const void* act, const void* B, const TapEpilogue& e,
+                      cudaStream_t s) {
+  CUtensorMap tmAct, tmW;
+  PP_TRY(make_map_tiled4d(&tmAct, act, g, g.Q, pl.dev.halo_rows, 1));
+  PP_TRY(make_map_2d(&tmW, B, (uint64_t)g.Nout, (uint64_t)g.Ktot, (uint32_t)g.Nout));
+  PxnDev& d = pl.dev;
+  d.out = e.out; d.out_f32 = e.out_f32; d.scale = e.scale; d.shift = e.shift; d.relu = e.relu;
+  d.stats_partial = e.stats_partial;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* ev = getenv("PP_DEBUG"); dbg = ev ? atoi(ev) : 0; }
+    d.dbg = dbg;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(pxn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  prof_begin(PROF_TAPGEMM, 2.0 * (double)d.M * g.Nout * g.ntaps * g.C, g.C, g.Nout, g.ntaps, s);
+  pxn_kernel<<<pl.grid, kThreads, pl.smem_bytes, s>>>(tmAct, tmW, d);
+  prof_end(PROF_TAPGEMM, s);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
+int tapgemm_tcgen05_grid(const TapGemm& g) {
+  {
+    PxnPlan pl = plan_pxn(g);
+    if (pl.ok) return pl.grid;
+  }
+  const int bn = pick_bn(g);
+  const long long M = (long long)g.N * g.P * g.Q;
+  const long long tiles = ((M + kBM - 1) / kBM) * (g.Nout / bn);
+  const int sms = device_sm_count();
+  return (int)(tiles < sms ? tiles : sms);
+}
+
 int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapEpilogue& e, cudaStream_t s) {
   PP_TRY(resolve_encoders());
   PP_REQUIRE(tapgemm_tcgen05_supported(g), PP_EUNSUPPORTED,
              "tcgen05 tap-GEMM needs C%%64==0 and Nout%%64==0 (C=%d Nout=%d)", g.C, g.Nout);
+  {
+    PxnPlan pl = plan_pxn(g);
+    if (pl.ok) return launch_pxn(g, pl, act, B, e, s);
+  }
   switch (pick_bn(g)) {
     case 256: return launch_tapgemm<256, false>(g, act, B, e, s);
     case 128: return launch_tapgemm<128, false>(g, act, B, e, s);

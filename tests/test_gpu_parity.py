@@ -70,6 +70,8 @@ GEOMS = [  # N, C, H, O, k, s, p
     (2, 64, 8, 64, 1, 1, 0), (3, 64, 4, 64, 3, 1, 1), (9, 64, 4, 128, 3, 1, 1), (4, 192, 8, 384, 3, 1, 1),
     (16, 512, 4, 512, 3, 1, 1), (8, 256, 8, 512, 3, 2, 1), (8, 256, 8, 512, 1, 2, 0), (2, 64, 32, 64, 3, 1, 1),
     (5, 256, 7, 256, 3, 1, 1), (3, 128, 14, 256, 3, 2, 1), (1, 64, 4, 64, 3, 1, 1),
+    # geometries that take the pixels-on-N kernel (<=128 output columns, 32x32 / 16x16 maps), incl. strided dgrad
+    (3, 128, 16, 128, 3, 1, 1), (2, 64, 32, 128, 3, 2, 1), (2, 64, 32, 128, 1, 2, 0), (2, 128, 32, 64, 3, 1, 1),
 ]
 
 
