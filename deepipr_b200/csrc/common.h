@@ -51,7 +51,7 @@ constexpr int kMaxTaps = 49;  // up to 7x7 filters
 //     act pixel = (base_h + p*step_h + dh, base_w + q*step_w + dw), zero outside the tensor
 //   output row m is written at pixel (p*out_sh + out_ph, q*out_sw + out_pw) of an out_H x out_W image.
 // The forward conv, the stride-1 data gradient and every phase of a strided data gradient are all
-// instances of this (see igemm_sm100.cu: plan_fprop / plan_dgrad).
+// instances of this (see api.cu: plan_fprop / plan_dgrad_phase / plan_col).
 struct TapGemm {
   // activation tensor, NHWC bf16
   int N, H, W, C;

@@ -628,9 +628,9 @@ struct PxnDev {
   int relu;
   float* stats_partial;
   int dbg;
+  int m64;   // Nout == 64: issue M=64 MMAs; 1 = accumulator row r in TMEM lane r, 2 = lane 32*(r/16) + r%16
 };
 
-constexpr int kPxnStageStaging = 32 * 128 * 4;   // 32 pixels x 128 channels fp32
 constexpr int kPxnMaxStages = 8;
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -641,9 +641,7 @@ pxn_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CU
   uint8_t* res_base = smem;
   uint8_t* stage_base = smem + p.res_bytes;
   uint8_t* tail = stage_base + (size_t)p.nstages * p.stage_bytes;
-  float* s_stage = reinterpret_cast<float*>(tail);                         // [32 px][128 ch]
-  long long* s_orow = reinterpret_cast<long long*>(tail + kPxnStageStaging);  // [32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + kPxnStageStaging + 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full = bars;
   uint64_t* empty = bars + kPxnMaxStages;
   uint64_t* tfull = bars + 2 * kPxnMaxStages;
@@ -727,7 +725,7 @@ pxn_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = make_idesc_bf16(128, p.npx, 0, 0);
+    const uint32_t idesc = make_idesc_bf16(p.m64 ? 64 : 128, p.npx, 0, 0);
     const uint32_t stage0 = smem_u32(stage_base);
     const uint32_t res0 = smem_u32(res_base);
     int stage = 0;
@@ -770,9 +768,12 @@ pxn_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CU
   } else {
     // ===================== epilogue: one output channel per thread =====================
     const int quarter = warp & 3;
-    const int o = quarter * 32 + lane;
-    const int tid_e = (warp - 2) * 32 + lane;
-    const bool o_valid = o < p.Nout;
+    int o = quarter * 32 + lane;
+    bool o_valid = o < p.Nout;
+    if (p.m64 == 2) {   // M=64 accumulator: row r lives in lane 32*(r/16) + r%16
+      o = quarter * 16 + (lane & 15);
+      o_valid = lane < 16;
+    }
     const float ca = (o_valid && p.scale) ? __ldg(p.scale + o) : 1.0f;
     const float cb = (o_valid && p.shift) ? __ldg(p.shift + o) : 0.0f;
     const bool has_affine = (p.scale != nullptr) || (p.shift != nullptr);
@@ -930,7 +931,7 @@ static PxnPlan plan_pxn(const TapGemm& g) {
   d.slab_bytes = d.halo_rows * g.Q * 128;
   if (d.slab_bytes % 1024 != 0) return pl;
   d.wtile_bytes = g.Nout * 128;
-  const int tail = kPxnStageStaging + 256 + 256;
+  const int tail = 256;   // mbarriers + TMEM slot
   const int budget = 232448 - 1024 - tail;
   // resident weights: all (tap, chunk) tiles + one tile of slack (an M=128 MMA reads 128 rows even when Nout = 64)
   const int res_bytes = (wtiles + 1) * d.wtile_bytes + (g.Nout == 64 ? d.wtile_bytes : 0);
@@ -967,9 +968,11 @@ static int launch_pxn(const TapGemm& g, PxnPlan& pl, const void* act, const void
   d.out = e.out; d.out_f32 = e.out_f32; d.scale = e.scale; d.shift = e.shift; d.relu = e.relu;
   d.stats_partial = e.stats_partial;
   {
-    static int dbg = -1;
+    static int dbg = -1, m64 = -1;
     if (dbg < 0) { const char* ev = getenv("PP_DEBUG"); dbg = ev ? atoi(ev) : 0; }
+    if (m64 < 0) { const char* ev = getenv("PP_M64"); m64 = ev ? atoi(ev) : 0; }
     d.dbg = dbg;
+    d.m64 = (g.Nout == 64) ? m64 : 0;
   }
   static bool attr_set = false;
   if (!attr_set) {
