@@ -1203,9 +1203,11 @@ bool wgrad_tcgen05_supported(const TapGemm& g, int O) {
 
 static int wgrad_bn(int O) { return (O % 256 == 0) ? 256 : ((O % 128 == 0) ? 128 : 64); }
 
+static bool wgrad_om_applies(const TapGemm& g, int O);
+
 int wgrad_pick_splits(const TapGemm& g, int O) {
   const int Ktot = g.ntaps * g.C;
-  const int tiles = ((Ktot + 127) / 128) * (O / wgrad_bn(O));
+  const int tiles = wgrad_om_applies(g, O) ? (Ktot / 64 + 3) / 4 : ((Ktot + 127) / 128) * (O / wgrad_bn(O));
   const long long M = (long long)g.N * g.P * g.Q;
   const int chunks = (int)((M + kWK - 1) / kWK);
   int sms = device_sm_count();
@@ -1255,11 +1257,212 @@ static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, 
   return PP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// weight gradient for O <= 128: output channels on M, (tap, c) on N = 256.
+//   D[o, (tap,c)] = sum over pixels of dz[m, o] * x_tap[m, c]
+// A 128-row tcgen05.mma costs ~125 cycles + 0.28*N (profiles/README.md), so with only 64 / 128 output channels the
+// transposed kernel above (N = O) pays 142 / 155 cycles for a quarter / half of the MACs an N = 256 instruction does
+// in 197.  Here A = dz slabs (MN-major, o contiguous; the second slab is TMA-zero-filled when O = 64) and
+// B = four 64-wide (tap, c) slabs of x.
+// ------------------------------------------------------------------------------------------------
+struct WgradOmDev {
+  int M, P, Q, PQ;
+  int base_h, base_w, step_h, step_w;
+  int C, O, ntaps, Ktot, nslabs;
+  int x_tiled;
+  int chunks_total, chunks_per_split;
+  int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
+  float* partial;  // [splits][O][Ktot]
+};
+
+constexpr int kOmStageA = 2 * kWK * 128;   // two dz slabs (o 0..63, 64..127)
+constexpr int kOmStageB = 4 * kWK * 128;   // four (tap, c) slabs of x
+constexpr int kOmStageBytes = kOmStageA + kOmStageB;   // 48 KiB
+constexpr int kOmStages = 4;
+constexpr int kOmSmemBytes = 1024 + kOmStages * kOmStageBytes + 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_om_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDz,
+                const __grid_constant__ WgradOmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOmStages * kOmStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kOmStages;
+  uint64_t* tfull = bars + 2 * kOmStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x;            // four consecutive (tap, c) slabs
+  const int split = blockIdx.y;
+  const int chunk_lo = split * p.chunks_per_split;
+  int chunk_hi = chunk_lo + p.chunks_per_split;
+  if (chunk_hi > p.chunks_total) chunk_hi = p.chunks_total;
+  const int nchunks = chunk_hi > chunk_lo ? chunk_hi - chunk_lo : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDz);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < kOmStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int tap[4], c0[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int sidx = n_tile * 4 + i;
+      if (sidx >= p.nslabs) sidx = n_tile * 4;   // past the end: reload the first slab (its columns are not stored)
+      const int k0 = sidx * 64;
+      tap[i] = k0 / p.C;
+      c0[i] = k0 - tap[i] * p.C;
+    }
+    const int x_tiled = p.x_tiled;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ch = chunk_lo; ch < chunk_lo + nchunks; ++ch) {
+      const int m0 = ch * kWK;
+      const int img = m0 / p.PQ;
+      const int rem = m0 - img * p.PQ;
+      const int p0 = rem / p.Q;
+      const int q0 = rem - p0 * p.Q;
+      const int cw = p.base_w + q0 * p.step_w;
+      const int chh = p.base_h + p0 * p.step_h;
+      mbar_wait(&empty[stage], phase ^ 1, 1200 + stage);
+      if (elect_one()) {
+        uint8_t* sa = smem + stage * kOmStageBytes;
+        uint8_t* sb = sa + kOmStageA;
+        mbar_arrive_expect_tx(&full[stage], kOmStageBytes);
+        tma_load_2d(&tmDz, &full[stage], sa, 0, m0);
+        tma_load_2d(&tmDz, &full[stage], sa + kWK * 128, 64, m0);   // all zeros (out of bounds) when O == 64
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int dw = p.tap_dw[tap[i]], dh = p.tap_dh[tap[i]];
+          if (x_tiled) tma_load_4d(&tmX, &full[stage], sb + i * kWK * 128, c0[i], cw + dw, chh + dh, img);
+          else tma_load_im2col_4d(&tmX, &full[stage], sb + i * kWK * 128, c0[i], cw, chh, img, (uint16_t)dw,
+                                  (uint16_t)dh);
+        }
+      }
+      __syncwarp();
+      if (++stage == kOmStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 256, 1, 1);
+    const uint32_t smem0 = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < nchunks; ++it) {
+      mbar_wait(&full[stage], phase, 1300 + stage);
+      tc_fence_after();
+      const uint32_t sa = smem0 + stage * kOmStageBytes;
+      const uint32_t sb = sa + kOmStageA;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kWK / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(sa + k * 2048, kWK * 128, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kWK * 128, 1024);
+          tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty[stage]);
+        if (it == nchunks - 1) tc_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == kOmStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int o = quarter * 32 + lane;
+    if (nchunks > 0) {
+      mbar_wait(tfull, 0, 1400);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+    float* dst_row = p.partial + ((size_t)split * p.O + (size_t)o) * p.Ktot + (size_t)n_tile * 256;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      uint32_t raw[32];
+      if (nchunks > 0) {
+        tmem_ld_32x32(taddr + j * 32, raw);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = 0u;
+      }
+      const bool slab_valid = (n_tile * 4 + (j >> 1)) < p.nslabs;
+      if (o < p.O && slab_valid) {
+        float4* dst = reinterpret_cast<float4*>(dst_row + j * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]),
+                               __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static bool wgrad_om_applies(const TapGemm& g, int O) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("PP_NO_WGRAD_OM"); off = (e && e[0] == '1') ? 1 : 0; }
+  return !off && (O == 64 || O == 128) && g.C % 64 == 0;
+}
+
+static int launch_wgrad_om(const TapGemm& g, const void* x, const void* dz, int O, float* partial, int splits,
+                           cudaStream_t s) {
+  CUtensorMap tmDz, tmX;
+  const long long M = (long long)g.N * g.P * g.Q;
+  PP_TRY(make_map_2d(&tmDz, dz, (uint64_t)M, (uint64_t)O, kWK));
+  int bw = 0, bh = 0, bn = 0;
+  const bool x_tiled = prefer_tiled() && tiled_box_for(g, kWK, &bw, &bh, &bn);
+  if (x_tiled) PP_TRY(make_map_tiled4d(&tmX, x, g, bw, bh, bn));
+  else PP_TRY(make_map_im2col(&tmX, x, g, kWK));
+  WgradOmDev p;
+  p.x_tiled = x_tiled ? 1 : 0;
+  p.M = (int)M; p.P = g.P; p.Q = g.Q; p.PQ = g.P * g.Q;
+  p.base_h = g.base_h; p.base_w = g.base_w; p.step_h = g.step_h; p.step_w = g.step_w;
+  p.C = g.C; p.O = O; p.ntaps = g.ntaps; p.Ktot = g.ntaps * g.C; p.nslabs = p.Ktot / 64;
+  p.chunks_total = (int)((M + kWK - 1) / kWK);
+  p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
+  for (int t = 0; t < g.ntaps; ++t) { p.tap_dh[t] = g.tap_dh[t]; p.tap_dw[t] = g.tap_dw[t]; }
+  p.partial = partial;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_om_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOmSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((p.nslabs + 3) / 4, splits);
+  prof_begin(PROF_WGRAD, 2.0 * (double)M * O * g.ntaps * g.C, g.C, O, g.ntaps, s);
+  wgrad_om_kernel<<<grid, kThreads, kOmSmemBytes, s>>>(tmX, tmDz, p);
+  prof_end(PROF_WGRAD, s);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
 int wgrad_tcgen05(const TapGemm& g, const void* x, const void* dz, int O, float* partial, int splits,
                   cudaStream_t s) {
   PP_TRY(resolve_encoders());
   PP_REQUIRE(wgrad_tcgen05_supported(g, O), PP_EUNSUPPORTED, "tcgen05 wgrad needs C%%64==0 and O%%64==0 (C=%d O=%d)",
              g.C, O);
+  if (wgrad_om_applies(g, O)) return launch_wgrad_om(g, x, dz, O, partial, splits, s);
   switch (wgrad_bn(O)) {
     case 256: return launch_wgrad<256>(g, x, dz, O, partial, splits, s);
     case 128: return launch_wgrad<128>(g, x, dz, O, partial, splits, s);
