@@ -481,3 +481,54 @@ def test_shared_trunk_matches_two_full_passes():
         assert rel_l2(b[3][k], a[3][k]) < 2.5e-2, k
     for k in a[4]:
         assert rel_l2(b[4][k], a[4][k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 8, 16, 128, 3, 1, 1), (2, 128, 16, 8, 64, 3, 2, 1), (2, 64, 12, 20, 64, 1, 1, 0),
+                                   (2, 64, 16, 32, 64, 3, 1, 1)])
+def test_rectangular_feature_maps(shape):
+    """H != W: fprop / dgrad / wgrad against the CPU operator (the reference only uses square maps, the kernels
+    must not assume it)."""
+    N, C, H, W, O, k, s, p = shape
+    spec = F_.ConvSpec(C, O, k, k, s, p)
+    g = torch.Generator().manual_seed(0)
+    x = bf16r(torch.randn(N, C, H, W, generator=g))
+    w = bf16r(torch.randn(O, C, k, k, generator=g) * (2.0 / (C * k * k)) ** 0.5)
+    P, Q = spec.out_hw(H, W)
+    dzc = bf16r(torch.randn(N, O, P, Q, generator=g))
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    z_ref = torch.nn.functional.conv2d(xr, wr, None, s, p)
+    z_ref.backward(dzc)
+    prep = F_.prepare_weight(w.cuda(), spec, True)
+    dz = dzc.permute(0, 2, 3, 1).contiguous().cuda()
+    z = F_.conv_fwd_raw(x.cuda(), prep, spec, z_f32=True).permute(0, 3, 1, 2)
+    dx = F_.conv_dgrad(dz, prep, spec, N, H, W).float().permute(0, 3, 1, 2)
+    dw = F_.conv_wgrad(dz, x.cuda(), spec)
+    assert rel_l2(z, z_ref) < 2e-5
+    assert rel_l2(dx, bf16r(xr.grad)) < ACT_TOL
+    assert rel_l2(dw, wr.grad) < 2e-5
+
+
+def test_conv_block_without_relu_and_in_eval_matches_oracle():
+    for training in (True, False):
+        m = _make_block("conv", 64, 128, 3, 1, 1, "bn", 8, relu=False)
+        with torch.no_grad():
+            m.bn.weight.copy_(torch.rand(128) + 0.5)
+            m.bn.bias.copy_(torch.randn(128) * 0.1)
+            m.bn.running_mean.copy_(torch.randn(128) * 0.1)
+            m.bn.running_var.copy_(torch.rand(128) + 0.5)
+        x = bf16r(torch.randn(6, 64, 8, 8, generator=torch.Generator().manual_seed(3)))
+        oracle = po.mirror(m, round_bf16=True)
+        outs = []
+        for mod, dev in ((oracle, "cpu"), (m.cuda(), "cuda")):
+            mod.train(training)
+            xx = x.to(dev).clone().requires_grad_(True)
+            y = mod(xx)
+            r = bf16r(torch.randn(y.shape, generator=torch.Generator().manual_seed(5))).to(dev)
+            (y.float() * r).sum().backward()
+            outs.append((y.detach().float().cpu(), xx.grad.float().cpu(), mod.conv.weight.grad.float().cpu(),
+                         mod.bn.weight.grad.float().cpu(), mod.bn.bias.grad.float().cpu()))
+        ref, got = outs
+        assert (got[0] < 0).any(), "no ReLU expected"
+        assert rel_l2(got[0], bf16r(ref[0])) < ACT_TOL
+        for a, b in zip(got[1:], ref[1:]):
+            assert rel_l2(a, b) < GRAD_TOL
