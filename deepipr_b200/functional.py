@@ -361,8 +361,10 @@ class _AddReluFn(torch.autograd.Function):
 
 
 def add_relu(a, b):
-    """relu(a + b); fused kernel for dense bf16 tensors of identical layout, torch ops otherwise."""
-    if (a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape == b.shape
+    """relu(a + b) on the GPU: fused kernel for dense bf16 tensors of identical layout (the training configuration);
+    other dtypes / layouts use the stock CUDA ops.  CPU tensors are rejected like everywhere else in this package."""
+    require_cuda(a, "residual input")
+    if (a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape == b.shape
             and a.stride() == b.stride()
             and (a.is_contiguous() or (a.dim() == 4 and a.is_contiguous(memory_format=torch.channels_last)))):
         return _AddReluFn.apply(a, b)
