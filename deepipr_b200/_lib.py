@@ -10,8 +10,8 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpassport_sm100.so")
 
-PP_ABI_VERSION = 7
-PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL = 0, 1, 2
+PP_ABI_VERSION = 8
+PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL, PP_NORM_GN = 0, 1, 2, 3
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1
 
@@ -32,7 +32,7 @@ class PPConvDesc(C.Structure):
         ("stride", C.c_int32), ("pad", C.c_int32),
         ("norm", C.c_int32), ("relu", C.c_int32), ("z_f32", C.c_int32),
         ("eps", C.c_float), ("momentum", C.c_float),
-        ("algo", C.c_int32), ("reserved", C.c_int32),
+        ("algo", C.c_int32), ("groups", C.c_int32),
     ]
 
 

@@ -188,6 +188,12 @@ static void plan_col(const PPConvDesc& d, const Geo& geo, int Kpad, TapGemm& g) 
   g.out_H = 1; g.out_W = (int)geo.rows; g.out_sh = 1; g.out_sw = 1; g.out_ph = 0; g.out_pw = 0; g.out_identity = 1;
 }
 
+// rows of partial[.][2][O] the GroupNorm statistics kernels write (groupnorm.cu)
+static size_t gn_partial_rows(const PPConvDesc& d, const Geo& geo) {
+  if (d.O % 8 != 0 || d.O > 2048) return 1;  // rejected later by the launch; keep the carve well-defined
+  return (size_t)d.N * gn_chunks(d.N, geo.P * geo.Q, d.O);
+}
+
 struct FwdWs {
   float* ca; float* cb; float* partial;
   __nv_bfloat16* col; __nv_bfloat16* wpad;
@@ -197,9 +203,11 @@ static FwdWs carve_fwd(const PPConvDesc& d, const Geo& geo, void* base) {
   FwdWs w;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;
-  w.ca = reinterpret_cast<float*>(p + off); off += align256((size_t)d.O * 4);
-  w.cb = reinterpret_cast<float*>(p + off); off += align256((size_t)d.O * 4);
-  const size_t max_part = (size_t)(bwd_reduce_max_partials() > 160 ? bwd_reduce_max_partials() : 160);
+  const size_t coef_rows = d.norm == PP_NORM_GN ? (size_t)d.N : 1;  // GN/IN: a coefficient row per sample
+  w.ca = reinterpret_cast<float*>(p + off); off += align256(coef_rows * d.O * 4);
+  w.cb = reinterpret_cast<float*>(p + off); off += align256(coef_rows * d.O * 4);
+  size_t max_part = (size_t)(bwd_reduce_max_partials() > 160 ? bwd_reduce_max_partials() : 160);
+  if (d.norm == PP_NORM_GN) max_part = gn_partial_rows(d, geo);
   w.partial = reinterpret_cast<float*>(p + off); off += align256(max_part * 2 * d.O * 4);
   const int Kpad = col_kpad(d, geo);
   w.col = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * (size_t)Kpad * 2);
@@ -209,7 +217,7 @@ static FwdWs carve_fwd(const PPConvDesc& d, const Geo& geo, void* base) {
 }
 
 struct BwdWs {
-  float* ca; float* cb; float* k1; float* k2; float* k3; float* partial;
+  float* ca; float* cb; float* k1; float* k2; float* k3; float* partial; float* contrib;
   __nv_bfloat16* dz; __nv_bfloat16* col; float* wpartial;
   size_t total;
 };
@@ -217,13 +225,16 @@ static BwdWs carve_bwd(const PPConvDesc& d, const Geo& geo, void* base, int wg_s
   BwdWs w;
   uint8_t* p = reinterpret_cast<uint8_t*>(base);
   size_t off = 0;
-  const size_t vec = align256((size_t)d.O * 4);
+  const bool gn = d.norm == PP_NORM_GN;
+  const size_t vec = align256((gn ? (size_t)d.N : 1) * d.O * 4);
   w.ca = reinterpret_cast<float*>(p + off); off += vec;
   w.cb = reinterpret_cast<float*>(p + off); off += vec;
   w.k1 = reinterpret_cast<float*>(p + off); off += vec;
   w.k2 = reinterpret_cast<float*>(p + off); off += vec;
   w.k3 = reinterpret_cast<float*>(p + off); off += vec;
-  w.partial = reinterpret_cast<float*>(p + off); off += align256((size_t)bwd_reduce_max_partials() * 2 * d.O * 4);
+  const size_t part_rows = gn ? gn_partial_rows(d, geo) : (size_t)bwd_reduce_max_partials();
+  w.partial = reinterpret_cast<float*>(p + off); off += align256(part_rows * 2 * d.O * 4);
+  w.contrib = reinterpret_cast<float*>(p + off); off += gn ? align256((size_t)d.N * 2 * d.O * 4) : 0;
   w.dz = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * d.O * 2);
   const int Kpad = col_kpad(d, geo);
   w.col = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * (size_t)Kpad * 2);
@@ -418,8 +429,12 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
   PP_TRY(check_device());
   cudaStream_t s = (cudaStream_t)stream;
   PP_REQUIRE(x && w_fprop && y, PP_EBADARG, "conv block fwd: NULL pointer");
-  PP_REQUIRE(d->norm == PP_NORM_NONE || d->norm == PP_NORM_BN_TRAIN || d->norm == PP_NORM_BN_EVAL, PP_EBADARG,
-             "unknown norm %d", d->norm);
+  PP_REQUIRE(d->norm == PP_NORM_NONE || d->norm == PP_NORM_BN_TRAIN || d->norm == PP_NORM_BN_EVAL ||
+                 d->norm == PP_NORM_GN,
+             PP_EBADARG, "unknown norm %d", d->norm);
+  PP_REQUIRE(d->norm != PP_NORM_GN || z, PP_EBADARG, "group / instance norm needs the z buffer");
+  PP_REQUIRE(d->norm != PP_NORM_GN || (save_mean && save_invstd), PP_EBADARG,
+             "group / instance norm needs save_mean / save_invstd [N*groups]");
   PP_REQUIRE(d->norm != PP_NORM_BN_EVAL || (running_mean && running_var), PP_EBADARG, "BN eval needs running stats");
   PP_REQUIRE(d->norm != PP_NORM_BN_TRAIN || z, PP_EBADARG, "BN train needs the z buffer");
   FwdWs ws = carve_fwd(*d, geo, workspace);
@@ -439,6 +454,9 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
   e.stats_partial = fused_stats ? ws.partial : nullptr;
   bool tc = false;
   PP_TRY(run_fprop(*d, geo, x, w_fprop, e, &tc, ws.col, ws.wpad, s));
+  if (d->norm == PP_NORM_GN)
+    return launch_gn_fwd(*d, geo.P * geo.Q, z, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb, ws.partial,
+                         (__nv_bfloat16*)y, s);
   int num_partials = 0;
   if (d->norm == PP_NORM_BN_TRAIN) {
     if (tc && fused_stats) {
@@ -470,6 +488,16 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
   BwdWs ws = carve_bwd(*d, geo, workspace, splits);
   PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "bwd workspace too small: need %zu, got %zu", ws.total,
              ws_bytes);
+  if (d->norm == PP_NORM_GN) {
+    const int HW = geo.P * geo.Q;
+    PP_TRY(launch_gn_bwd_reduce(*d, HW, (const __nv_bfloat16*)dy, z, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb,
+                                ws.k1, ws.k2, ws.k3, ws.partial, ws.contrib, dgamma, dbeta, s));
+    if (!dx && !dw_oihw) return PP_OK;
+    PP_TRY(launch_gn_dz(*d, HW, (const __nv_bfloat16*)dy, z, ws.ca, ws.cb, ws.k1, ws.k2, ws.k3, ws.dz, s));
+    if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));
+    if (dw_oihw) PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s));
+    return PP_OK;
+  }
   PP_TRY(launch_affine_coef(d->O, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb, s));
   int num_partials = 0;
   PP_TRY(launch_bwd_reduce((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.partial,

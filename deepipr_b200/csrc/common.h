@@ -147,6 +147,17 @@ int launch_im2col_small(const PPConvDesc& d, const __nv_bfloat16* x, __nv_bfloat
 int launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int K, int Kpad, cudaStream_t s);
 int launch_add_relu_fwd(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, size_t n, cudaStream_t s);
 int launch_add_relu_bwd(const __nv_bfloat16* g, const __nv_bfloat16* y, __nv_bfloat16* gx, size_t n, cudaStream_t s);
+// --- groupnorm.cu (GroupNorm / InstanceNorm: per-(sample, group) statistics, per-(sample, channel) coefficients) ---
+int gn_chunks(int N, int HW, int O);  // partial rows per sample written by the statistics kernels
+int launch_gn_fwd(const PPConvDesc& d, int HW, const void* z, const float* gamma, const float* beta, float* save_mean,
+                  float* save_invstd, float* ca, float* cb, float* partial, __nv_bfloat16* y, cudaStream_t s);
+int launch_gn_bwd_reduce(const PPConvDesc& d, int HW, const __nv_bfloat16* dy, const void* z, const float* gamma,
+                         const float* beta, const float* save_mean, const float* save_invstd, float* ca, float* cb,
+                         float* k1, float* k2, float* k3, float* partial, float* contrib, float* dgamma, float* dbeta,
+                         cudaStream_t s);
+int launch_gn_dz(const PPConvDesc& d, int HW, const __nv_bfloat16* dy, const void* z, const float* ca,
+                 const float* cb, const float* k1, const float* k2, const float* k3, __nv_bfloat16* dz,
+                 cudaStream_t s);
 int launch_sgd(size_t n, float* p, const float* g, float* buf, float lr, float mom, float wd, int first,
                cudaStream_t s);
 

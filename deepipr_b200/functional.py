@@ -59,14 +59,15 @@ def weight_epoch():
     return _weight_epoch
 
 
-def make_desc(spec: ConvSpec, N, H, W, norm=L.PP_NORM_NONE, relu=0, z_f32=0, eps=1e-5, momentum=0.1, algo=None):
+def make_desc(spec: ConvSpec, N, H, W, norm=L.PP_NORM_NONE, relu=0, z_f32=0, eps=1e-5, momentum=0.1, algo=None,
+              groups=0):
     algo = ALGO if algo is None else algo
-    key = (spec, N, H, W, norm, relu, z_f32, eps, momentum, algo)
+    key = (spec, N, H, W, norm, relu, z_f32, eps, momentum, algo, groups)
     d = _desc_cache.get(key)
     if d is None:
         d = L.PPConvDesc(N=N, C=spec.C, H=H, W=W, O=spec.O, kh=spec.kh, kw=spec.kw, stride=spec.stride, pad=spec.pad,
                          norm=norm, relu=int(relu), z_f32=int(z_f32), eps=eps, momentum=momentum, algo=algo,
-                         reserved=0)
+                         groups=int(groups))
         _desc_cache[key] = d
         if len(_desc_cache) > 4096:
             _desc_cache.clear()
@@ -259,6 +260,7 @@ class BlockOpts:
     running_var: Optional[torch.Tensor] = None
     out_dtype: Optional[torch.dtype] = None
     algo: Optional[int] = None
+    groups: int = 0           # PP_NORM_GN: number of groups (== O for InstanceNorm)
 
 
 class _ConvBlockFn(torch.autograd.Function):
@@ -275,13 +277,14 @@ class _ConvBlockFn(torch.autograd.Function):
         dev = x.device
         xc = to_nhwc_bf16(x.detach())
         need_grad = any(ctx.needs_input_grad[:4])
-        keep_z = need_grad or o.norm == L.PP_NORM_BN_TRAIN
-        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo)
+        keep_z = need_grad or o.norm in (L.PP_NORM_BN_TRAIN, L.PP_NORM_GN)
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups)
         y = torch.empty((N, spec.O, P, Q), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
         z = torch.empty((N, P, Q, spec.O), dtype=torch.float32 if o.z_f32 else torch.bfloat16, device=dev) \
             if keep_z else None
-        save_mean = torch.empty(spec.O, dtype=torch.float32, device=dev)
-        save_invstd = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        nstat = N * o.groups if o.norm == L.PP_NORM_GN else spec.O   # GN/IN: one (mean, invstd) per sample and group
+        save_mean = torch.empty(nstat, dtype=torch.float32, device=dev)
+        save_invstd = torch.empty(nstat, dtype=torch.float32, device=dev)
         g = None if gamma is None else gamma.detach().reshape(-1).float().contiguous()
         b = None if beta is None else beta.detach().reshape(-1).float().contiguous()
         ws, nbytes = workspace(d, key, L.PP_WS_FWD, dev)
@@ -311,7 +314,7 @@ class _ConvBlockFn(torch.autograd.Function):
         dev = gy.device
         gyc = to_nhwc_bf16(gy)
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo)
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups)
         dx = torch.empty((N, Cx, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last) \
             if need_dx else None
         dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dev) if need_dw else None

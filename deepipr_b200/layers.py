@@ -79,7 +79,19 @@ def _norm_mode(bn_module):
         return L.PP_NORM_BN_EVAL
     if bn_module is None or (isinstance(bn_module, nn.Sequential) and len(bn_module) == 0):
         return L.PP_NORM_NONE
+    if isinstance(bn_module, nn.GroupNorm):
+        return L.PP_NORM_GN
+    if isinstance(bn_module, nn.InstanceNorm2d) and not bn_module.track_running_stats:
+        return L.PP_NORM_GN          # instance norm == group norm with one channel per group
     return None
+
+
+def _norm_groups(bn_module):
+    if isinstance(bn_module, nn.GroupNorm):
+        return bn_module.num_groups
+    if isinstance(bn_module, nn.InstanceNorm2d):
+        return bn_module.num_features
+    return 0
 
 
 class _FusedConvMixin:
@@ -131,9 +143,19 @@ class _FusedConvMixin:
                 bn.num_batches_tracked.add_(1)
             if norm == L.PP_NORM_BN_TRAIN and not bn.training:
                 rm = rv = None  # track_running_stats=False in eval: batch statistics, nothing to update
+        groups = 0
+        if norm == L.PP_NORM_GN:
+            eps, groups = bn.eps, _norm_groups(bn)
+            if isinstance(bn, nn.InstanceNorm2d):
+                spec = self._spec()
+                P, Q = spec.out_hw(x.shape[2], x.shape[3])
+                if P * Q == 1 and bn.training:   # same refusal as F.instance_norm (torch/nn/functional.py)
+                    raise ValueError(f"Expected more than 1 spatial element when training, got input size "
+                                     f"{torch.Size((x.shape[0], spec.O, P, Q))}")
         out_dtype = torch.bfloat16 if (torch.is_autocast_enabled() or x.dtype == torch.bfloat16) else x.dtype
         return F_.BlockOpts(spec=self._spec(), norm=norm, relu=bool(relu), z_f32=bool(z_f32), eps=float(eps),
-                            momentum=float(momentum), running_mean=rm, running_var=rv, out_dtype=out_dtype)
+                            momentum=float(momentum), running_mean=rm, running_var=rv, out_dtype=out_dtype,
+                            groups=int(groups))
 
 
 class ConvBlock(nn.Module, _FusedConvMixin):
@@ -163,7 +185,8 @@ class ConvBlock(nn.Module, _FusedConvMixin):
         norm = _norm_mode(self.bn)
         prepared = self._prepared()
         if norm is None:
-            # GroupNorm / InstanceNorm: fused conv, then the torch norm module (library path)
+            # a norm module this library has no kernel for (e.g. InstanceNorm with running statistics):
+            # fused conv, then the module itself
             o = self._bn_opts(L.PP_NORM_NONE, False, False, x)
             y = F_.conv_block(x, self.conv.weight, None, self.conv.bias, prepared, o)
             y = self.bn(y)
@@ -171,6 +194,7 @@ class ConvBlock(nn.Module, _FusedConvMixin):
         if norm == L.PP_NORM_NONE:
             gamma, beta = None, self.conv.bias
         else:
+            # BatchNorm2d / GroupNorm carry an affine; InstanceNorm2d(o) does not (weight, bias are None)
             gamma, beta = self.bn.weight, self.bn.bias
         o = self._bn_opts(norm, self.relu is not None, self.z_f32, x)
         return F_.conv_block(x, self.conv.weight, gamma, beta, prepared, o)
@@ -333,7 +357,7 @@ class _PassportBase(nn.Module, _FusedConvMixin):
         self._check_conv()
         norm = _norm_mode(self.bn)
         prepared = self._prepared()
-        if norm is None:
+        if norm is None:   # norm module without a kernel here: fused conv, then the module and the affine in torch
             o = self._bn_opts(L.PP_NORM_NONE, False, False, x)
             y = F_.conv_block(x, self.weight, None, None, prepared, o)
             y = self.bn(y)

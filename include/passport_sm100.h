@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 7
+#define PP_ABI_VERSION 8
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -42,7 +42,10 @@ typedef enum PPStatus {
   PP_EBADARG = -6       /* NULL where a pointer is required                 */
 } PPStatus;
 
-enum { PP_NORM_NONE = 0, PP_NORM_BN_TRAIN = 1, PP_NORM_BN_EVAL = 2 };
+/* PP_NORM_GN: statistics per (sample, group) with `groups` groups of O/groups channels — nn.GroupNorm(o // 16, o)
+ * (passportconv2d.py:59-60, conv2d.py:13-14) and, with groups == O, nn.InstanceNorm2d(o) (:61-62, conv2d.py:15-16).
+ * Same arithmetic in train and eval mode (no running statistics). */
+enum { PP_NORM_NONE = 0, PP_NORM_BN_TRAIN = 1, PP_NORM_BN_EVAL = 2, PP_NORM_GN = 3 };
 enum { PP_ALGO_AUTO = 0, PP_ALGO_TCGEN05 = 1, PP_ALGO_SIMT = 2 };
 enum { PP_WS_FWD = 0, PP_WS_BWD = 1 };
 
@@ -55,13 +58,13 @@ typedef struct PPConvDesc {
   int32_t kh, kw;     /* filter size                                             */
   int32_t stride;     /* same in h and w (reference passes one int)              */
   int32_t pad;        /* same in h and w                                         */
-  int32_t norm;       /* PP_NORM_*  (bn in train / eval mode, or no norm)        */
+  int32_t norm;       /* PP_NORM_*  (bn in train / eval mode, group/instance norm, none) */
   int32_t relu;       /* 1: ReLU after the affine                                */
   int32_t z_f32;      /* 1: conv output z kept in fp32, 0: bf16                  */
   float eps;          /* BatchNorm eps (1e-5)                                    */
   float momentum;     /* BatchNorm momentum (0.1)                                */
   int32_t algo;       /* PP_ALGO_*; AUTO picks tcgen05 when C%64==0 && O%64==0   */
-  int32_t reserved;
+  int32_t groups;     /* PP_NORM_GN only: number of groups (O for InstanceNorm); else 0  */
 } PPConvDesc;
 
 int pp_version(void);
@@ -123,10 +126,10 @@ int pp_sign_loss_bwd(int O, const float* gamma, const float* b_sign, float alpha
  *   x        bf16 [N,H,W,C]          w_fprop   bf16 [O,kh,kw,C]
  *   gamma/beta fp32 [O]              running_* fp32 [O]  (updated in BN_TRAIN, read in BN_EVAL, may be NULL for NONE)
  *   z        conv output [N,P,Q,O] (bf16 or fp32 per d->z_f32); NULL => not kept (inference;
- *            then norm must not be BN_TRAIN and the affine is fused into the conv epilogue)
+ *            then norm must not be BN_TRAIN / GN and the affine is fused into the conv epilogue)
  *   y        bf16 [N,P,Q,O]
  *   save_mean / save_invstd fp32 [O]: statistics the backward needs (batch stats, running
- *            stats, or 0/1 for NONE). */
+ *            stats, or 0/1 for NONE); fp32 [N*groups] (per sample and group) for PP_NORM_GN. */
 int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, const float* gamma,
                       const float* beta, float* running_mean, float* running_var, void* z, void* y,
                       float* save_mean, float* save_invstd, void* workspace, size_t ws_bytes,
