@@ -21,7 +21,7 @@ EXPORTS = (
     "pp_passport_affine_fwd", "pp_passport_affine_bwd", "pp_sign_loss_fwd", "pp_sign_loss_bwd",
     "pp_conv_block_fwd", "pp_conv_block_bwd", "pp_conv_fwd_raw", "pp_conv_dgrad", "pp_conv_wgrad",
     "pp_sgd_step", "pp_debug_last_timeout", "pp_launch_count", "pp_profile_enable", "pp_profile_read",
-    "pp_add_relu_fwd", "pp_add_relu_bwd", "pp_passport_key_grad",
+    "pp_add_relu_fwd", "pp_add_relu_bwd", "pp_passport_key_grad", "pp_signature_verify",
 )
 
 
@@ -33,6 +33,16 @@ class PPConvDesc(C.Structure):
         ("norm", C.c_int32), ("relu", C.c_int32), ("z_f32", C.c_int32),
         ("eps", C.c_float), ("momentum", C.c_float),
         ("algo", C.c_int32), ("groups", C.c_int32),
+    ]
+
+
+PP_SIG_MAX_LAYERS = 64
+
+
+class PPSigLayer(C.Structure):
+    _fields_ = [
+        ("w_fprop", C.c_void_p), ("S_skey", C.c_void_p), ("b_sign", C.c_void_p),
+        ("O", C.c_int32), ("K", C.c_int32), ("gamma_offset", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -51,6 +61,7 @@ _PROTOS = {
     "pp_passport_affine_fwd": (C.c_int, [_desc, _vp, _dp, _dp, _fp, _f, _fp, _fp, _fp, _fp, _vp]),
     "pp_passport_affine_bwd": (C.c_int, [_desc, _dp, _dp, _fp, _fp, _f, _fp, _fp, _fp, _fp, _i, _vp]),
     "pp_passport_key_grad": (C.c_int, [_desc, _i, _vp, _fp, _fp, _f, _fp, _fp, _fp, _dp, _fp, _fp, _vp]),
+    "pp_signature_verify": (C.c_int, [_i, C.POINTER(PPSigLayer), _vp, _fp, _vp]),
     "pp_sign_loss_fwd": (C.c_int, [_i, _fp, _fp, _f, _fp, _fp, _vp]),
     "pp_sign_loss_bwd": (C.c_int, [_i, _fp, _fp, _f, _fp, _fp, _vp]),
     "pp_conv_block_fwd": (C.c_int, [_desc, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp, _sz, _vp]),

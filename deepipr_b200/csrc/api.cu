@@ -407,6 +407,21 @@ int pp_passport_key_grad(const PPConvDesc* d, int Bk, const void* w_fprop, const
                                   scratch, scratch + K, dskey_nchw, dkey_nchw, (cudaStream_t)stream);
 }
 
+int pp_signature_verify(int nlayers, const PPSigLayer* layers, int32_t* matched, float* gamma_out, void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(nlayers >= 0 && nlayers <= PP_SIG_MAX_LAYERS, PP_EBADARG, "signature verify: %d layers (max %d per call)",
+             nlayers, PP_SIG_MAX_LAYERS);
+  if (nlayers == 0) return PP_OK;
+  PP_REQUIRE(layers && matched, PP_EBADARG, "signature verify: NULL pointer");
+  for (int i = 0; i < nlayers; ++i) {
+    PP_REQUIRE(layers[i].w_fprop && layers[i].S_skey && layers[i].b_sign, PP_EBADARG,
+               "signature verify: layer %d has a NULL pointer", i);
+    PP_REQUIRE(layers[i].O > 0 && layers[i].K > 0 && layers[i].gamma_offset >= 0, PP_EBADSHAPE,
+               "signature verify: layer %d has O=%d K=%d", i, layers[i].O, layers[i].K);
+  }
+  return launch_signature_verify(nlayers, layers, matched, gamma_out, (cudaStream_t)stream);
+}
+
 int pp_sign_loss_fwd(int O, const float* gamma, const float* b_sign, float alpha, float* sign_loss, float* sign_acc,
                      void* stream) {
   PP_TRY(check_device());

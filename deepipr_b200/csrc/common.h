@@ -117,6 +117,7 @@ int launch_passport_affine_bwd(const PPConvDesc& d, const double* Ss, const doub
 int launch_passport_key_grad(const PPConvDesc& d, int Bk, const __nv_bfloat16* wf, const float* gamma, const float* b,
                              float alpha, const float* gg, const float* gb, const float* gl, double* dSs, double* dSk,
                              float* dskey, float* dkey, cudaStream_t s);
+int launch_signature_verify(int nlayers, const PPSigLayer* layers, int* matched, float* gamma_out, cudaStream_t s);
 int launch_sign_loss_fwd(int O, const float* gamma, const float* b, float alpha, float* loss, float* acc,
                          cudaStream_t s);
 int launch_sign_loss_bwd(int O, const float* gamma, const float* b, float alpha, const float* gl, float* gg,

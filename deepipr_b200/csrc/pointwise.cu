@@ -104,6 +104,49 @@ __global__ void passport_gemv_kernel(const __nv_bfloat16* __restrict__ wf, const
   }
 }
 
+// Ownership verification of a whole model in one launch (TesterPrivate.test_signature, trainer_private.py:37-71):
+// for every passport layer l and channel o, gamma = Wf_l[o,:] . S_skey_l with exactly the arithmetic of
+// passport_gemv_kernel (so the signs are the ones get_scale() yields) and matched[l] += [sign(gamma) == b_l[o]].
+// grid = (ceil(maxO / 8), nlayers), one warp per channel; integer atomics only (deterministic).
+struct SigBatch {
+  PPSigLayer layer[PP_SIG_MAX_LAYERS];
+};
+__global__ void signature_verify_kernel(const __grid_constant__ SigBatch batch, int* __restrict__ matched,
+                                        float* __restrict__ gamma_out) {
+  const PPSigLayer& ly = batch.layer[blockIdx.y];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= ly.O) return;
+  const int K = ly.K;
+  const __nv_bfloat16* row = reinterpret_cast<const __nv_bfloat16*>(ly.w_fprop) + (size_t)warp * K;
+  const double* Ss = ly.S_skey;
+  double g = 0.0;
+  for (int k = lane; k < K; k += 32) g = fma((double)__bfloat162float(row[k]), Ss[k], g);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
+  if (lane == 0) {
+    const float gf = (float)g;
+    const float sg = (float)((gf > 0.f) - (gf < 0.f));
+    if (sg == ly.b_sign[warp]) atomicAdd(&matched[blockIdx.y], 1);
+    if (gamma_out) gamma_out[ly.gamma_offset + warp] = gf;
+  }
+}
+
+int launch_signature_verify(int nlayers, const PPSigLayer* layers, int* matched, float* gamma_out, cudaStream_t s) {
+  SigBatch batch;
+  int maxO = 0;
+  for (int i = 0; i < nlayers; ++i) {
+    batch.layer[i] = layers[i];
+    maxO = layers[i].O > maxO ? layers[i].O : maxO;
+  }
+  PP_CHECK_CUDA(cudaMemsetAsync(matched, 0, sizeof(int) * nlayers, s));
+  const int warps_per_block = 8;
+  signature_verify_kernel<<<dim3((maxO + warps_per_block - 1) / warps_per_block, nlayers), warps_per_block * 32, 0,
+                            s>>>(batch, matched, gamma_out);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
 // SignLoss.add (sign_loss.py:25-28, 53-54): one block, fixed-order tree reduction in fp64.
 __global__ void sign_loss_kernel(const float* __restrict__ gamma, const float* __restrict__ b, float alpha,
                                  float* __restrict__ loss, float* __restrict__ acc, int O) {

@@ -215,6 +215,36 @@ def passport_affine(weight, actx: AffineCtx, skey=None, key=None):
     return out
 
 
+def signature_verify(entries, want_gamma=False):
+    """Batched ownership verification: ``entries`` = [(PreparedWeight, S_skey fp64 [K], b fp32 [O])] for every
+    passport layer (all on one device).  Returns (matched int32 [n] device tensor, O list, gamma list or None);
+    detection of layer i = matched[i] / O[i]  (trainer_private.py:37-71).  One kernel launch per 64 layers."""
+    if not entries:
+        return None, [], ([] if want_gamma else None)
+    dev = entries[0][1].device
+    n = len(entries)
+    matched = torch.empty(n, dtype=torch.int32, device=dev)
+    Os = [int(b.numel()) for _, _, b in entries]
+    gamma = torch.empty(sum(Os), dtype=torch.float32, device=dev) if want_gamma else None
+    keep, ofs = [], 0
+    for start in range(0, n, L.PP_SIG_MAX_LAYERS):
+        chunk = entries[start:start + L.PP_SIG_MAX_LAYERS]
+        arr = (L.PPSigLayer * len(chunk))()
+        for i, (prep, S, b) in enumerate(chunk):
+            require_cuda(S, "pooled skey")
+            bf = b.detach().reshape(-1).float().contiguous()
+            keep.append(bf)
+            O, K = prep.wf.shape[0], prep.wf.numel() // prep.wf.shape[0]
+            if S.numel() != K or bf.numel() != O:
+                raise RuntimeError(f"signature_verify: layer {start + i} has O={O} K={K} but |S|={S.numel()} |b|={bf.numel()}")
+            arr[i] = L.PPSigLayer(prep.wf.data_ptr(), S.data_ptr(), bf.data_ptr(), O, K, ofs, 0)
+            ofs += O
+        L.check(L.load().pp_signature_verify(len(chunk), arr, C.c_void_p(matched[start:].data_ptr()), L.ptr(gamma),
+                                             _stream()), "pp_signature_verify")
+    gammas = list(torch.split(gamma, Os)) if want_gamma else None
+    return matched, Os, gammas
+
+
 class _SignLossFn(torch.autograd.Function):
     """SignLoss.add on an arbitrary scale tensor (sign_loss.py:18-54)."""
 

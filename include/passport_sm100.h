@@ -114,6 +114,27 @@ int pp_passport_key_grad(const PPConvDesc* d, int Bk, const void* w_fprop, const
                          float alpha, const float* g_gamma, const float* g_beta, const float* g_loss,
                          double* scratch, float* dskey_nchw, float* dkey_nchw, void* stream);
 
+/* Ownership verification of every passport layer of a model in ONE launch — the loop of
+ * TesterPrivate.test_signature (experiments/trainer_private.py:37-71; also tester of passport_attack_1.py:112-170):
+ *   signbit = m.get_scale(ind=1).view(-1).sign();  detection = (signbit == m.b).float().mean()
+ * layers: HOST array of nlayers (<= PP_SIG_MAX_LAYERS) entries whose pointers are device pointers:
+ *   w_fprop bf16 [O, K] (pp_weight_prep), S_skey fp64 [K] (pp_key_pool of skey), b_sign fp32 [O] (+-1), K = kh*kw*C.
+ * matched: device int32 [nlayers], overwritten with the number of channels whose sign(gamma) equals b
+ *   (detection = matched / O).  gamma_out: NULL or device fp32 buffer; layer i writes its gamma at
+ *   gamma_out[layers[i].gamma_offset ...].  The arithmetic is that of pp_passport_affine_fwd, so the bits are
+ *   identical to the per-layer path. */
+#define PP_SIG_MAX_LAYERS 64
+typedef struct PPSigLayer {
+  const void* w_fprop;
+  const double* S_skey;
+  const float* b_sign;
+  int32_t O;
+  int32_t K;
+  int32_t gamma_offset;
+  int32_t reserved;
+} PPSigLayer;
+int pp_signature_verify(int nlayers, const PPSigLayer* layers, int32_t* matched, float* gamma_out, void* stream);
+
 /* Stand-alone SignLoss.add on an arbitrary scale vector (sign_loss.py:18-54). */
 int pp_sign_loss_fwd(int O, const float* gamma, const float* b_sign, float alpha, float* sign_loss,
                      float* sign_acc, void* stream);

@@ -581,3 +581,36 @@ def test_instance_norm_single_pixel_training_is_refused_like_torch():
     m = _make_block("v1", 64, 64, 3, 2, 1, "in", 2).cuda().train()
     with pytest.raises(ValueError, match="Expected more than 1 spatial element"):
         m(torch.randn(2, 64, 2, 2, device="cuda"))
+
+
+def test_batched_signature_verification_equals_per_layer_path():
+    """pp_signature_verify (all passport layers, one launch) returns exactly what the reference's per-layer loop
+    (get_scale + sign + compare, trainer_private.py:37-71) returns, and its gamma bits are those of get_scale()."""
+    from deepipr_b200.trainer import test_signature, test_signature_per_layer
+    seed_all(4)
+    kw = nets.passport_kwargs_from_config(nets.resnet18_passport_config(("layer3", "layer4"),
+                                                                        signature="this is my signature"))
+    model = quiet(nets.ResNet18, "private", 10, kw).cuda()
+    with torch.no_grad():   # random keys of the right shape for every passport layer
+        model.train()
+        model(torch.randn(2, 3, 32, 32, device="cuda"), ind=1)
+    batched = test_signature(model)
+    looped = test_signature_per_layer(model)
+    assert list(batched) == list(looped) and len(batched) == 10
+    for k in looped:
+        assert batched[k] == looped[k], k
+    blocks = [m for m in model.modules() if isinstance(m, layers.PassportPrivateBlock)]
+    entries = [(m._prepared(), m._pooled_keys()[0], m.b) for m in blocks]
+    matched, Os, gammas = F_.signature_verify(entries, want_gamma=True)
+    with torch.no_grad():
+        for m, g, o, c in zip(blocks, gammas, Os, matched.tolist()):
+            ref = m.get_scale(ind=1).reshape(-1)
+            assert torch.equal(g, ref) and o == ref.numel()
+            assert c == int((ref.sign() == m.b).sum())
+    # a V1 block with a learnable scale (init_scale(True)) reports on that scale, as get_scale() does
+    v1 = _make_block("v1", 64, 64, 3, 1, 1, "bn", 8).cuda()
+    v1.init_scale(True)
+    with torch.no_grad():
+        v1.scale.copy_(-v1.b)
+    holder = torch.nn.Sequential(v1)
+    assert test_signature(holder) == {"public_0": 0.0} == test_signature_per_layer(holder)
