@@ -484,7 +484,12 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
   }
   PP_TRY(launch_bn_finalize(*d, (int)geo.rows, ws.partial, num_partials, gamma, beta, running_mean, running_var,
                             save_mean, save_invstd, ws.ca, ws.cb, s));
-  return launch_affine_apply(z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, (__nv_bfloat16*)y, s);
+  // algorithmic bytes of the pass: read z once, write y (bf16) once
+  const double zb = d->z_f32 ? 4.0 : 2.0;
+  prof_begin(PROF_AFFINE, (double)geo.rows * d->O * (zb + 2.0), d->C, d->O, geo.T, s);
+  const int rc = launch_affine_apply(z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, (__nv_bfloat16*)y, s);
+  prof_end(PROF_AFFINE, s);
+  return rc;
 }
 
 int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad, const void* z,
@@ -515,13 +520,20 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
   }
   PP_TRY(launch_affine_coef(d->O, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb, s));
   int num_partials = 0;
-  PP_TRY(launch_bwd_reduce((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.partial,
-                           &num_partials, s));
+  const double zb = d->z_f32 ? 4.0 : 2.0;
+  prof_begin(PROF_REDUCE, (double)geo.rows * d->O * (zb + 2.0), d->C, d->O, geo.T, s);   // read dy + z
+  const int rc_red = launch_bwd_reduce((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu,
+                                       ws.partial, &num_partials, s);
+  prof_end(PROF_REDUCE, s);
+  PP_TRY(rc_red);
   PP_TRY(launch_bwd_coef(*d, geo.rows, ws.partial, num_partials, gamma, save_mean, save_invstd, dgamma, dbeta, ws.k1,
                          ws.k2, ws.k3, s));
   if (!dx && !dw_oihw) return PP_OK;
-  PP_TRY(launch_bwd_dz((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.k1, ws.k2,
-                       ws.k3, ws.dz, s));
+  prof_begin(PROF_DZ, (double)geo.rows * d->O * (zb + 4.0), d->C, d->O, geo.T, s);       // read dy + z, write dz
+  const int rc_dz = launch_bwd_dz((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.k1,
+                                  ws.k2, ws.k3, ws.dz, s);
+  prof_end(PROF_DZ, s);
+  PP_TRY(rc_dz);
   if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));
   if (dw_oihw) PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s));
   return PP_OK;

@@ -80,8 +80,9 @@ struct TapEpilogue {
 };
 
 void count_launch();
-// optional per-kernel CUDA-event timing of the two tensor-core kernels (bench.py roofline leg)
-enum { PROF_TAPGEMM = 0, PROF_WGRAD = 1, PROF_KINDS = 2 };
+// optional per-kernel CUDA-event timing (bench.py roofline legs): the two tensor-core kernels (work = FLOPs) and the
+// three HBM-bound passes of the block (work = algorithmic bytes: affine z->y, backward reduce, dz)
+enum { PROF_TAPGEMM = 0, PROF_WGRAD = 1, PROF_AFFINE = 2, PROF_REDUCE = 3, PROF_DZ = 4, PROF_KINDS = 5 };
 void prof_begin(int kind, double flops, int c, int nout, int taps, cudaStream_t s);
 void prof_end(int kind, cudaStream_t s);
 

@@ -14,6 +14,29 @@ static inline int grid_for(size_t work_items, int threads, int max_blocks) {
   return (int)b;
 }
 
+// Grid of a grid-stride streaming kernel: every resident slot of the chip, once (no partial last wave), rounded so
+// that grid*threads is a whole number of `vec_per_row`-vector rows whenever possible (the kernels then keep their
+// per-channel coefficients in registers).
+template <typename Kern>
+static int streaming_grid(Kern kernel, int* cached_occ, size_t work_items, int threads, int vec_per_row) {
+  if (*cached_occ <= 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      occ = 4;
+    }
+    *cached_occ = occ;
+  }
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  int grid = grid_for(work_items, threads, sms * *cached_occ);
+  int a = vec_per_row, b = threads;   // q = vec_per_row / gcd(vec_per_row, threads)
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int q = vec_per_row / (a > 0 ? a : 1);
+  if (q > 1 && grid >= q) grid -= grid % q;
+  return grid;
+}
+
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // ---------------------------------------------------------------------------------------------
@@ -411,7 +434,42 @@ __global__ void affine_apply_kernel(const void* __restrict__ z, int z_f32, size_
                                     const float* __restrict__ a, const float* __restrict__ b, int relu,
                                     __nv_bfloat16* __restrict__ y) {
   const int vec_per_row = O >> 3;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (stride % vec_per_row == 0) {
+    // the grid stride is a whole number of rows: this thread's 8 channels never change, so the coefficient
+    // vectors are loaded once and the loop is pure streaming (two independent vectors in flight per trip)
+    float ca[8], cb[8];
+    const int ch = (int)(i0 % vec_per_row) << 3;
+    load8_coef(a, ch, ca);
+    load8_coef(b, ch, cb);
+    size_t i = i0;
+    for (; i + stride < nvec; i += 2 * stride) {
+      float v0[8], v1[8];
+      load8(z, z_f32, i, v0);
+      load8(z, z_f32, i + stride, v1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v0[k] = fmaf(v0[k], ca[k], cb[k]);
+        v1[k] = fmaf(v1[k], ca[k], cb[k]);
+        if (relu) { v0[k] = fmaxf(v0[k], 0.0f); v1[k] = fmaxf(v1[k], 0.0f); }
+      }
+      store8_bf16(y, i, v0);
+      store8_bf16(y, i + stride, v1);
+    }
+    if (i < nvec) {
+      float v[8];
+      load8(z, z_f32, i, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] = fmaf(v[k], ca[k], cb[k]);
+        if (relu) v[k] = fmaxf(v[k], 0.0f);
+      }
+      store8_bf16(y, i, v);
+    }
+    return;
+  }
+  for (size_t i = i0; i < nvec; i += stride) {
     const int ch = (int)(i % vec_per_row) << 3;
     float v[8], ca[8], cb[8];
     load8(z, z_f32, i, v);
@@ -430,7 +488,9 @@ int launch_affine_apply(const void* z, int z_f32, size_t rows, int O, const floa
                         __nv_bfloat16* y, cudaStream_t s) {
   PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "affine pass needs O%%8==0 (O=%d)", O);
   const size_t nvec = rows * (size_t)(O / 8);
-  affine_apply_kernel<<<grid_for(nvec, 256, 148 * 8), 256, 0, s>>>(z, z_f32, nvec, O, a, b, relu, y);
+  static int occ = 0;
+  affine_apply_kernel<<<streaming_grid(affine_apply_kernel, &occ, nvec, 256, O / 8), 256, 0, s>>>(z, z_f32, nvec, O, a,
+                                                                                                 b, relu, y);
   PP_POST_LAUNCH();
   return PP_OK;
 }
@@ -587,7 +647,50 @@ __global__ void bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const void* 
                               const float* __restrict__ k1, const float* __restrict__ k2,
                               const float* __restrict__ k3, __nv_bfloat16* __restrict__ dz) {
   const int vec_per_row = O >> 3;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (stride % vec_per_row == 0) {
+    // fixed channels per thread (see affine_apply_kernel): the five coefficient vectors live in registers
+    float ca[8], cb[8], c1[8], c2[8], c3[8];
+    const int ch = (int)(i0 % vec_per_row) << 3;
+    load8_coef(a, ch, ca);
+    load8_coef(b, ch, cb);
+    load8_coef(k1, ch, c1);
+    load8_coef(k2, ch, c2);
+    load8_coef(k3, ch, c3);
+    size_t i = i0;
+    for (; i + stride < nvec; i += 2 * stride) {
+      float z0[8], z1[8], g0[8], g1[8], o0[8], o1[8];
+      load8(z, z_f32, i, z0);
+      load8(z, z_f32, i + stride, z1);
+      load8_bf16(dy, i, g0);
+      load8_bf16(dy, i + stride, g1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float gm0 = g0[k], gm1 = g1[k];
+        if (relu && !(fmaf(z0[k], ca[k], cb[k]) > 0.0f)) gm0 = 0.0f;
+        if (relu && !(fmaf(z1[k], ca[k], cb[k]) > 0.0f)) gm1 = 0.0f;
+        o0[k] = fmaf(c1[k], gm0, fmaf(c2[k], z0[k], c3[k]));
+        o1[k] = fmaf(c1[k], gm1, fmaf(c2[k], z1[k], c3[k]));
+      }
+      store8_bf16(dz, i, o0);
+      store8_bf16(dz, i + stride, o1);
+    }
+    if (i < nvec) {
+      float zv[8], g[8], out[8];
+      load8(z, z_f32, i, zv);
+      load8_bf16(dy, i, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float gm = g[k];
+        if (relu && !(fmaf(zv[k], ca[k], cb[k]) > 0.0f)) gm = 0.0f;
+        out[k] = fmaf(c1[k], gm, fmaf(c2[k], zv[k], c3[k]));
+      }
+      store8_bf16(dz, i, out);
+    }
+    return;
+  }
+  for (size_t i = i0; i < nvec; i += stride) {
     const int ch = (int)(i % vec_per_row) << 3;
     float zv[8], g[8], ca[8], cb[8], c1[8], c2[8], c3[8], out[8];
     load8(z, z_f32, i, zv);
@@ -612,7 +715,9 @@ int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows
                   cudaStream_t s) {
   PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "dz pass needs O%%8==0 (O=%d)", O);
   const size_t nvec = rows * (size_t)(O / 8);
-  bwd_dz_kernel<<<grid_for(nvec, 256, 148 * 8), 256, 0, s>>>(dy, z, z_f32, nvec, O, a, b, relu, k1, k2, k3, dz);
+  static int occ = 0;
+  bwd_dz_kernel<<<streaming_grid(bwd_dz_kernel, &occ, nvec, 256, O / 8), 256, 0, s>>>(dy, z, z_f32, nvec, O, a, b, relu,
+                                                                                     k1, k2, k3, dz);
   PP_POST_LAUNCH();
   return PP_OK;
 }
