@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpassport_sm100.so")
-SOURCES = ["api.cu", "igemm_sm100.cu", "direct_conv.cu", "pointwise.cu", "groupnorm.cu"]
+SOURCES = ["api.cu", "igemm_sm100.cu", "direct_conv.cu", "pointwise.cu", "groupnorm.cu", "stem_conv.cu"]
 HEADERS = ["common.h", "ptx.cuh", "vec8.cuh", os.path.join("..", "..", "include", "passport_sm100.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

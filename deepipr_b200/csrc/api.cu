@@ -247,6 +247,10 @@ static BwdWs carve_bwd(const PPConvDesc& d, const Geo& geo, void* base, int wg_s
 
 static int wgrad_splits_for(const PPConvDesc& d, const Geo& geo, bool* tc) {
   TapGemm g;
+  if (stem_direct_supported(d)) {   // one partial tile per CTA of stem_wgrad_kernel
+    *tc = false;
+    return stem_grid(d);
+  }
   const int Kpad = col_kpad(d, geo);
   if (Kpad) {
     plan_col(d, geo, Kpad, g);
@@ -259,15 +263,24 @@ static int wgrad_splits_for(const PPConvDesc& d, const Geo& geo, bool* tc) {
 }
 
 // scratch: col / wpad are only touched on the small-C im2col path (may be NULL otherwise)
+// *stats_rows (optional) receives the number of rows of e.stats_partial the kernel wrote (0: none)
 static int run_fprop(const PPConvDesc& d, const Geo& geo, const void* x, const void* wf, const TapEpilogue& e,
-                     bool* used_tc, __nv_bfloat16* col, __nv_bfloat16* wpad, cudaStream_t s) {
+                     bool* used_tc, __nv_bfloat16* col, __nv_bfloat16* wpad, cudaStream_t s,
+                     int* stats_rows = nullptr) {
   TapGemm g;
+  if (stats_rows) *stats_rows = 0;
+  if (stem_direct_supported(d)) {
+    if (used_tc) *used_tc = false;
+    if (stats_rows && e.stats_partial) *stats_rows = stem_grid(d);
+    return stem_fprop(d, x, wf, e, s);
+  }
   const int Kpad = col_kpad(d, geo);
   if (Kpad && col && wpad) {
     PP_TRY(launch_im2col_small(d, (const __nv_bfloat16*)x, col, geo.rows, geo.P, geo.Q, Kpad, s));
     PP_TRY(launch_pad_rows((const __nv_bfloat16*)wf, wpad, d.O, geo.T * d.C, Kpad, s));
     plan_col(d, geo, Kpad, g);
     if (used_tc) *used_tc = true;
+    if (stats_rows && e.stats_partial) *stats_rows = tapgemm_tcgen05_grid(g);
     return tapgemm_tcgen05(g, col, wpad, e, s);
   }
   plan_fprop(d, geo, g);
@@ -275,7 +288,10 @@ static int run_fprop(const PPConvDesc& d, const Geo& geo, const void* x, const v
   PP_REQUIRE(tc || d.algo != PP_ALGO_TCGEN05, PP_EUNSUPPORTED, "PP_ALGO_TCGEN05 requested but C=%d O=%d unsupported",
              d.C, d.O);
   if (used_tc) *used_tc = tc;
-  if (tc) return tapgemm_tcgen05(g, x, wf, e, s);
+  if (tc) {
+    if (stats_rows && e.stats_partial) *stats_rows = tapgemm_tcgen05_grid(g);
+    return tapgemm_tcgen05(g, x, wf, e, s);
+  }
   TapEpilogue e2 = e;
   e2.stats_partial = nullptr;
   return tapgemm_simt(g, x, wf, e2, s);
@@ -307,6 +323,10 @@ static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
 static int run_wgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const void* x, float* dw, float* wpartial,
                      __nv_bfloat16* col, int splits, bool tc, cudaStream_t s) {
   TapGemm g;
+  if (stem_direct_supported(d)) {
+    PP_TRY(stem_wgrad(d, x, dz, wpartial, s));
+    return launch_wgrad_finalize(d, wpartial, splits, geo.T * d.C, dw, s);
+  }
   const int Kpad = col_kpad(d, geo);
   if (Kpad && col) {
     PP_TRY(launch_im2col_small(d, (const __nv_bfloat16*)x, col, geo.rows, geo.P, geo.Q, Kpad, s));
@@ -468,16 +488,15 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
   const bool fused_stats = d->norm == PP_NORM_BN_TRAIN && d->O <= tapgemm_tcgen05_max_stats_width();
   e.stats_partial = fused_stats ? ws.partial : nullptr;
   bool tc = false;
-  PP_TRY(run_fprop(*d, geo, x, w_fprop, e, &tc, ws.col, ws.wpad, s));
+  int stats_rows = 0;   // rows of ws.partial the conv kernel's epilogue wrote (0: it has no fused statistics)
+  PP_TRY(run_fprop(*d, geo, x, w_fprop, e, &tc, ws.col, ws.wpad, s, &stats_rows));
   if (d->norm == PP_NORM_GN)
     return launch_gn_fwd(*d, geo.P * geo.Q, z, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb, ws.partial,
                          (__nv_bfloat16*)y, s);
   int num_partials = 0;
   if (d->norm == PP_NORM_BN_TRAIN) {
-    if (tc && fused_stats) {
-      TapGemm g;
-      plan_fprop(*d, geo, g);
-      num_partials = tapgemm_tcgen05_grid(g);
+    if (stats_rows > 0) {
+      num_partials = stats_rows;
     } else {
       PP_TRY(launch_col_stats(z, d->z_f32, geo.rows, d->O, ws.partial, &num_partials, s));
     }

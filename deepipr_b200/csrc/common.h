@@ -106,6 +106,12 @@ int tapgemm_simt(const TapGemm& g, const void* act, const void* B, const TapEpil
 int wgrad_simt(const TapGemm& g, const void* x, const void* dz, int O, float* partial, int splits, cudaStream_t s);
 int wgrad_simt_pick_splits(const TapGemm& g, int O);
 
+// --- stem_conv.cu (direct CUDA-core kernels for the 3 -> 64 channel 3x3/s1/p1 stem) ---
+bool stem_direct_supported(const PPConvDesc& d);
+int stem_grid(const PPConvDesc& d);  // CTAs launched == rows of stats_partial / wgrad partial tiles written
+int stem_fprop(const PPConvDesc& d, const void* x, const void* wf, const TapEpilogue& e, cudaStream_t s);
+int stem_wgrad(const PPConvDesc& d, const void* x, const void* dz, float* partial /*[grid][64][27]*/, cudaStream_t s);
+
 // --- pointwise.cu ---
 int launch_weight_prep(const PPConvDesc& d, const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s);
 int launch_key_pool(const PPConvDesc& d, int Bk, const float* key, double* S, cudaStream_t s);

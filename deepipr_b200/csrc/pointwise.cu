@@ -524,7 +524,47 @@ __global__ void column_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
       load8_coef(a, col * 8, ca);
       load8_coef(b, col * 8, cb);
     }
-    for (size_t r = (size_t)blockIdx.x * row_lanes + rl; r < rows; r += (size_t)gridDim.x * row_lanes) {
+    const size_t rstride = (size_t)gridDim.x * row_lanes;
+    size_t r = (size_t)blockIdx.x * row_lanes + rl;
+    // two rows per trip: all four loads are issued before the first use (more bytes in flight per thread);
+    // the accumulation order r, r + rstride, r + 2 rstride, ... is unchanged
+    for (; r + rstride < rows; r += 2 * rstride) {
+      const size_t v0 = r * vec_per_row + col, v1 = (r + rstride) * vec_per_row + col;
+      float z0[8], z1[8];
+      load8(z, z_f32, v0, z0);
+      load8(z, z_f32, v1, z1);
+      if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s1[k] += z0[k];
+          s2[k] = fmaf(z0[k], z0[k], s2[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s1[k] += z1[k];
+          s2[k] = fmaf(z1[k], z1[k], s2[k]);
+        }
+      } else {
+        float g0[8], g1[8];
+        load8_bf16(dy, v0, g0);
+        load8_bf16(dy, v1, g1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float gm = g0[k];
+          if (relu && !(fmaf(z0[k], ca[k], cb[k]) > 0.0f)) gm = 0.0f;
+          s1[k] += gm;
+          s2[k] = fmaf(gm, z0[k], s2[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float gm = g1[k];
+          if (relu && !(fmaf(z1[k], ca[k], cb[k]) > 0.0f)) gm = 0.0f;
+          s1[k] += gm;
+          s2[k] = fmaf(gm, z1[k], s2[k]);
+        }
+      }
+    }
+    if (r < rows) {
       const size_t vi = r * vec_per_row + col;
       float zv[8];
       load8(z, z_f32, vi, zv);
@@ -566,10 +606,24 @@ static int column_reduce_launch(int mode, const __nv_bfloat16* dy, const void* z
   PP_REQUIRE(O % 8 == 0 && O / 8 <= kRedThreads, PP_EBADSHAPE, "column reduce needs O%%8==0 and O<=2048 (O=%d)", O);
   const int vec_per_row = O / 8;
   const int row_lanes = kRedThreads / vec_per_row;
-  size_t blocks = (rows + row_lanes - 1) / row_lanes;
-  if (blocks > (size_t)kRedMaxBlocks) blocks = kRedMaxBlocks;
-  if (blocks < 1) blocks = 1;
   const size_t smem = (size_t)row_lanes * 2 * O * sizeof(float);
+  // one wave: every block gets the same share of rows, so a partial second wave would cost a full one
+  static int occ[2] = {0, 0};
+  if (occ[mode] <= 0) {
+    int o = 0;
+    cudaError_t e = mode == 0
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, column_reduce_kernel<0>, kRedThreads, smem)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, column_reduce_kernel<1>, kRedThreads, smem);
+    if (e != cudaSuccess || o < 1) { cudaGetLastError(); o = 2; }
+    occ[mode] = o;
+  }
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  size_t max_blocks = (size_t)sms * occ[mode];
+  if (max_blocks > (size_t)kRedMaxBlocks) max_blocks = kRedMaxBlocks;
+  size_t blocks = (rows + row_lanes - 1) / row_lanes;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
   if (mode == 0) {
     static bool attr0 = false;
     if (!attr0) {

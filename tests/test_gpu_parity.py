@@ -614,3 +614,46 @@ def test_batched_signature_verification_equals_per_layer_path():
         v1.scale.copy_(-v1.b)
     holder = torch.nn.Sequential(v1)
     assert test_signature(holder) == {"public_0": 0.0} == test_signature_per_layer(holder)
+
+
+@pytest.mark.parametrize("shape", [(3, 20, 20), (2, 12, 40), (1, 5, 70), (5, 32, 32)])
+def test_direct_stem_kernels_ragged_shapes(shape):
+    """stem_conv.cu (3 -> 64 channels, 3x3/s1/p1): fprop, fused statistics, eval epilogue and wgrad on maps that do
+    not fill the 8 x 32 tile, against the operator the reference calls and against the SIMT kernels."""
+    N, H, W = shape
+    spec = F_.ConvSpec(3, 64, 3, 3, 1, 1)
+    g = torch.Generator().manual_seed(21)
+    x = bf16r(torch.randn(N, 3, H, W, generator=g))
+    w = bf16r(torch.randn(64, 3, 3, 3, generator=g) * 0.3)
+    dzc = bf16r(torch.randn(N, 64, H, W, generator=g))
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    z_ref = torch.nn.functional.conv2d(xr, wr, None, 1, 1)
+    z_ref.backward(dzc)
+    prep = F_.prepare_weight(w.cuda(), spec, True)
+    dz = dzc.permute(0, 2, 3, 1).contiguous().cuda()
+    z = F_.conv_fwd_raw(x.cuda(), prep, spec, z_f32=True).permute(0, 3, 1, 2)
+    zb = F_.conv_fwd_raw(x.cuda(), prep, spec, z_f32=False).float().permute(0, 3, 1, 2)
+    dw = F_.conv_wgrad(dz, x.cuda(), spec)
+    assert rel_l2(z, z_ref) < 2e-5
+    assert rel_l2(zb, bf16r(z_ref)) < ACT_TOL
+    assert rel_l2(dw, wr.grad) < 2e-5
+    z_simt = F_.conv_fwd_raw(x.cuda(), prep, spec, z_f32=True, algo=L.PP_ALGO_SIMT).permute(0, 3, 1, 2)
+    assert rel_l2(z, z_simt) < 1e-5
+    # whole block: training statistics (fused into the stem kernel) and the eval epilogue (affine + ReLU folded in)
+    seed_all(1)
+    m = layers.ConvBlock(3, 64, 3, 1, 1, bn="bn", relu=True)
+    with torch.no_grad():
+        m.conv.weight.copy_(w)
+        m.bn.weight.copy_(torch.rand(64) + 0.5)
+        m.bn.bias.copy_(torch.randn(64) * 0.1)
+    oracle = po.mirror(m, round_bf16=True)
+    ref = _fwd_bwd(oracle, "conv", x, "cpu", (0,))
+    got = _fwd_bwd(m.cuda(), "conv", x, "cuda", (0,))
+    assert rel_l2(got["y"][0], bf16r(ref["y"][0])) < ACT_TOL
+    for key, gref in ref["grads"].items():
+        assert rel_l2(got["grads"][key], gref) < GRAD_TOL, key
+    assert rel_l2(m.bn.running_mean.cpu(), oracle.bn.running_mean) < VEC_TOL
+    assert rel_l2(m.bn.running_var.cpu(), oracle.bn.running_var) < VEC_TOL
+    m.eval(); oracle.eval()
+    with torch.no_grad():
+        assert rel_l2(m(x.cuda()).float().cpu(), bf16r(oracle(x))) < ACT_TOL
