@@ -779,15 +779,20 @@ int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows
 // ---------------------------------------------------------------------------------------------
 // weight-gradient finalise: dw[o][c][t] = sum_split partial[split][o][t*C + c]   (one block per o)
 // ---------------------------------------------------------------------------------------------
+// grid = (ceil(C / 32), O): a block reduces the splits for one output channel and 32 input channels over all T taps
+// (coalesced 128-byte reads along c for every tap), transposes (t, c) -> (c, t) through shared memory and writes the
+// cn * T contiguous floats of dw[o][c0 .. c0+cn)[T].  Summation order over the splits is ascending, as before.
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dw, int O,
                                       int C, int T, int kstride) {
-  const int K = T * C;
-  const size_t total = (size_t)O * K;
+  __shared__ float s_t[kMaxTaps][33];
+  const int o = blockIdx.y;
+  const int c0 = blockIdx.x * 32;
+  const int cn = C - c0 < 32 ? C - c0 : 32;
   const size_t split_stride = (size_t)O * kstride;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % K);
-    const int o = (int)(i / K);
-    const float* src = partial + (size_t)o * kstride + k;
+  for (int idx = threadIdx.x; idx < T * 32; idx += blockDim.x) {
+    const int t = idx >> 5, cc = idx & 31;
+    if (cc >= cn) continue;
+    const float* src = partial + (size_t)o * kstride + (size_t)t * C + c0 + cc;
     float acc = 0.0f;
     int sidx = 0;
     for (; sidx + 4 <= splits; sidx += 4) {   // fixed summation order, four loads in flight
@@ -798,17 +803,23 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int spl
       acc = (((acc + a0) + a1) + a2) + a3;
     }
     for (; sidx < splits; ++sidx) acc += src[(size_t)sidx * split_stride];
-    const int t = k / C;
-    const int c = k - t * C;
-    dw[((size_t)o * C + c) * T + t] = acc;
+    s_t[t][cc] = acc;
+  }
+  __syncthreads();
+  float* dst = dw + ((size_t)o * C + c0) * T;
+  for (int j = threadIdx.x; j < cn * T; j += blockDim.x) {
+    const int cc = j / T, t = j - cc * T;
+    dst[j] = s_t[t][cc];
   }
 }
 
 int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, int kstride, float* dw_oihw,
                           cudaStream_t s) {
   const int T = d.kh * d.kw;
-  const size_t total = (size_t)d.O * T * d.C;
-  wgrad_finalize_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
+  PP_REQUIRE(T <= kMaxTaps, PP_EUNSUPPORTED, "wgrad finalize: %d taps > %d", T, kMaxTaps);
+  PP_REQUIRE(d.O <= 65535, PP_EBADSHAPE, "wgrad finalize: O=%d > 65535", d.O);
+  const int threads = T * 32 >= 256 ? 256 : (T * 32 >= 128 ? 128 : 64);
+  wgrad_finalize_kernel<<<dim3((d.C + 31) / 32, d.O), threads, 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
   PP_POST_LAUNCH();
   return PP_OK;
 }
