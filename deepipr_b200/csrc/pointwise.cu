@@ -777,49 +777,92 @@ int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight-gradient finalise: dw[o][c][t] = sum_split partial[split][o][t*C + c]   (one block per o)
+// weight-gradient finalise: dw[o][c][t] = sum_split partial[split][o][t*C + c]
 // ---------------------------------------------------------------------------------------------
-// grid = (ceil(C / 32), O): a block reduces the splits for one output channel and 32 input channels over all T taps
-// (coalesced 128-byte reads along c for every tap), transposes (t, c) -> (c, t) through shared memory and writes the
-// cn * T contiguous floats of dw[o][c0 .. c0+cn)[T].  Summation order over the splits is ascending, as before.
+// A block is (items, split groups) = (256 / G, G) threads.  An item is 4 consecutive k of one output channel (one
+// 128-bit load per split; scalar items when K or the row stride is not a multiple of 4).  Group g sums the splits
+// s = g, g + G, ... (four loads in flight), the groups are combined in shared memory in group order: a fixed
+// summation order, so results are run-to-run deterministic.  G grows with the split count so that the layers with
+// few outputs and many splits (64-channel layers: 98 splits) still put enough loads in flight.
+template <bool VEC4>
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dw, int O,
                                       int C, int T, int kstride) {
-  __shared__ float s_t[kMaxTaps][33];
-  const int o = blockIdx.y;
-  const int c0 = blockIdx.x * 32;
-  const int cn = C - c0 < 32 ? C - c0 : 32;
+  __shared__ float4 s_g[256];
+  const int ipb = blockDim.x, G = blockDim.y, g = threadIdx.y;
+  const int K = T * C;
+  const int per_row = VEC4 ? K >> 2 : K;
+  const size_t total = (size_t)O * per_row;
   const size_t split_stride = (size_t)O * kstride;
-  for (int idx = threadIdx.x; idx < T * 32; idx += blockDim.x) {
-    const int t = idx >> 5, cc = idx & 31;
-    if (cc >= cn) continue;
-    const float* src = partial + (size_t)o * kstride + (size_t)t * C + c0 + cc;
-    float acc = 0.0f;
-    int sidx = 0;
-    for (; sidx + 4 <= splits; sidx += 4) {   // fixed summation order, four loads in flight
-      const float a0 = src[(size_t)(sidx + 0) * split_stride];
-      const float a1 = src[(size_t)(sidx + 1) * split_stride];
-      const float a2 = src[(size_t)(sidx + 2) * split_stride];
-      const float a3 = src[(size_t)(sidx + 3) * split_stride];
-      acc = (((acc + a0) + a1) + a2) + a3;
+  for (size_t base = (size_t)blockIdx.x * ipb; base < total; base += (size_t)gridDim.x * ipb) {
+    const size_t item = base + threadIdx.x;
+    const bool valid = item < total;
+    const int o = valid ? (int)(item / per_row) : 0;
+    const int k0 = valid ? (int)(item - (size_t)o * per_row) * (VEC4 ? 4 : 1) : 0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      const float* src = partial + (size_t)o * kstride + k0;
+      int sidx = g;
+      if (VEC4) {
+        for (; sidx + 3 * G < splits; sidx += 4 * G) {
+          const float4 a0 = *reinterpret_cast<const float4*>(src + (size_t)sidx * split_stride);
+          const float4 a1 = *reinterpret_cast<const float4*>(src + (size_t)(sidx + G) * split_stride);
+          const float4 a2 = *reinterpret_cast<const float4*>(src + (size_t)(sidx + 2 * G) * split_stride);
+          const float4 a3 = *reinterpret_cast<const float4*>(src + (size_t)(sidx + 3 * G) * split_stride);
+          acc.x = (((acc.x + a0.x) + a1.x) + a2.x) + a3.x;
+          acc.y = (((acc.y + a0.y) + a1.y) + a2.y) + a3.y;
+          acc.z = (((acc.z + a0.z) + a1.z) + a2.z) + a3.z;
+          acc.w = (((acc.w + a0.w) + a1.w) + a2.w) + a3.w;
+        }
+        for (; sidx < splits; sidx += G) {
+          const float4 a0 = *reinterpret_cast<const float4*>(src + (size_t)sidx * split_stride);
+          acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+        }
+      } else {
+        for (; sidx + 3 * G < splits; sidx += 4 * G) {
+          const float a0 = src[(size_t)sidx * split_stride];
+          const float a1 = src[(size_t)(sidx + G) * split_stride];
+          const float a2 = src[(size_t)(sidx + 2 * G) * split_stride];
+          const float a3 = src[(size_t)(sidx + 3 * G) * split_stride];
+          acc.x = (((acc.x + a0) + a1) + a2) + a3;
+        }
+        for (; sidx < splits; sidx += G) acc.x += src[(size_t)sidx * split_stride];
+      }
     }
-    for (; sidx < splits; ++sidx) acc += src[(size_t)sidx * split_stride];
-    s_t[t][cc] = acc;
-  }
-  __syncthreads();
-  float* dst = dw + ((size_t)o * C + c0) * T;
-  for (int j = threadIdx.x; j < cn * T; j += blockDim.x) {
-    const int cc = j / T, t = j - cc * T;
-    dst[j] = s_t[t][cc];
+    if (G > 1) {
+      s_g[g * ipb + threadIdx.x] = acc;
+      __syncthreads();
+      if (g == 0) {
+        for (int gg = 1; gg < G; ++gg) {
+          const float4 v = s_g[gg * ipb + threadIdx.x];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+      __syncthreads();
+    }
+    if (g == 0 && valid) {
+      const float out[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < (VEC4 ? 4 : 1); ++j) {
+        const int k = k0 + j;
+        const int t = k / C;
+        const int c = k - t * C;
+        dw[((size_t)o * C + c) * T + t] = out[j];
+      }
+    }
   }
 }
 
 int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, int kstride, float* dw_oihw,
                           cudaStream_t s) {
   const int T = d.kh * d.kw;
-  PP_REQUIRE(T <= kMaxTaps, PP_EUNSUPPORTED, "wgrad finalize: %d taps > %d", T, kMaxTaps);
-  PP_REQUIRE(d.O <= 65535, PP_EBADSHAPE, "wgrad finalize: O=%d > 65535", d.O);
-  const int threads = T * 32 >= 256 ? 256 : (T * 32 >= 128 ? 128 : 64);
-  wgrad_finalize_kernel<<<dim3((d.C + 31) / 32, d.O), threads, 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
+  const int K = T * d.C;
+  const bool vec4 = (K % 4 == 0) && (kstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(partial) & 15) == 0);
+  const int G = splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1));
+  const int ipb = 256 / G;
+  const size_t total = (size_t)d.O * (vec4 ? K / 4 : K);
+  const int grid = grid_for(total, ipb, 148 * 8);
+  if (vec4) wgrad_finalize_kernel<true><<<grid, dim3(ipb, G), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
+  else wgrad_finalize_kernel<false><<<grid, dim3(ipb, G), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
   PP_POST_LAUNCH();
   return PP_OK;
 }

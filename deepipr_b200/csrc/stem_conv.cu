@@ -8,8 +8,8 @@
 //           of 4 pixels whose 3 x 6 x 3 input patch is read from a zero-padded shared-memory halo tile with
 //           broadcast 128-bit loads; every pixel is one coalesced 256-byte (fp32) / 128-byte (bf16) store per warp;
 //           the BatchNorm statistics (sum z, sum z^2 per channel) are plain per-lane running sums.
-//   wgrad : same walk, 2 x 27 accumulators per lane, dz read as coalesced bf16x2; warps are combined in a fixed
-//           order in shared memory, blocks by wgrad_finalize (deterministic).
+//   wgrad : same walk, 2 x 27 accumulators per lane, the tile's dz staged in shared memory by 128-bit loads; warps
+//           are combined in a fixed order in shared memory, blocks by wgrad_finalize (deterministic).
 // The data gradient of the stem is not needed in training (images carry no gradient); when it is requested the
 // generic tap-GEMM path computes it.
 #include <stdlib.h>
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(kStemThreads, 2)
 stem_wgrad_kernel(const __grid_constant__ StemDev p, const __nv_bfloat16* __restrict__ x,
                   const __nv_bfloat16* __restrict__ dz /*[N*H*W, 64]*/, float* __restrict__ partial) {
   __shared__ __align__(16) float s_in[kStemHaloRows * kStemRowF];
+  __shared__ __align__(16) __nv_bfloat16 s_dz[kStemTH * kStemTW * kStemO];   // the tile's dz, [row][px][64]: 32 KiB
   __shared__ float s_red[kStemO * kStemK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = 2 * lane;
@@ -197,10 +198,19 @@ stem_wgrad_kernel(const __grid_constant__ StemDev p, const __nv_bfloat16* __rest
     stem_tile_coords(p, tile, n, p0, q0);
     __syncthreads();
     stem_load_halo(x, s_in, n, p0, q0, p.H, p.W);
+    // dz of the tile through shared memory: eight independent 128-bit loads per thread are in flight at once
+    // (a per-strip global load would expose its latency 8 times per row); pixels outside the image read as 0
+    for (int idx = threadIdx.x; idx < kStemTH * kStemTW * 8; idx += kStemThreads) {
+      const int row = idx >> 8, px = (idx >> 3) & 31, part = idx & 7;
+      const int pr_ = p0 + row, q_ = q0 + px;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (pr_ < p.H && q_ < p.W)
+        v = *reinterpret_cast<const uint4*>(dz + (((size_t)n * p.H + pr_) * p.W + q_) * kStemO + part * 8);
+      reinterpret_cast<uint4*>(s_dz)[idx] = v;
+    }
     __syncthreads();
     const int pr = p0 + warp;
     if (pr >= p.H) continue;
-    const size_t row_base = ((size_t)n * p.H + pr) * p.W;
 #pragma unroll 1
     for (int s = 0; s < kStemTW / 4; ++s) {
       const int qs = q0 + 4 * s;
@@ -208,12 +218,9 @@ stem_wgrad_kernel(const __grid_constant__ StemDev p, const __nv_bfloat16* __rest
       float d0[4], d1[4];
 #pragma unroll
       for (int px = 0; px < 4; ++px) {
-        d0[px] = d1[px] = 0.0f;
-        if (qs + px < p.W) {
-          const float2 f = __bfloat1622float2(
-              *reinterpret_cast<const __nv_bfloat162*>(dz + (row_base + qs + px) * kStemO + c0));
-          d0[px] = f.x; d1[px] = f.y;
-        }
+        const float2 f = __bfloat1622float2(
+            *reinterpret_cast<const __nv_bfloat162*>(s_dz + ((warp * kStemTW) + 4 * s + px) * kStemO + c0));
+        d0[px] = f.x; d1[px] = f.y;
       }
 #pragma unroll
       for (int dh = 0; dh < 3; ++dh) {

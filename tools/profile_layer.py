@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 LAYERS = {  # name: (C, O, k, s, p, H)
     "layer1": (64, 64, 3, 1, 1, 32), "layer2": (128, 128, 3, 1, 1, 16), "layer3": (256, 256, 3, 1, 1, 8),
     "layer4": (512, 512, 3, 1, 1, 4), "layer4s2": (256, 512, 3, 2, 1, 8), "layer4sc": (256, 512, 1, 2, 0, 8),
-    "alex4": (192, 384, 3, 1, 1, 8), "alex5": (384, 256, 3, 1, 1, 8), "imagenet4": (512, 512, 3, 1, 1, 7),
+    "stem": (3, 64, 3, 1, 1, 32), "alex4": (192, 384, 3, 1, 1, 8), "alex5": (384, 256, 3, 1, 1, 8), "imagenet4": (512, 512, 3, 1, 1, 7),
 }
 
 
@@ -48,7 +48,7 @@ def main():
         m.set_key(torch.rand(1, Ci, H, H) * 2 - 1, torch.rand(1, Ci, H, H) * 2 - 1)
     m = m.cuda().train()
     x = torch.randn(args.batch, Ci, H, H, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    x.requires_grad_(True)
+    x.requires_grad_(Ci != 3)      # the network input carries no gradient
     P = (H + 2 * p - k) // s + 1
     gy = torch.randn(args.batch, O, P, P, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     lib = L.load()
