@@ -1204,10 +1204,12 @@ bool wgrad_tcgen05_supported(const TapGemm& g, int O) {
 static int wgrad_bn(int O) { return (O % 256 == 0) ? 256 : ((O % 128 == 0) ? 128 : 64); }
 
 static bool wgrad_om_applies(const TapGemm& g, int O);
+static bool wgrad_om_paired(const TapGemm& g, int O);
 
 int wgrad_pick_splits(const TapGemm& g, int O) {
   const int Ktot = g.ntaps * g.C;
-  const int tiles = wgrad_om_applies(g, O) ? (Ktot / 64 + 3) / 4 : ((Ktot + 127) / 128) * (O / wgrad_bn(O));
+  const int tiles = wgrad_om_paired(g, O) ? 2
+                    : wgrad_om_applies(g, O) ? (Ktot / 64 + 3) / 4 : ((Ktot + 127) / 128) * (O / wgrad_bn(O));
   const long long M = (long long)g.N * g.P * g.Q;
   const int chunks = (int)((M + kWK - 1) / kWK);
   int sms = device_sm_count();
@@ -1265,11 +1267,20 @@ static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, 
 // in 197.  Here A = dz slabs (MN-major, o contiguous; the second slab is TMA-zero-filled when O = 64) and
 // B = four 64-wide (tap, c) slabs of x.
 // ------------------------------------------------------------------------------------------------
+//
+// Tap pairing (O == C == 64, 3x3 / stride 1 / pad 1: the layer1 convs).  With O = 64 the upper 64 accumulator rows
+// would multiply zeros.  Instead they get dz shifted down by one image row (a 4-D TMA box on dz, rows past the image
+// zero-filled): against the x slab of tap (dh, dw) the lower rows accumulate dW[(dh, dw)] and the upper rows
+//   sum_pixel dz[pixel + Q] x[pixel + (dh, dw)] = sum_pixel' dz[pixel'] x[pixel' + (dh - 1, dw)] = dW[(dh - 1, dw)]
+// (the pixel' in image row 0 that the shift drops only ever meets the zero padding row when dh - 1 = 0).  Two CTAs
+// columns of N = 192 — taps (1, .) giving dW[1, .] and dW[0, .], taps (2, .) giving dW[2, .] — replace three of
+// N = 256: 6 slab products instead of 12 for the 9 useful ones.
 struct WgradOmDev {
   int M, P, Q, PQ;
   int base_h, base_w, step_h, step_w;
   int C, O, ntaps, Ktot, nslabs;
   int x_tiled;
+  int paired;   // 1: tap pairing (see above); grid.x == 2
   int chunks_total, chunks_per_split;
   int8_t tap_dh[kMaxTaps], tap_dw[kMaxTaps];
   float* partial;  // [splits][O][Ktot]
@@ -1283,6 +1294,7 @@ constexpr int kOmSmemBytes = 1024 + kOmStages * kOmStageBytes + 256;
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_om_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDz,
+                const __grid_constant__ CUtensorMap tmDzS /*dz as [N,P,Q,O], row-shifted loads (paired mode)*/,
                 const __grid_constant__ WgradOmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1300,10 +1312,13 @@ wgrad_om_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   int chunk_hi = chunk_lo + p.chunks_per_split;
   if (chunk_hi > p.chunks_total) chunk_hi = p.chunks_total;
   const int nchunks = chunk_hi > chunk_lo ? chunk_hi - chunk_lo : 0;
+  const int paired = p.paired;
+  const int nb = paired ? 3 : 4;            // x slabs per stage
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDz);
     tma_prefetch_desc(&tmX);
+    if (paired) tma_prefetch_desc(&tmDzS);
     for (int i = 0; i < kOmStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -1329,8 +1344,13 @@ wgrad_om_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int k0 = sidx * 64;
       tap[i] = k0 / p.C;
       c0[i] = k0 - tap[i] * p.C;
+      if (paired) {   // C == 64: slab == tap; this CTA column owns filter row dh = n_tile + 1
+        tap[i] = (n_tile + 1) * 3 + (i < 3 ? i : 0);
+        c0[i] = 0;
+      }
     }
     const int x_tiled = p.x_tiled;
+    const uint32_t stage_tx = kOmStageA + nb * kWK * 128;
     int stage = 0;
     uint32_t phase = 0;
     for (int ch = chunk_lo; ch < chunk_lo + nchunks; ++ch) {
@@ -1345,11 +1365,15 @@ wgrad_om_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (elect_one()) {
         uint8_t* sa = smem + stage * kOmStageBytes;
         uint8_t* sb = sa + kOmStageA;
-        mbar_arrive_expect_tx(&full[stage], kOmStageBytes);
+        mbar_arrive_expect_tx(&full[stage], stage_tx);
         tma_load_2d(&tmDz, &full[stage], sa, 0, m0);
-        tma_load_2d(&tmDz, &full[stage], sa + kWK * 128, 64, m0);   // all zeros (out of bounds) when O == 64
+        if (paired && n_tile == 0)   // dz one image row further down; rows past the image read as zeros
+          tma_load_4d(&tmDzS, &full[stage], sa + kWK * 128, 0, 0, p0 + 1, img);
+        else
+          tma_load_2d(&tmDz, &full[stage], sa + kWK * 128, 64, m0);   // all zeros (out of bounds) when O == 64
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          if (i >= nb) break;
           const int dw = p.tap_dw[tap[i]], dh = p.tap_dh[tap[i]];
           if (x_tiled) tma_load_4d(&tmX, &full[stage], sb + i * kWK * 128, c0[i], cw + dw, chh + dh, img);
           else tma_load_im2col_4d(&tmX, &full[stage], sb + i * kWK * 128, c0[i], cw, chh, img, (uint16_t)dw,
@@ -1360,7 +1384,7 @@ wgrad_om_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (++stage == kOmStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, 256, 1, 1);
+    const uint32_t idesc = paired ? make_idesc_bf16(128, 192, 1, 1) : make_idesc_bf16(128, 256, 1, 1);
     const uint32_t smem0 = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
@@ -1391,8 +1415,19 @@ wgrad_om_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
     const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
     float* dst_row = p.partial + ((size_t)split * p.O + (size_t)o) * p.Ktot + (size_t)n_tile * 256;
+    int nj = 8;
+    bool row_valid = o < p.O;
+    if (paired) {
+      // rows 0..63: dW[o][(dh = n_tile + 1, dw)] ; rows 64..127: dW[o - 64][(dh - 1, dw)], kept for dh - 1 == 0 only
+      const bool hi = o >= 64;
+      const int orow = hi ? o - 64 : o;
+      const int kbase = hi ? 0 : (n_tile + 1) * 192;
+      row_valid = !hi || n_tile == 0;
+      dst_row = p.partial + ((size_t)split * p.O + (size_t)orow) * p.Ktot + kbase;
+      nj = 6;
+    }
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < nj; ++j) {
       uint32_t raw[32];
       if (nchunks > 0) {
         tmem_ld_32x32(taddr + j * 32, raw);
@@ -1401,8 +1436,8 @@ wgrad_om_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 32; ++i) raw[i] = 0u;
       }
-      const bool slab_valid = (n_tile * 4 + (j >> 1)) < p.nslabs;
-      if (o < p.O && slab_valid) {
+      const bool slab_valid = paired || (n_tile * 4 + (j >> 1)) < p.nslabs;
+      if (row_valid && slab_valid) {
         float4* dst = reinterpret_cast<float4*>(dst_row + j * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -1426,11 +1461,32 @@ static bool wgrad_om_applies(const TapGemm& g, int O) {
   return !off && (O == 64 || O == 128) && g.C % 64 == 0;
 }
 
+// tap pairing needs: O == C == 64, canonical 3x3 / stride 1 / pad 1 tap list, and chunks of kWK pixels that are whole
+// rows of one image (so the row-shifted dz chunk is a 4-D box)
+static bool wgrad_om_paired(const TapGemm& g, int O) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("PP_NO_WGRAD_PAIR"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off || !wgrad_om_applies(g, O)) return false;
+  if (O != 64 || g.C != 64 || g.ntaps != 9 || g.step_h != 1 || g.step_w != 1 || g.base_h != -1 || g.base_w != -1)
+    return false;
+  if (g.P != g.H || g.Q != g.W || g.Q > kWK || kWK % g.Q != 0 || (g.P * g.Q) % kWK != 0) return false;
+  for (int t = 0; t < 9; ++t)
+    if (g.tap_dh[t] != t / 3 || g.tap_dw[t] != t % 3) return false;
+  return true;
+}
+
 static int launch_wgrad_om(const TapGemm& g, const void* x, const void* dz, int O, float* partial, int splits,
                            cudaStream_t s) {
-  CUtensorMap tmDz, tmX;
+  CUtensorMap tmDz, tmX, tmDzS;
   const long long M = (long long)g.N * g.P * g.Q;
   PP_TRY(make_map_2d(&tmDz, dz, (uint64_t)M, (uint64_t)O, kWK));
+  const bool paired = wgrad_om_paired(g, O);
+  tmDzS = tmDz;
+  if (paired) {
+    TapGemm gz = g;   // dz viewed as an NHWC image [N, P, Q, O]
+    gz.C = O; gz.H = g.P; gz.W = g.Q;
+    PP_TRY(make_map_tiled4d(&tmDzS, dz, gz, g.Q, kWK / g.Q, 1));
+  }
   int bw = 0, bh = 0, bn = 0;
   const bool x_tiled = prefer_tiled() && tiled_box_for(g, kWK, &bw, &bh, &bn);
   if (x_tiled) PP_TRY(make_map_tiled4d(&tmX, x, g, bw, bh, bn));
@@ -1440,6 +1496,7 @@ static int launch_wgrad_om(const TapGemm& g, const void* x, const void* dz, int 
   p.M = (int)M; p.P = g.P; p.Q = g.Q; p.PQ = g.P * g.Q;
   p.base_h = g.base_h; p.base_w = g.base_w; p.step_h = g.step_h; p.step_w = g.step_w;
   p.C = g.C; p.O = O; p.ntaps = g.ntaps; p.Ktot = g.ntaps * g.C; p.nslabs = p.Ktot / 64;
+  p.paired = paired ? 1 : 0;
   p.chunks_total = (int)((M + kWK - 1) / kWK);
   p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
   for (int t = 0; t < g.ntaps; ++t) { p.tap_dh[t] = g.tap_dh[t]; p.tap_dw[t] = g.tap_dw[t]; }
@@ -1449,9 +1506,9 @@ static int launch_wgrad_om(const TapGemm& g, const void* x, const void* dz, int 
     PP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_om_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOmSmemBytes));
     attr_set = true;
   }
-  dim3 grid((p.nslabs + 3) / 4, splits);
+  dim3 grid(paired ? 2 : (p.nslabs + 3) / 4, splits);
   prof_begin(PROF_WGRAD, 2.0 * (double)M * O * g.ntaps * g.C, g.C, O, g.ntaps, s);
-  wgrad_om_kernel<<<grid, kThreads, kOmSmemBytes, s>>>(tmX, tmDz, p);
+  wgrad_om_kernel<<<grid, kThreads, kOmSmemBytes, s>>>(tmX, tmDz, tmDzS, p);
   prof_end(PROF_WGRAD, s);
   PP_POST_LAUNCH();
   return PP_OK;

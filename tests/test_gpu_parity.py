@@ -72,6 +72,9 @@ GEOMS = [  # N, C, H, O, k, s, p
     (5, 256, 7, 256, 3, 1, 1), (3, 128, 14, 256, 3, 2, 1), (1, 64, 4, 64, 3, 1, 1),
     # geometries that take the pixels-on-N kernel (<=128 output columns, 32x32 / 16x16 maps), incl. strided dgrad
     (3, 128, 16, 128, 3, 1, 1), (2, 64, 32, 128, 3, 2, 1), (2, 64, 32, 128, 1, 2, 0), (2, 128, 32, 64, 3, 1, 1),
+    # 64 -> 64 channels: tap-paired weight gradient (row-shifted dz in the upper accumulator rows) at 2 / 4 / 8 image
+    # rows per 64-pixel chunk, batch 1 included
+    (3, 64, 16, 64, 3, 1, 1), (1, 64, 32, 64, 3, 1, 1), (5, 64, 8, 64, 3, 1, 1),
 ]
 
 
