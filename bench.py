@@ -296,11 +296,12 @@ def main():
         if msp > 0 and roof is not None:
             ach = flp / (msp * 1e-3) / 1e12
             # traffic: dram__bytes_read+write per launch from the ncu --set full capture of this geometry at batch
-            # 1024 (profiles/r1_tapgemm_layer4.txt), scaled to this batch; algorithmic = x + W bytes
+            # 1184 (profiles/r1b_ncu_layer4_batch1184.txt: fprop 24.17 + 0.51 MB, dgrad 24.17 MB), scaled to this
+            # batch; algorithmic = x + W bytes (the fp32 z / bf16 dx tile stays in the 126 MB L2 for the next pass)
             roof["passport_layer"] = {"geometry": "layer4 3x3 512->512 @4x4, fprop+dgrad launches", "achieved": ach,
                                       "frac": ach / pk["tflops"], "launches_per_step": npl // 3,
                                       "avg_launch_us": msp * 1e3 / max(npl, 1),
-                                      "traffic": 21.53e6 * B / 1024.0,
+                                      "traffic": 24.42e6 * B / 1184.0,
                                       "algorithmic_bytes": 2.0 * (B * 16 * 512 + 512 * 4608)}
         # the HBM-bound passes of the block: algorithmic bytes / CUDA-event time
         hbm_parts, tot_ms, tot_b = {}, 0.0, 0.0
@@ -316,7 +317,12 @@ def main():
             ach = tot_b / (tot_ms * 1e-3) / 1e9
             roof_hbm = {"kernel": "affine_apply + column_reduce<1> + bwd_dz (norm/affine/ReLU passes)", "bound": "hbm",
                         "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                        "peak_source": pk["src"] + " copy bandwidth", "traffic": None,
+                        "peak_source": pk["src"] + " copy bandwidth",
+                        # dram bytes per launch at the layer1 geometry, batch 1184 (profiles/r1b_ncu_layer1_pointwise.txt)
+                        "traffic": {"geometry": "layer1 64ch 32x32, batch 1184",
+                                    "affine_apply": 421.5e6, "bwd_reduce": 469.4e6, "bwd_dz": 599.1e6,
+                                    "algorithmic": {"affine_apply": 465.6e6, "bwd_reduce": 465.6e6,
+                                                    "bwd_dz": 620.8e6}},
                         "share_of_step": (tot_ms / 3) / (ms_total / args.steps), "per_kernel": hbm_parts,
                         "note": "small layers (layer3/4) re-read z/dy from the 126 MB L2, so a per-kernel figure can "
                                 "exceed the HBM peak; the aggregate is dominated by layer1/2"}
