@@ -321,23 +321,23 @@ static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
 }
 
 static int run_wgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const void* x, float* dw, float* wpartial,
-                     __nv_bfloat16* col, int splits, bool tc, cudaStream_t s) {
+                     __nv_bfloat16* col, int splits, bool tc, cudaStream_t s, int accumulate = 0) {
   TapGemm g;
   if (stem_direct_supported(d)) {
     PP_TRY(stem_wgrad(d, x, dz, wpartial, s));
-    return launch_wgrad_finalize(d, wpartial, splits, geo.T * d.C, dw, s);
+    return launch_wgrad_finalize(d, wpartial, splits, geo.T * d.C, dw, s, accumulate);
   }
   const int Kpad = col_kpad(d, geo);
   if (Kpad && col) {
     PP_TRY(launch_im2col_small(d, (const __nv_bfloat16*)x, col, geo.rows, geo.P, geo.Q, Kpad, s));
     plan_col(d, geo, Kpad, g);
     PP_TRY(wgrad_tcgen05(g, col, dz, d.O, wpartial, splits, s));
-    return launch_wgrad_finalize(d, wpartial, splits, Kpad, dw, s);
+    return launch_wgrad_finalize(d, wpartial, splits, Kpad, dw, s, accumulate);
   }
   plan_fprop(d, geo, g);
   if (tc) PP_TRY(wgrad_tcgen05(g, x, dz, d.O, wpartial, splits, s));
   else PP_TRY(wgrad_simt(g, x, dz, d.O, wpartial, splits, s));
-  return launch_wgrad_finalize(d, wpartial, splits, geo.T * d.C, dw, s);
+  return launch_wgrad_finalize(d, wpartial, splits, geo.T * d.C, dw, s, accumulate);
 }
 
 }  // namespace pp
@@ -534,7 +534,8 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
     if (!dx && !dw_oihw) return PP_OK;
     PP_TRY(launch_gn_dz(*d, HW, (const __nv_bfloat16*)dy, z, ws.ca, ws.cb, ws.k1, ws.k2, ws.k3, ws.dz, s));
     if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));
-    if (dw_oihw) PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s));
+    if (dw_oihw)
+      PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s, d->flags & PP_FLAG_ACC_DW));
     return PP_OK;
   }
   PP_TRY(launch_affine_coef(d->O, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb, s));
@@ -554,7 +555,8 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
   prof_end(PROF_DZ, s);
   PP_TRY(rc_dz);
   if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));
-  if (dw_oihw) PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s));
+  if (dw_oihw)
+    PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s, d->flags & PP_FLAG_ACC_DW));
   return PP_OK;
 }
 

@@ -149,7 +149,7 @@ int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows
                   const float* b, int relu, const float* k1, const float* k2, const float* k3, __nv_bfloat16* dz,
                   cudaStream_t s);
 int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, int kstride, float* dw_oihw,
-                          cudaStream_t s);
+                          cudaStream_t s, int accumulate = 0);
 int launch_im2col_small(const PPConvDesc& d, const __nv_bfloat16* x, __nv_bfloat16* col, size_t rows, int P, int Q,
                         int Kpad, cudaStream_t s);
 int launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int K, int Kpad, cudaStream_t s);

@@ -211,7 +211,8 @@ __global__ void gn_bwd_coef_kernel(const float* __restrict__ partial, int chunks
 
 // dgamma[o] = sum_n contrib[n][0][o], dbeta[o] = sum_n contrib[n][1][o]; block (32 channels, 32 sample slices)
 __global__ void __launch_bounds__(1024) gn_dparam_kernel(const float* __restrict__ contrib, int N, int O,
-                                                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                         int flags) {
   __shared__ double sh1[32][33], sh2[32][33];
   const int o = blockIdx.x * 32 + threadIdx.x;
   const int slice = threadIdx.y;
@@ -231,8 +232,8 @@ __global__ void __launch_bounds__(1024) gn_dparam_kernel(const float* __restrict
     s1 += sh1[k][threadIdx.x];
     s2 += sh2[k][threadIdx.x];
   }
-  dgamma[o] = (float)s1;
-  dbeta[o] = (float)s2;
+  dgamma[o] = (flags & PP_FLAG_ACC_DGAMMA) ? dgamma[o] + (float)s1 : (float)s1;
+  dbeta[o] = (flags & PP_FLAG_ACC_DBETA) ? dbeta[o] + (float)s2 : (float)s2;
 }
 
 // dz[r,o] = k1[n,o]*dy_m + k2[n,o]*z + k3[n,o]
@@ -318,7 +319,7 @@ int launch_gn_bwd_reduce(const PPConvDesc& d, int HW, const __nv_bfloat16* dy, c
   gn_bwd_coef_kernel<<<(ng + 127) / 128, 128, 0, s>>>(partial, chunks, d.N, d.O, d.groups, HW, gamma, save_mean,
                                                       save_invstd, contrib, k1, k2, k3);
   PP_POST_LAUNCH();
-  gn_dparam_kernel<<<(d.O + 31) / 32, dim3(32, 32), 0, s>>>(contrib, d.N, d.O, dgamma, dbeta);
+  gn_dparam_kernel<<<(d.O + 31) / 32, dim3(32, 32), 0, s>>>(contrib, d.N, d.O, dgamma, dbeta, d.flags);
   PP_POST_LAUNCH();
   return PP_OK;
 }

@@ -665,15 +665,15 @@ __global__ void __launch_bounds__(1024) bwd_coef_kernel(int norm, double n, cons
                                 const float* __restrict__ gamma, const float* __restrict__ mean,
                                 const float* __restrict__ invstd, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2,
-                                float* __restrict__ k3, int O) {
+                                float* __restrict__ k3, int O, int flags) {
   const int o = blockIdx.x * 32 + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
   if (!reduce_partials_32x32(partial, num, O, o, s1, s2)) return;
   const double mu = mean[o], is = invstd[o];
   const double g = gamma ? (double)gamma[o] : 1.0;
   const double dg = is * (s2 - mu * s1);
-  dgamma[o] = (float)dg;
-  dbeta[o] = (float)s1;
+  dgamma[o] = (flags & PP_FLAG_ACC_DGAMMA) ? dgamma[o] + (float)dg : (float)dg;
+  dbeta[o] = (flags & PP_FLAG_ACC_DBETA) ? dbeta[o] + (float)s1 : (float)s1;
   const double a = g * is;
   if (norm == PP_NORM_BN_TRAIN) {
     const double c2 = -a * is * dg / n;
@@ -691,7 +691,7 @@ int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int 
                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* k1,
                     float* k2, float* k3, cudaStream_t s) {
   bwd_coef_kernel<<<(d.O + 31) / 32, dim3(32, 32), 0, s>>>(d.norm, (double)rows, partial, num_partials, gamma, save_mean,
-                                                save_invstd, dgamma, dbeta, k1, k2, k3, d.O);
+                                                save_invstd, dgamma, dbeta, k1, k2, k3, d.O, d.flags);
   PP_POST_LAUNCH();
   return PP_OK;
 }
@@ -786,7 +786,7 @@ int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows
 // few outputs and many splits (64-channel layers: 98 splits) still put enough loads in flight.
 template <bool VEC4>
 __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dw, int O,
-                                      int C, int T, int kstride) {
+                                      int C, int T, int kstride, int accumulate) {
   __shared__ float4 s_g[256];
   const int ipb = blockDim.x, G = blockDim.y, g = threadIdx.y;
   const int K = T * C;
@@ -846,14 +846,15 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int spl
         const int k = k0 + j;
         const int t = k / C;
         const int c = k - t * C;
-        dw[((size_t)o * C + c) * T + t] = out[j];
+        float* dst = dw + ((size_t)o * C + c) * T + t;
+        *dst = accumulate ? *dst + out[j] : out[j];
       }
     }
   }
 }
 
 int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, int kstride, float* dw_oihw,
-                          cudaStream_t s) {
+                          cudaStream_t s, int accumulate) {
   const int T = d.kh * d.kw;
   const int K = T * d.C;
   const bool vec4 = (K % 4 == 0) && (kstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(partial) & 15) == 0);
@@ -861,8 +862,11 @@ int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits,
   const int ipb = 256 / G;
   const size_t total = (size_t)d.O * (vec4 ? K / 4 : K);
   const int grid = grid_for(total, ipb, 148 * 8);
-  if (vec4) wgrad_finalize_kernel<true><<<grid, dim3(ipb, G), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
-  else wgrad_finalize_kernel<false><<<grid, dim3(ipb, G), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride);
+  if (vec4)
+    wgrad_finalize_kernel<true><<<grid, dim3(ipb, G), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride, accumulate);
+  else
+    wgrad_finalize_kernel<false><<<grid, dim3(ipb, G), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride,
+                                                               accumulate);
   PP_POST_LAUNCH();
   return PP_OK;
 }

@@ -60,14 +60,14 @@ def weight_epoch():
 
 
 def make_desc(spec: ConvSpec, N, H, W, norm=L.PP_NORM_NONE, relu=0, z_f32=0, eps=1e-5, momentum=0.1, algo=None,
-              groups=0):
+              groups=0, flags=0):
     algo = ALGO if algo is None else algo
-    key = (spec, N, H, W, norm, relu, z_f32, eps, momentum, algo, groups)
+    key = (spec, N, H, W, norm, relu, z_f32, eps, momentum, algo, groups, flags)
     d = _desc_cache.get(key)
     if d is None:
         d = L.PPConvDesc(N=N, C=spec.C, H=H, W=W, O=spec.O, kh=spec.kh, kw=spec.kw, stride=spec.stride, pad=spec.pad,
                          norm=norm, relu=int(relu), z_f32=int(z_f32), eps=eps, momentum=momentum, algo=algo,
-                         groups=int(groups))
+                         groups=int(groups), flags=int(flags))
         _desc_cache[key] = d
         if len(_desc_cache) > 4096:
             _desc_cache.clear()
@@ -291,6 +291,25 @@ class BlockOpts:
     out_dtype: Optional[torch.dtype] = None
     algo: Optional[int] = None
     groups: int = 0           # PP_NORM_GN: number of groups (== O for InstanceNorm)
+    #: the block's weight / gamma / beta are Parameters that receive gradients from this operator ONLY (ConvBlock):
+    #: when they live in a parallel.FlatParams their gradients are accumulated straight into the flat buffer by
+    #: the producing kernels (PP_FLAG_ACC_*), and autograd sees no gradient for them
+    direct_grad_ok: bool = False
+
+
+def _flat_slot(t):
+    """(FlatParams, index) when `t` is a Parameter re-homed by parallel.FlatParams with direct accumulation on."""
+    slot = getattr(t, '_pp_flat_slot', None)
+    if slot is None:
+        return None
+    flat = slot[0]()
+    if flat is None or not flat.direct or flat.params[slot[1]] is not t:
+        return None
+    # only while .grad IS the flat view (an external zero_grad(set_to_none=True) or a foreign optimizer takes the
+    # parameter back to the ordinary autograd path)
+    if t.grad is None or t.grad.data_ptr() != flat.grad_view(slot[1]).data_ptr():
+        return None
+    return flat, slot[1]
 
 
 class _ConvBlockFn(torch.autograd.Function):
@@ -324,6 +343,15 @@ class _ConvBlockFn(torch.autograd.Function):
             C.c_size_t(nbytes), _stream()), "pp_conv_block_fwd")
         if need_grad:
             ctx.save_for_backward(xc, z, g, b, save_mean, save_invstd)
+            # gradients that can be accumulated by the kernels themselves into a flat gradient buffer
+            ctx.slots = [None, None, None]
+            if o.direct_grad_ok:
+                for k, t in enumerate((weight, gamma, beta)):
+                    if t is not None and ctx.needs_input_grad[1 + k] and t.dtype == torch.float32:
+                        slot = _flat_slot(t)
+                        if slot is not None and (k == 0 or t.numel() == spec.O):
+                            ctx.slots[k] = slot
+                            slot[0].direct_begin(slot[1])
             ctx.prepared = prepared
             ctx.o = o
             ctx.x_dtype = x.dtype
@@ -344,12 +372,17 @@ class _ConvBlockFn(torch.autograd.Function):
         dev = gy.device
         gyc = to_nhwc_bf16(gy)
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups)
+        sw, sg, sb = ctx.slots
+        flags = (L.PP_FLAG_ACC_DW if sw else 0) | (L.PP_FLAG_ACC_DGAMMA if sg else 0) | (L.PP_FLAG_ACC_DBETA if sb else 0)
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, flags)
         dx = torch.empty((N, Cx, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last) \
             if need_dx else None
-        dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dev) if need_dw else None
-        dgamma = torch.empty(spec.O, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        if sw:
+            dw = sw[0].grad_view(sw[1])
+        else:
+            dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dev) if need_dw else None
+        dgamma = sg[0].grad_view(sg[1]).view(-1) if sg else torch.empty(spec.O, dtype=torch.float32, device=dev)
+        dbeta = sb[0].grad_view(sb[1]).view(-1) if sb else torch.empty(spec.O, dtype=torch.float32, device=dev)
         if need_dx and ctx.prepared.wd is None:
             raise RuntimeError("deepipr_b200: dgrad weights were not prepared")
         ws, nbytes = workspace(d, key, L.PP_WS_BWD, dev)
@@ -361,7 +394,11 @@ class _ConvBlockFn(torch.autograd.Function):
             dx = dx.to(ctx.x_dtype)
         gg = dgamma.reshape(ctx.gshape).to(ctx.gdtype) if (ctx.gshape is not None and ctx.needs_input_grad[2]) else None
         gb = dbeta.reshape(ctx.bshape).to(ctx.bdtype) if (ctx.bshape is not None and ctx.needs_input_grad[3]) else None
-        return dx, dw, gg, gb, None, None
+        # directly accumulated gradients are already in the flat buffer: autograd gets None for them
+        for slot in (sw, sg, sb):
+            if slot:
+                slot[0].direct_done(slot[1])
+        return dx, (None if sw else dw), (None if sg else gg), (None if sb else gb), None, None
 
 
 def conv_block(x, weight, gamma, beta, prepared: PreparedWeight, opts: BlockOpts):

@@ -197,6 +197,7 @@ class ConvBlock(nn.Module, _FusedConvMixin):
             # BatchNorm2d / GroupNorm carry an affine; InstanceNorm2d(o) does not (weight, bias are None)
             gamma, beta = self.bn.weight, self.bn.bias
         o = self._bn_opts(norm, self.relu is not None, self.z_f32, x)
+        o.direct_grad_ok = True      # conv.weight / bn.weight / bn.bias (or conv.bias) feed this operator only
         return F_.conv_block(x, self.conv.weight, gamma, beta, prepared, o)
 
 

@@ -15,6 +15,7 @@ per-rank (what DataParallel does too).
                   (momentum, weight decay: experiments/classification.py:47-50)
 """
 import ctypes as C
+import weakref
 
 import torch
 import torch.distributed as dist
@@ -46,13 +47,30 @@ class FlatParams:
         self.numel = off
         self.flat = torch.zeros(off, dtype=dt, device=dev)
         self.flat_grad = torch.zeros(off, dtype=dt, device=dev)
+        #: Direct accumulation: the fused conv operator adds the weight / BN-affine gradients of ConvBlocks into
+        #: flat_grad from inside its own kernels (PP_FLAG_ACC_*) instead of handing them to autograd, which would
+        #: spend one `grad += g` launch per parameter and pass (~120 tiny launches per V2 step).  Set False to get
+        #: the plain autograd path back (identical results; tests compare the two).
+        self.direct = True
+        self._direct_pending = [0] * len(self.params)   # forward uses of parameter i whose backward has not run yet
+        self.on_ready = None                             # GradBuckets: called with i when parameter i's grad is final
         with torch.no_grad():
-            for p, o in zip(self.params, self.offsets):
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
                 view = self.flat[o:o + p.numel()].view_as(p)
                 view.copy_(p)
                 p.data = view
                 p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+                p._pp_flat_slot = (weakref.ref(self), i)
         F_.bump_weight_epoch()
+
+    # ---- direct accumulation bookkeeping (functional._ConvBlockFn)
+    def direct_begin(self, i):
+        self._direct_pending[i] += 1
+
+    def direct_done(self, i):
+        self._direct_pending[i] -= 1
+        if self._direct_pending[i] == 0 and self.on_ready is not None:
+            self.on_ready(i)
 
     def grad_view(self, i):
         p, o = self.params[i], self.offsets[i]
@@ -71,6 +89,9 @@ class FlatParams:
     def zero_grad(self):
         self.flat_grad.zero_()
         self.ensure_grad_views()
+        # forwards whose backward never ran (evaluation with grad enabled, an aborted step) must not leak into the
+        # next step's readiness count
+        self._direct_pending = [0] * len(self.params)
 
 
 class GradBuckets:
@@ -104,6 +125,9 @@ class GradBuckets:
         if overlap and self.world > 1:
             for i, p in enumerate(flat.params):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+            # parameters whose gradients are accumulated directly by the kernels never reach AccumulateGrad:
+            # FlatParams tells us when their last pending backward has run
+            flat.on_ready = self._param_ready
 
     def _close(self, start, end, members):
         idx = len(self.buckets)
@@ -111,18 +135,21 @@ class GradBuckets:
             self.bucket_of[i] = idx
         self.buckets.append((start, end, list(members)))
 
+    def _param_ready(self, i):
+        b = self.bucket_of[i]
+        self._pending[b] -= 1
+        # collectives must be issued in the same order on every rank: launch strictly in bucket order
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
+
     def _make_hook(self, i):
         def hook(p):
             view = self.flat.grad_view(i)
             if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
                 p.grad = view
-            b = self.bucket_of[i]
-            self._pending[b] -= 1
-            # collectives must be issued in the same order on every rank: launch strictly in bucket order
-            while self._next < len(self.buckets) and self._pending[self._next] == 0:
-                self._launch(self._next)
-                self._next += 1
+            self._param_ready(i)
         return hook
 
     def _launch(self, b):
@@ -149,6 +176,8 @@ class GradBuckets:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        if self.flat.on_ready == self._param_ready:
+            self.flat.on_ready = None
 
 
 def broadcast_state(module, src=0, group=None):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 8
+#define PP_ABI_VERSION 9
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -47,6 +47,11 @@ typedef enum PPStatus {
  * Same arithmetic in train and eval mode (no running statistics). */
 enum { PP_NORM_NONE = 0, PP_NORM_BN_TRAIN = 1, PP_NORM_BN_EVAL = 2, PP_NORM_GN = 3 };
 enum { PP_ALGO_AUTO = 0, PP_ALGO_TCGEN05 = 1, PP_ALGO_SIMT = 2 };
+/* PPConvDesc.flags, read by pp_conv_block_bwd: ADD the gradient into the caller's buffer instead of overwriting it
+ * (what autograd's AccumulateGrad does with `param.grad += g`, one launch per parameter and pass; here it is the
+ * last store of the producing kernel, so the gradients of a two-pass V2 step land in a flat gradient buffer with
+ * no extra launches). */
+enum { PP_FLAG_ACC_DW = 1, PP_FLAG_ACC_DGAMMA = 2, PP_FLAG_ACC_DBETA = 4 };
 enum { PP_WS_FWD = 0, PP_WS_BWD = 1 };
 
 /* Geometry + mode of one conv block.  Mirrors the constructor arguments of the
@@ -65,6 +70,7 @@ typedef struct PPConvDesc {
   float momentum;     /* BatchNorm momentum (0.1)                                */
   int32_t algo;       /* PP_ALGO_*; AUTO picks tcgen05 when C%64==0 && O%64==0   */
   int32_t groups;     /* PP_NORM_GN only: number of groups (O for InstanceNorm); else 0  */
+  int32_t flags;      /* PP_FLAG_* (backward only); 0 = overwrite dw / dgamma / dbeta    */
 } PPConvDesc;
 
 int pp_version(void);
@@ -158,7 +164,8 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
 
 /* Backward of pp_conv_block_fwd (autograd of the same reference lines).
  *   dy bf16 [N,P,Q,O];  dx bf16 [N,H,W,C] or NULL;  dw_oihw fp32 [O,C,kh,kw] or NULL
- *   dgamma / dbeta fp32 [O] (always written). */
+ *   dgamma / dbeta fp32 [O] (always written; added to when d->flags has PP_FLAG_ACC_DGAMMA / _DBETA,
+ *   as dw_oihw is with PP_FLAG_ACC_DW). */
 int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad,
                       const void* z, const float* gamma, const float* beta, const float* save_mean,
                       const float* save_invstd, void* dx, float* dw_oihw, float* dgamma,

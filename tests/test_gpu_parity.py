@@ -660,3 +660,42 @@ def test_direct_stem_kernels_ragged_shapes(shape):
     m.eval(); oracle.eval()
     with torch.no_grad():
         assert rel_l2(m(x.cuda()).float().cpu(), bf16r(oracle(x))) < ACT_TOL
+
+
+def test_direct_gradient_accumulation_equals_autograd_path():
+    """ConvBlock gradients accumulated by the kernels straight into the flat buffer (PP_FLAG_ACC_*, FlatParams.direct)
+    == the same step with autograd's AccumulateGrad doing `grad += g` (two passes of a V2 step), parameter for
+    parameter; and a torch optimizer that detaches .grad from the flat views falls back to the autograd path."""
+    from deepipr_b200.parallel import FlatParams, FlatSGD
+    from deepipr_b200.trainer import StepRunner
+    import bench
+    x = bf16r(torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(2))).cuda()
+    t = torch.randint(0, 10, (8,), generator=torch.Generator().manual_seed(3)).cuda()
+    grads, states = [], []
+    for direct in (True, False):
+        model = bench.build_model(seed=0).cuda().train()
+        flat = FlatParams(model.parameters())
+        flat.direct = direct
+        opt = FlatSGD(flat, lr=0.01, momentum=0.9, weight_decay=1e-4)
+        runner = StepRunner(model, opt, private=True, autocast=True)
+        L.load().pp_launch_count(1)
+        runner.forward_backward(x, t)
+        assert all(v == 0 for v in flat._direct_pending)
+        grads.append(flat.flat_grad.clone())
+        opt.step()
+        runner.forward_backward(x, t)          # second step: zero_grad + accumulation into a used buffer
+        grads.append(flat.flat_grad.clone())
+        states.append({k: v.clone() for k, v in model.state_dict().items()})
+    assert rel_l2(grads[0], grads[2]) < 1e-6 and rel_l2(grads[1], grads[3]) < 1e-6
+    assert grads[0].abs().sum() > 0
+    for k in states[0]:
+        if states[0][k].dtype.is_floating_point:
+            assert rel_l2(states[0][k], states[1][k]) < 1e-6, k
+    # foreign optimizer: zero_grad(set_to_none=True) detaches .grad from the flat views
+    model = bench.build_model(seed=0).cuda().train()
+    flat = FlatParams(model.parameters())
+    opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    StepRunner(model, opt, private=True, autocast=True).forward_backward(x, t)
+    got = torch.cat([p.grad.reshape(-1) for p in flat.params])
+    want = torch.cat([grads[0][o:o + p.numel()] for p, o in zip(flat.params, flat.offsets)])
+    assert rel_l2(got, want) < 1e-6

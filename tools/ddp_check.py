@@ -1,0 +1,69 @@
+"""Multi-GPU sanity of the gradient exchange (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/ddp_check.py
+
+Every rank runs the same V2 step twice on identical replicas and its own shard of a fixed batch: once with the kernels
+accumulating ConvBlock gradients straight into the flat buffer (bucket readiness signalled by FlatParams.direct_done)
+and once through autograd's AccumulateGrad hooks.  The all-reduced flat gradients must agree, be identical on all ranks,
+and equal the mean of the per-rank gradients computed without any exchange."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+import bench
+from deepipr_b200.parallel import FlatParams, FlatSGD, GradBuckets, broadcast_state
+from deepipr_b200.trainer import StepRunner
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(16 * world, 3, 32, 32, generator=g).to(torch.bfloat16).float()
+    T = torch.randint(0, 10, (16 * world,), generator=g)
+    x, t = X[rank::world].to(dev), T[rank::world].to(dev)
+    out = {}
+    for tag, direct, use_buckets in (("direct", True, True), ("autograd", False, True), ("local", True, False)):
+        model = bench.build_model(seed=0).to(dev).train()
+        broadcast_state(model)
+        flat = FlatParams(model.parameters())
+        flat.direct = direct
+        opt = FlatSGD(flat, lr=0.01, momentum=0.9, weight_decay=1e-4)
+        buckets = GradBuckets(flat, bucket_bytes=4 << 20) if use_buckets else None
+        StepRunner(model, opt, private=True, buckets=buckets, autocast=True).forward_backward(x, t)
+        torch.cuda.synchronize()
+        out[tag] = flat.flat_grad.clone()
+        if buckets is not None:
+            buckets.remove_hooks()
+    mean_local = out["local"].clone()
+    dist.all_reduce(mean_local)
+    mean_local /= world
+
+    def rel(a, b):
+        return ((a - b).double().norm() / b.double().norm()).item()
+
+    e1, e2, e3 = rel(out["direct"], out["autograd"]), rel(out["direct"], mean_local), rel(out["autograd"], mean_local)
+    same = out["direct"].clone()
+    dist.broadcast(same, 0)
+    e4 = rel(out["direct"], same)
+    ok = e1 < 1e-6 and e2 < 1e-5 and e3 < 1e-5 and e4 == 0.0
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"ddp_check world={world}: direct vs autograd {e1:.2e}, direct vs mean(local) {e2:.2e}, "
+              f"autograd vs mean(local) {e3:.2e}, rank0 vs rank{rank} {e4:.1e} -> {'OK' if flag.item() == 1.0 else 'FAIL'}")
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
