@@ -853,20 +853,91 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ partial, int spl
   }
 }
 
+// Tiled variant (C % 64 == 0): a block owns one output channel and CC consecutive input channels over ALL T taps, so
+// its outputs are the CC*T contiguous floats dw[o][c0 .. c0+CC)[T].  Thread (item, g): item = (tap t, 4 channels),
+// one 128-bit load per split for the splits s = g, g + G, ...; groups are combined in group order, the (t, c) tile is
+// transposed through shared memory and written — or added to what is there (accumulate) — with coalesced accesses.
+constexpr int kFinMaxOut = 49 * 128;   // T <= 49 taps, CC <= 128 channels
+__global__ void wgrad_finalize_tiled_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dw, int O,
+                                            int C, int T, int kstride, int CC, int accumulate) {
+  __shared__ float4 s_g[1024];
+  __shared__ float s_out[kFinMaxOut + 64];
+  const int items = blockDim.x, G = blockDim.y, g = threadIdx.y;
+  const int per_t = CC >> 2;                 // float4 items per tap
+  const int o = blockIdx.y;
+  const int c0 = blockIdx.x * CC;
+  const int t = threadIdx.x / per_t;
+  const int c4 = (threadIdx.x - t * per_t) << 2;
+  const size_t split_stride = (size_t)O * kstride;
+  const float* src = partial + (size_t)o * kstride + (size_t)t * C + c0 + c4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int sidx = g;
+  for (; sidx + 3 * G < splits; sidx += 4 * G) {
+    const float4 a0 = *reinterpret_cast<const float4*>(src + (size_t)sidx * split_stride);
+    const float4 a1 = *reinterpret_cast<const float4*>(src + (size_t)(sidx + G) * split_stride);
+    const float4 a2 = *reinterpret_cast<const float4*>(src + (size_t)(sidx + 2 * G) * split_stride);
+    const float4 a3 = *reinterpret_cast<const float4*>(src + (size_t)(sidx + 3 * G) * split_stride);
+    acc.x = (((acc.x + a0.x) + a1.x) + a2.x) + a3.x;
+    acc.y = (((acc.y + a0.y) + a1.y) + a2.y) + a3.y;
+    acc.z = (((acc.z + a0.z) + a1.z) + a2.z) + a3.z;
+    acc.w = (((acc.w + a0.w) + a1.w) + a2.w) + a3.w;
+  }
+  for (; sidx < splits; sidx += G) {
+    const float4 a0 = *reinterpret_cast<const float4*>(src + (size_t)sidx * split_stride);
+    acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+  }
+  if (G > 1) {
+    s_g[g * items + threadIdx.x] = acc;
+    __syncthreads();
+    if (g == 0) {
+      for (int gg = 1; gg < G; ++gg) {
+        const float4 v = s_g[gg * items + threadIdx.x];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+  }
+  if (g == 0) {   // s_out[c][t]: the order of dw[o][c0 + c][t]
+    s_out[(c4 + 0) * T + t] = acc.x;
+    s_out[(c4 + 1) * T + t] = acc.y;
+    s_out[(c4 + 2) * T + t] = acc.z;
+    s_out[(c4 + 3) * T + t] = acc.w;
+  }
+  __syncthreads();
+  float* dst = dw + ((size_t)o * C + c0) * T;
+  const int nout = CC * T;
+  for (int j = threadIdx.y * items + threadIdx.x; j < nout; j += items * G)
+    dst[j] = accumulate ? dst[j] + s_out[j] : s_out[j];
+}
+
 int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, int kstride, float* dw_oihw,
                           cudaStream_t s, int accumulate) {
   const int T = d.kh * d.kw;
   const int K = T * d.C;
-  const bool vec4 = (K % 4 == 0) && (kstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(partial) & 15) == 0);
-  const int G = splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1));
-  const int ipb = 256 / G;
+  const bool aligned = (kstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(partial) & 15) == 0);
+  int Gw = splits >= 32 ? 8 : (splits >= 16 ? 4 : (splits >= 8 ? 2 : 1));
+  if (aligned && d.C % 64 == 0 && T <= 49 && d.O <= 65535) {
+    int CC = (d.C % 128 == 0) ? 128 : 64;
+    if (T == 1 && d.C % 256 == 0) CC = 256;      // 1x1 filters: keep a block at >= 64 items
+    while (CC > 64 && (CC / 4) * T > 1024) CC >>= 1;
+    const int items = (CC / 4) * T;
+    if (items <= 1024 && CC * T <= kFinMaxOut) {
+      while (Gw > 1 && items * Gw > 1024) Gw >>= 1;
+      wgrad_finalize_tiled_kernel<<<dim3(d.C / CC, d.O), dim3(items, Gw), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T,
+                                                                                  kstride, CC, accumulate);
+      PP_POST_LAUNCH();
+      return PP_OK;
+    }
+  }
+  const bool vec4 = aligned && (K % 4 == 0);
+  const int ipb = 256 / Gw;
   const size_t total = (size_t)d.O * (vec4 ? K / 4 : K);
   const int grid = grid_for(total, ipb, 148 * 8);
   if (vec4)
-    wgrad_finalize_kernel<true><<<grid, dim3(ipb, G), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride, accumulate);
+    wgrad_finalize_kernel<true><<<grid, dim3(ipb, Gw), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride,
+                                                                accumulate);
   else
-    wgrad_finalize_kernel<false><<<grid, dim3(ipb, G), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride,
-                                                               accumulate);
+    wgrad_finalize_kernel<false><<<grid, dim3(ipb, Gw), 0, s>>>(partial, splits, dw_oihw, d.O, d.C, T, kstride,
+                                                                 accumulate);
   PP_POST_LAUNCH();
   return PP_OK;
 }
