@@ -53,6 +53,7 @@ class FlatParams:
         #: the plain autograd path back (identical results; tests compare the two).
         self.direct = True
         self._direct_pending = [0] * len(self.params)   # forward uses of parameter i whose backward has not run yet
+        self._direct_uses = [0] * len(self.params)      # direct uses of parameter i since the last zero_grad()
         self.on_ready = None                             # GradBuckets: called with i when parameter i's grad is final
         with torch.no_grad():
             for i, (p, o) in enumerate(zip(self.params, self.offsets)):
@@ -66,6 +67,13 @@ class FlatParams:
     # ---- direct accumulation bookkeeping (functional._ConvBlockFn)
     def direct_begin(self, i):
         self._direct_pending[i] += 1
+        self._direct_uses[i] += 1
+
+    def is_direct(self, i):
+        """True when parameter i's gradient is being produced by direct accumulation in the current step: its
+        readiness is reported by direct_done(), and the AccumulateGrad hook autograd still fires for it (with an
+        undefined gradient) must not be counted a second time."""
+        return self._direct_uses[i] > 0
 
     def direct_done(self, i):
         self._direct_pending[i] -= 1
@@ -92,6 +100,7 @@ class FlatParams:
         # forwards whose backward never ran (evaluation with grad enabled, an aborted step) must not leak into the
         # next step's readiness count
         self._direct_pending = [0] * len(self.params)
+        self._direct_uses = [0] * len(self.params)
 
 
 class GradBuckets:
@@ -145,6 +154,8 @@ class GradBuckets:
 
     def _make_hook(self, i):
         def hook(p):
+            if self.flat.is_direct(i):
+                return          # FlatParams.direct_done() reports this parameter (see FlatParams.is_direct)
             view = self.flat.grad_view(i)
             if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)

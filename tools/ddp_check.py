@@ -32,7 +32,9 @@ def main():
     T = torch.randint(0, 10, (16 * world,), generator=g)
     x, t = X[rank::world].to(dev), T[rank::world].to(dev)
     out = {}
-    for tag, direct, use_buckets in (("direct", True, True), ("autograd", False, True), ("local", True, False)):
+    names = None
+    for tag, direct, use_buckets in (("autograd", False, True), ("direct", True, True), ("local", True, False),
+                                     ("direct_again", True, True)):
         model = bench.build_model(seed=0).to(dev).train()
         broadcast_state(model)
         flat = FlatParams(model.parameters())
@@ -42,6 +44,9 @@ def main():
         StepRunner(model, opt, private=True, buckets=buckets, autocast=True).forward_backward(x, t)
         torch.cuda.synchronize()
         out[tag] = flat.flat_grad.clone()
+        if names is None:
+            ids = {id(p): n for n, p in model.named_parameters()}
+            names = [(ids[id(p)], o, p.numel()) for p, o in zip(flat.params, flat.offsets)]
         if buckets is not None:
             buckets.remove_hooks()
     mean_local = out["local"].clone()
@@ -55,12 +60,22 @@ def main():
     same = out["direct"].clone()
     dist.broadcast(same, 0)
     e4 = rel(out["direct"], same)
-    ok = e1 < 1e-6 and e2 < 1e-5 and e3 < 1e-5 and e4 == 0.0
+    e5 = rel(out["direct_again"], mean_local)
+    if rank == 0 and (e2 > 1e-5 or e5 > 1e-5):
+        bad = []
+        for n, o, k in names:
+            a, b = out["direct"][o:o + k], mean_local[o:o + k]
+            r = rel(a, b) if b.abs().sum() > 0 else 0.0
+            if r > 1e-5:
+                ratio = (a.double().norm() / b.double().norm()).item()
+                bad.append(f"{n}: rel {r:.3e} |direct|/|ref| {ratio:.4f}")
+        print(f"{len(bad)} of {len(names)} parameters differ; first 40:\n  " + "\n  ".join(bad[:40]))
+    ok = e1 < 1e-6 and e2 < 1e-5 and e3 < 1e-5 and e4 == 0.0 and e5 < 1e-5
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"ddp_check world={world}: direct vs autograd {e1:.2e}, direct vs mean(local) {e2:.2e}, "
-              f"autograd vs mean(local) {e3:.2e}, rank0 vs rank{rank} {e4:.1e} -> {'OK' if flag.item() == 1.0 else 'FAIL'}")
+              f"autograd vs mean(local) {e3:.2e}, rank0 vs rank{rank} {e4:.1e}, direct_again vs mean(local) {e5:.2e} -> {'OK' if flag.item() == 1.0 else 'FAIL'}")
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 
