@@ -97,3 +97,89 @@ def test_flat_params_keeps_values_and_views():
     assert flat.flat_grad.abs().sum() > 0              # gradients landed in the flat gradient buffer
     flat.zero_grad()
     assert flat.flat_grad.abs().sum() == 0 and all(p.grad is not None for p in flat.params)
+
+
+# ---- directly accumulated gradients (what functional._ConvBlockFn does on the GPU): the operator adds its weight
+# gradient into FlatParams.flat_grad itself, returns None to autograd and reports readiness through
+# FlatParams.direct_done().  Autograd still runs the parameter's AccumulateGrad node (with an undefined gradient) and
+# fires its post-accumulate hook; counting that hook as a second readiness signal launched buckets early.
+class _DirectLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, flat, i):
+        ctx.save_for_backward(x, w)
+        ctx.flat, ctx.i = flat, i
+        flat.direct_begin(i)
+        return x @ w.t()
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        ctx.flat.grad_view(ctx.i).add_(gy.t() @ x)
+        ctx.flat.direct_done(ctx.i)
+        return gy @ w, None, None, None
+
+
+def _two_pass_loss(ws, x, y, lin):
+    loss = 0
+    for scale in (1.0, 0.5):                       # two passes over the same weights, one backward (V2 step shape)
+        h = torch.relu(lin(0, x * scale, ws[0]))
+        h = torch.relu(lin(1, h, ws[1]))
+        h = torch.relu(lin(2, h, ws[2]))
+        loss = loss + torch.nn.functional.cross_entropy(torch.nn.functional.linear(h, ws[3]), y)
+    return loss
+
+
+def _weights():
+    g = torch.Generator().manual_seed(3)
+    return [torch.nn.Parameter(torch.randn(s, generator=g) * 0.3) for s in ((32, 12), (32, 32), (32, 32), (5, 32))]
+
+
+def _direct_worker(rank, world, port, bucket_bytes, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ws = _weights()
+        flat = FlatParams(ws)
+        buckets = GradBuckets(flat, bucket_bytes=bucket_bytes, overlap=True)
+        g = torch.Generator().manual_seed(7)
+        X, Y = torch.randn(8, 12, generator=g), torch.randint(0, 5, (8,), generator=g)
+        xs, ys = X[rank * 4:(rank + 1) * 4], Y[rank * 4:(rank + 1) * 4]
+        grads = []
+        for step in range(2):
+            flat.zero_grad()
+            _two_pass_loss(ws, xs, ys, lambda i, x, w: _DirectLinear.apply(x, w, flat, i)).backward()
+            buckets.finish()
+            grads.append(flat.flat_grad.clone())
+        out[rank] = dict(grads=grads, nbuckets=len(buckets.buckets), offsets=list(flat.offsets))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_direct(bucket_bytes, want_buckets):
+    port = _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_direct_worker, args=(2, port, bucket_bytes, out), nprocs=2, join=True)
+    ws = _weights()
+    g = torch.Generator().manual_seed(7)
+    X, Y = torch.randn(8, 12, generator=g), torch.randint(0, 5, (8,), generator=g)
+    # mean over the global batch == mean of the per-rank means (equal shard sizes)
+    loss = 0.5 * (_two_pass_loss(ws, X[:4], Y[:4], lambda i, x, w: torch.nn.functional.linear(x, w)) +
+                  _two_pass_loss(ws, X[4:], Y[4:], lambda i, x, w: torch.nn.functional.linear(x, w)))
+    loss.backward()
+    assert out[0]["nbuckets"] == want_buckets
+    for rank in (0, 1):
+        for step in range(2):
+            for w, o in zip(ws, out[rank]["offsets"]):
+                got = out[rank]["grads"][step][o:o + w.numel()].view_as(w)
+                assert torch.allclose(got, w.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_directly_accumulated_gradients_shared_bucket():
+    # all four parameters in ONE bucket: with the hook double-counted it was launched after two of the three
+    # direct parameters, before the first layer's gradient existed
+    _run_direct(bucket_bytes=1 << 16, want_buckets=1)
+
+
+def test_directly_accumulated_gradients_many_buckets():
+    _run_direct(bucket_bytes=6000, want_buckets=2)
