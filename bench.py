@@ -171,6 +171,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own logging (NCCL_DEBUG=VERSION/INFO on the box prints
+        # "NCCL version ..." there) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
 
