@@ -699,3 +699,52 @@ def test_direct_gradient_accumulation_equals_autograd_path():
     got = torch.cat([p.grad.reshape(-1) for p in flat.params])
     want = torch.cat([grads[0][o:o + p.numel()] for p, o in zip(flat.params, flat.offsets)])
     assert rel_l2(got, want) < 1e-6
+
+
+def test_trainer_private_epoch_with_trigger_set_matches_the_reference_loop():
+    """V3 (BASELINE config 4): TrainerPrivate.train over two minibatches with a trigger-set loader that is exhausted
+    and restarted (trainer_private.py:131-146), then TrainerPrivate.test — against the same loop restated with the
+    oracle (trainer_private.py:148-211, 73-105): dictionary keys, loss / sign-loss bookkeeping (mean vs sum), sign
+    accuracy and the signature entries."""
+    from deepipr_b200.trainer import TrainerPrivate
+    import bench
+    model = bench.build_model(seed=0)
+    oracle = po.mirror(model, round_bf16=True).train()
+    g = torch.Generator().manual_seed(5)
+    data = [(bf16r(torch.randn(6, 3, 32, 32, generator=g)), torch.randint(0, 10, (6,), generator=g)) for _ in range(2)]
+    wm = [(bf16r(torch.randn(2, 3, 32, 32, generator=g)), torch.randint(0, 10, (2,), generator=g))]
+    model = model.cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    trainer = TrainerPrivate(model, opt, None, torch.device("cuda"), autocast=False)
+    res = trainer.train(0, data, wm)
+    assert set(res) == {"loss", "sign_loss", "sign_acc", "acc_public", "acc_private", "time"}
+
+    opt_o = torch.optim.SGD(oracle.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    it, ref = iter(wm), []
+    for x, t in data:
+        try:
+            wx, wt = next(it)
+        except StopIteration:
+            it = iter(wm)
+            wx, wt = next(it)
+        ref.append(po.train_step(oracle, opt_o, torch.cat([x, wx]), torch.cat([t, wt]), private=True))
+    loss_ref = sum(r["loss"] for r in ref) / len(ref)             # mean over batches (:186)
+    sign_ref = sum(r["sign_loss"] for r in ref)                    # SUM over batches (:175, never divided)
+    assert abs(res["loss"] - loss_ref) < 3e-2 * abs(loss_ref)
+    assert abs(res["sign_loss"] - sign_ref) < 2e-3 * abs(sign_ref)
+    accs = [float(m.acc) for m in po.sign_loss_modules(oracle)]
+    assert len(accs) == 5 and abs(res["sign_acc"] - sum(accs) / len(accs)) < 0.02
+    for key in ("acc_public", "acc_private"):
+        assert 0.0 <= res[key] <= 100.0
+        assert abs(res[key] - sum(r[key] for r in ref) / len(ref)) <= 12.5 + 1e-6      # at most one of 8 images
+
+    out = trainer.test(data)
+    sig = po.test_signature(oracle.eval())
+    assert {"loss_public", "acc_public", "loss_private", "acc_private", "total_acc"} <= set(out)
+    assert {"s_" + k for k in sig} <= set(out) and len(sig) == 5
+    with torch.no_grad():
+        for ind, key in enumerate(("public", "private")):
+            lo = sum(torch.nn.functional.cross_entropy(oracle(x, ind=ind), t, reduction="sum").item() for x, t in data)
+            assert abs(out["loss_" + key] - lo / 12) < 3e-2 * abs(lo / 12), key
+    for k, v in sig.items():
+        assert abs(out["s_" + k] - v) < 0.02, k
