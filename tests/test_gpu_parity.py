@@ -748,3 +748,59 @@ def test_trainer_private_epoch_with_trigger_set_matches_the_reference_loop():
             assert abs(out["loss_" + key] - lo / 12) < 3e-2 * abs(lo / 12), key
     for k, v in sig.items():
         assert abs(out["s_" + k] - v) < 0.02, k
+
+
+def test_trainer_v1_epoch_and_eval_match_the_reference_loop():
+    """V1 (BASELINE config 2): Trainer.train / Trainer.test on AlexNet with passport layers 4/5/6
+    (trainer.py:111-214) against the oracle's restatement of the same loop: keys and bookkeeping (sign loss is the
+    MEAN over batches here, :150-152)."""
+    from deepipr_b200.trainer import Trainer
+    seed_all(0)
+    pk = nets.passport_kwargs_from_config(nets.alexnet_passport_config(), "bn", "random", 0.1)
+    model = quiet(nets.AlexNetCifar, "v1", 3, 10, pk)
+    with torch.no_grad():
+        for mod in model.modules():
+            if getattr(mod, "KIND", None) == "v1":
+                c = mod.conv.in_channels
+                mod.set_key(bf16r(torch.rand(1, c, 8, 8) * 2 - 1), bf16r(torch.rand(1, c, 8, 8) * 2 - 1))
+    oracle = po.mirror(model, round_bf16=True).train()
+    g = torch.Generator().manual_seed(9)
+    data = [(bf16r(torch.randn(8, 3, 32, 32, generator=g)), torch.randint(0, 10, (8,), generator=g)) for _ in range(2)]
+    model = model.cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    trainer = Trainer(model, opt, None, torch.device("cuda"), autocast=False)
+    res = trainer.train(0, data)
+    assert set(res) == {"loss", "sign_loss", "sign_acc", "acc", "time"}
+    opt_o = torch.optim.SGD(oracle.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    ref = [po.train_step(oracle, opt_o, x, t, private=False) for x, t in data]
+    assert abs(res["loss"] - sum(r["loss"] for r in ref) / 2) < 3e-2 * abs(sum(r["loss"] for r in ref) / 2)
+    assert abs(res["sign_loss"] - sum(r["sign_loss"] for r in ref) / 2) < 2e-3 * abs(sum(r["sign_loss"] for r in ref) / 2)
+    accs = [float(m.acc) for m in po.sign_loss_modules(oracle)]
+    assert len(accs) == 3 and abs(res["sign_acc"] - sum(accs) / 3) < 0.02
+    out = trainer.test(data)
+    assert set(out) == {"loss", "acc", "time"}
+    oracle.eval()
+    with torch.no_grad():
+        lo = sum(torch.nn.functional.cross_entropy(oracle(x), t, reduction="sum").item() for x, t in data) / 16
+    assert abs(out["loss"] - lo) < 3e-2 * abs(lo)
+
+
+def test_group_norm_conv_block_direct_gradient_accumulation():
+    """PP_FLAG_ACC_* through the GroupNorm kernels (gn_dparam_kernel) and a conv bias (norm 'none'): two uses of the
+    same blocks in one backward, gradients accumulated straight into FlatParams.flat_grad == autograd's sums."""
+    from deepipr_b200.parallel import FlatParams
+    x = bf16r(torch.randn(4, 64, 8, 8, generator=torch.Generator().manual_seed(4))).cuda()
+    got = []
+    for direct in (True, False):
+        seed_all(3)
+        net = torch.nn.Sequential(layers.ConvBlock(64, 64, 3, 1, 1, bn="gn"), layers.ConvBlock(64, 128, 3, 2, 1, bn="none"),
+                                  layers.ConvBlock(128, 64, 1, 1, 0, bn="in")).cuda()
+        flat = FlatParams(net.parameters())
+        flat.direct = direct
+        flat.zero_grad()
+        L.load().pp_launch_count(1)
+        (net(x).float().square().mean() + net(x * 0.5).float().abs().mean()).backward()
+        assert all(v == 0 for v in flat._direct_pending)
+        assert any(flat._direct_uses) == direct
+        got.append(flat.flat_grad.clone())
+    assert got[0].abs().sum() > 0 and rel_l2(got[0], got[1]) < 1e-6
