@@ -25,12 +25,49 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert getattr(lib, name) is not None
 
 
+def test_ctypes_mirror_matches_the_c_header(tmp_path):
+    """Compile a probe against include/passport_sm100.h with gcc and compare struct layouts and constants with the
+    ctypes mirror in deepipr_b200/_lib.py (what a cgo / JNI / ctypes binding of the ABI has to agree on)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    inc = os.path.join(os.path.dirname(L._HERE), "include")
+    fields_desc = [f[0] for f in L.PPConvDesc._fields_]
+    fields_sig = [f[0] for f in L.PPSigLayer._fields_]
+    consts = ["PP_ABI_VERSION", "PP_NORM_NONE", "PP_NORM_BN_TRAIN", "PP_NORM_BN_EVAL", "PP_NORM_GN", "PP_ALGO_AUTO",
+              "PP_ALGO_TCGEN05", "PP_ALGO_SIMT", "PP_WS_FWD", "PP_WS_BWD", "PP_FLAG_ACC_DW", "PP_FLAG_ACC_DGAMMA",
+              "PP_FLAG_ACC_DBETA", "PP_SIG_MAX_LAYERS"]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "passport_sm100.h"', 'int main(void) {',
+           'printf("sizeof PPConvDesc %zu\\n", sizeof(PPConvDesc));',
+           'printf("sizeof PPSigLayer %zu\\n", sizeof(PPSigLayer));']
+    src += [f'printf("PPConvDesc.{f} %zu\\n", offsetof(PPConvDesc, {f}));' for f in fields_desc]
+    src += [f'printf("PPSigLayer.{f} %zu\\n", offsetof(PPSigLayer, {f}));' for f in fields_sig]
+    src += [f'printf("{c} %d\\n", (int){c});' for c in consts]
+    src += ['printf("PP_ENODEVICE %d\\n", (int)PP_ENODEVICE);', 'return 0; }']
+    cfile = tmp_path / "probe.c"
+    cfile.write_text("\n".join(src))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(cfile), "-o", str(exe)], check=True)
+    got = dict(line.rsplit(" ", 1) for line in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                              check=True).stdout.splitlines())
+    assert int(got["sizeof PPConvDesc"]) == C.sizeof(L.PPConvDesc)
+    assert int(got["sizeof PPSigLayer"]) == C.sizeof(L.PPSigLayer)
+    for f in fields_desc:
+        assert int(got[f"PPConvDesc.{f}"]) == getattr(L.PPConvDesc, f).offset, f
+    for f in fields_sig:
+        assert int(got[f"PPSigLayer.{f}"]) == getattr(L.PPSigLayer, f).offset, f
+    for c in consts:
+        assert int(got[c]) == getattr(L, c), c
+    assert int(got["PP_ENODEVICE"]) == -5
+
+
 def test_library_fails_loudly_without_device():
     if torch.cuda.is_available():
         pytest.skip("device present")
     lib = L.load()
     d = L.PPConvDesc(N=2, C=64, H=8, W=8, O=64, kh=3, kw=3, stride=1, pad=1, norm=0, relu=1, z_f32=0, eps=1e-5,
-                     momentum=0.1, algo=0, reserved=0)
+                     momentum=0.1, algo=0, groups=0, flags=0)
     rc = lib.pp_conv_fwd_raw(C.byref(d), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), None, 0, None)
     assert rc == -5 and "no CUDA device" in L.last_error()
     out = C.c_size_t(0)
