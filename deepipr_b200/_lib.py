@@ -10,7 +10,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpassport_sm100.so")
 
-PP_ABI_VERSION = 9
+PP_ABI_VERSION = 10
 PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL, PP_NORM_GN = 0, 1, 2, 3
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1
@@ -42,8 +42,8 @@ PP_SIG_MAX_LAYERS = 64
 
 class PPSigLayer(C.Structure):
     _fields_ = [
-        ("w_fprop", C.c_void_p), ("S_skey", C.c_void_p), ("b_sign", C.c_void_p),
-        ("O", C.c_int32), ("K", C.c_int32), ("gamma_offset", C.c_int32), ("reserved", C.c_int32),
+        ("w_oihw", C.c_void_p), ("S_skey", C.c_void_p), ("b_sign", C.c_void_p),
+        ("O", C.c_int32), ("K", C.c_int32), ("gamma_offset", C.c_int32), ("C", C.c_int32),
     ]
 
 

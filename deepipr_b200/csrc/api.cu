@@ -391,14 +391,14 @@ int pp_key_pool(const PPConvDesc* d, int Bk, const float* key_nchw, double* S, v
   return launch_key_pool(*d, Bk, key_nchw, S, (cudaStream_t)stream);
 }
 
-int pp_passport_affine_fwd(const PPConvDesc* d, const void* w_fprop, const double* S_skey, const double* S_key,
+int pp_passport_affine_fwd(const PPConvDesc* d, const float* w_oihw, const double* S_skey, const double* S_key,
                            const float* b_sign, float alpha, float* gamma, float* beta, float* sign_loss,
                            float* sign_acc, void* stream) {
   Geo geo;
   PP_TRY(geo_of(d, &geo));
   PP_TRY(check_device());
-  PP_REQUIRE(w_fprop && S_skey && S_key && gamma && beta, PP_EBADARG, "passport affine: NULL pointer");
-  return launch_passport_affine_fwd(*d, (const __nv_bfloat16*)w_fprop, S_skey, S_key, b_sign, alpha, gamma, beta,
+  PP_REQUIRE(w_oihw && S_skey && S_key && gamma && beta, PP_EBADARG, "passport affine: NULL pointer");
+  return launch_passport_affine_fwd(*d, w_oihw, S_skey, S_key, b_sign, alpha, gamma, beta,
                                     sign_loss, sign_acc, (cudaStream_t)stream);
 }
 
@@ -414,16 +414,16 @@ int pp_passport_affine_bwd(const PPConvDesc* d, const double* S_skey, const doub
                                     accumulate, (cudaStream_t)stream);
 }
 
-int pp_passport_key_grad(const PPConvDesc* d, int Bk, const void* w_fprop, const float* gamma, const float* b_sign,
+int pp_passport_key_grad(const PPConvDesc* d, int Bk, const float* w_oihw, const float* gamma, const float* b_sign,
                          float alpha, const float* g_gamma, const float* g_beta, const float* g_loss,
                          double* scratch, float* dskey_nchw, float* dkey_nchw, void* stream) {
   Geo geo;
   PP_TRY(geo_of(d, &geo));
   PP_TRY(check_device());
-  PP_REQUIRE(w_fprop && scratch && Bk > 0, PP_EBADARG, "passport key grad: NULL pointer");
+  PP_REQUIRE(w_oihw && scratch && Bk > 0, PP_EBADARG, "passport key grad: NULL pointer");
   PP_REQUIRE(!(g_loss && b_sign) || gamma, PP_EBADARG, "passport key grad: gamma needed for the sign-loss term");
   const int K = geo.T * d->C;
-  return launch_passport_key_grad(*d, Bk, (const __nv_bfloat16*)w_fprop, gamma, b_sign, alpha, g_gamma, g_beta, g_loss,
+  return launch_passport_key_grad(*d, Bk, w_oihw, gamma, b_sign, alpha, g_gamma, g_beta, g_loss,
                                   scratch, scratch + K, dskey_nchw, dkey_nchw, (cudaStream_t)stream);
 }
 
@@ -434,10 +434,12 @@ int pp_signature_verify(int nlayers, const PPSigLayer* layers, int32_t* matched,
   if (nlayers == 0) return PP_OK;
   PP_REQUIRE(layers && matched, PP_EBADARG, "signature verify: NULL pointer");
   for (int i = 0; i < nlayers; ++i) {
-    PP_REQUIRE(layers[i].w_fprop && layers[i].S_skey && layers[i].b_sign, PP_EBADARG,
+    PP_REQUIRE(layers[i].w_oihw && layers[i].S_skey && layers[i].b_sign, PP_EBADARG,
                "signature verify: layer %d has a NULL pointer", i);
-    PP_REQUIRE(layers[i].O > 0 && layers[i].K > 0 && layers[i].gamma_offset >= 0, PP_EBADSHAPE,
-               "signature verify: layer %d has O=%d K=%d", i, layers[i].O, layers[i].K);
+    PP_REQUIRE(layers[i].O > 0 && layers[i].K > 0 && layers[i].gamma_offset >= 0 && layers[i].C > 0 &&
+                   layers[i].K % layers[i].C == 0,
+               PP_EBADSHAPE, "signature verify: layer %d has O=%d K=%d C=%d", i, layers[i].O, layers[i].K,
+               layers[i].C);
   }
   return launch_signature_verify(nlayers, layers, matched, gamma_out, (cudaStream_t)stream);
 }

@@ -115,13 +115,13 @@ int stem_wgrad(const PPConvDesc& d, const void* x, const void* dz, float* partia
 // --- pointwise.cu ---
 int launch_weight_prep(const PPConvDesc& d, const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s);
 int launch_key_pool(const PPConvDesc& d, int Bk, const float* key, double* S, cudaStream_t s);
-int launch_passport_affine_fwd(const PPConvDesc& d, const __nv_bfloat16* wf, const double* Ss, const double* Sk,
+int launch_passport_affine_fwd(const PPConvDesc& d, const float* w_oihw, const double* Ss, const double* Sk,
                                const float* b, float alpha, float* gamma, float* beta, float* loss, float* acc,
                                cudaStream_t s);
 int launch_passport_affine_bwd(const PPConvDesc& d, const double* Ss, const double* Sk, const float* gamma,
                                const float* b, float alpha, const float* gg, const float* gb, const float* gl,
                                float* dw, int accumulate, cudaStream_t s);
-int launch_passport_key_grad(const PPConvDesc& d, int Bk, const __nv_bfloat16* wf, const float* gamma, const float* b,
+int launch_passport_key_grad(const PPConvDesc& d, int Bk, const float* w_oihw, const float* gamma, const float* b,
                              float alpha, const float* gg, const float* gb, const float* gl, double* dSs, double* dSk,
                              float* dskey, float* dkey, cudaStream_t s);
 int launch_signature_verify(int nlayers, const PPSigLayer* layers, int* matched, float* gamma_out, cudaStream_t s);

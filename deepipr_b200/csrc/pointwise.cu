@@ -84,7 +84,7 @@ __global__ void key_pool_kernel(const float* __restrict__ key, double* __restric
       for (int q = 0; q < Q; ++q) {
         const int w = q * stride - pad + sx;
         if (w < 0 || w >= W) continue;
-        acc += (double)bf16_round(kp[h * W + w]);
+        acc += (double)kp[h * W + w];
       }
     }
   }
@@ -102,25 +102,38 @@ int launch_key_pool(const PPConvDesc& d, int Bk, const float* key, double* S, cu
 
 // ---------------------------------------------------------------------------------------------
 // gamma/beta GEMV (one warp per output channel, fp64 accumulate, fixed-order shuffle tree)
+// Reads the fp32 OIHW MASTER weight (the nn.Parameter itself) and the un-rounded pooled keys: sign(gamma) is the
+// signature, and must be the one the reference's fp32 get_scale() yields on the same inputs — the bf16 operand copy
+// the tensor-core convs use is too coarse for that (rounding W and the key flips ~0.1 % of the bits at init).
 // ---------------------------------------------------------------------------------------------
-__global__ void passport_gemv_kernel(const __nv_bfloat16* __restrict__ wf, const double* __restrict__ Ss,
-                                     const double* __restrict__ Sk, float* __restrict__ gamma,
-                                     float* __restrict__ beta, int O, int K) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= O) return;
-  const __nv_bfloat16* row = wf + (size_t)warp * K;
-  double g = 0.0, b = 0.0;
-  for (int k = lane; k < K; k += 32) {
-    const double w = (double)__bfloat162float(row[k]);
+// lane-strided dot products of OIHW row `row` (i = c*T + t) with pooled patches indexed [t*C + c]
+__device__ __forceinline__ void passport_row_dot(const float* __restrict__ row, const double* __restrict__ Ss,
+                                                 const double* __restrict__ Sk, int C, int T, int lane, double& g,
+                                                 double& b) {
+  const int K = C * T;
+  g = 0.0; b = 0.0;
+  for (int i = lane; i < K; i += 32) {
+    const int c = i / T;
+    const int k = (i - c * T) * C + c;
+    const double w = (double)row[i];
     g = fma(w, Ss[k], g);
-    b = fma(w, Sk[k], b);
+    if (Sk) b = fma(w, Sk[k], b);
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     g += __shfl_xor_sync(0xffffffffu, g, off);
     b += __shfl_xor_sync(0xffffffffu, b, off);
   }
+}
+
+__global__ void passport_gemv_kernel(const float* __restrict__ w, const double* __restrict__ Ss,
+                                     const double* __restrict__ Sk, float* __restrict__ gamma,
+                                     float* __restrict__ beta, int O, int C, int T) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= O) return;
+  double g, b;
+  passport_row_dot(w + (size_t)warp * C * T, Ss, Sk, C, T, lane, g, b);
   if (lane == 0) {
     gamma[warp] = (float)g;
     beta[warp] = (float)b;
@@ -141,12 +154,8 @@ __global__ void signature_verify_kernel(const __grid_constant__ SigBatch batch, 
   const int lane = threadIdx.x & 31;
   if (warp >= ly.O) return;
   const int K = ly.K;
-  const __nv_bfloat16* row = reinterpret_cast<const __nv_bfloat16*>(ly.w_fprop) + (size_t)warp * K;
-  const double* Ss = ly.S_skey;
-  double g = 0.0;
-  for (int k = lane; k < K; k += 32) g = fma((double)__bfloat162float(row[k]), Ss[k], g);
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
+  double g, unused;
+  passport_row_dot(ly.w_oihw + (size_t)warp * K, ly.S_skey, nullptr, ly.C, K / ly.C, lane, g, unused);
   if (lane == 0) {
     const float gf = (float)g;
     const float sg = (float)((gf > 0.f) - (gf < 0.f));
@@ -229,13 +238,12 @@ int launch_sign_loss_bwd(int O, const float* gamma, const float* b, float alpha,
   return PP_OK;
 }
 
-int launch_passport_affine_fwd(const PPConvDesc& d, const __nv_bfloat16* wf, const double* Ss, const double* Sk,
+int launch_passport_affine_fwd(const PPConvDesc& d, const float* w, const double* Ss, const double* Sk,
                                const float* b, float alpha, float* gamma, float* beta, float* loss, float* acc,
                                cudaStream_t s) {
-  const int K = d.kh * d.kw * d.C;
   const int warps_per_block = 8;
   passport_gemv_kernel<<<(d.O + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
-      wf, Ss, Sk, gamma, beta, d.O, K);
+      w, Ss, Sk, gamma, beta, d.O, d.C, d.kh * d.kw);
   PP_POST_LAUNCH();
   if (b && (loss || acc)) PP_TRY(launch_sign_loss_fwd(d.O, gamma, b, alpha, loss, acc, s));
   return PP_OK;
@@ -302,21 +310,24 @@ __device__ __forceinline__ bool reduce_partials_32x32(const float* __restrict__ 
 //   dS_s[k] = sum_o cg[o] * W[o,k],  dS_k[k] = sum_o cb[o] * W[o,k]     (cg includes the sign-loss term)
 //   dkey[b,c,h,w] = 1/(Bk*P*Q) * sum over taps (r,s) that read pixel (h,w) of dS[(r,s), c]
 // ---------------------------------------------------------------------------------------------
-__global__ void passport_key_grad_gemv_kernel(const __nv_bfloat16* __restrict__ wf, const float* __restrict__ gamma,
+__global__ void passport_key_grad_gemv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                               const float* __restrict__ b, float alpha,
                                               const float* __restrict__ gg, const float* __restrict__ gb,
                                               const float* __restrict__ gl, double* __restrict__ dSs,
-                                              double* __restrict__ dSk, int O, int K) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+                                              double* __restrict__ dSk, int O, int C, int T) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;   // k = t*C + c (pooled-patch order)
+  const int K = C * T;
   if (k >= K) return;
+  const int t = k / C;
+  const int i = (k - t * C) * T + t;                      // the same element in the OIHW row
   double as = 0.0, ak = 0.0;
   for (int o = 0; o < O; ++o) {
     float cg = gg ? gg[o] : 0.0f;
     if (gl && b) cg += (*gl) * sign_loss_grad(gamma[o], b[o], alpha);
     const float cb = gb ? gb[o] : 0.0f;
-    const double w = (double)__bfloat162float(wf[(size_t)o * K + k]);
-    as = fma((double)cg, w, as);
-    ak = fma((double)cb, w, ak);
+    const double wv = (double)w[(size_t)o * K + i];
+    as = fma((double)cg, wv, as);
+    ak = fma((double)cb, wv, ak);
   }
   dSs[k] = as;
   dSk[k] = ak;
@@ -343,13 +354,14 @@ __global__ void key_unpool_kernel(const double* __restrict__ dS, float* __restri
   dkey[idx] = (float)(acc / ((double)Bk * P * Q));
 }
 
-int launch_passport_key_grad(const PPConvDesc& d, int Bk, const __nv_bfloat16* wf, const float* gamma, const float* b,
+int launch_passport_key_grad(const PPConvDesc& d, int Bk, const float* w, const float* gamma, const float* b,
                              float alpha, const float* gg, const float* gb, const float* gl, double* dSs, double* dSk,
                              float* dskey, float* dkey, cudaStream_t s) {
   const int K = d.kh * d.kw * d.C;
   const int P = (d.H + 2 * d.pad - d.kh) / d.stride + 1;
   const int Q = (d.W + 2 * d.pad - d.kw) / d.stride + 1;
-  passport_key_grad_gemv_kernel<<<(K + 127) / 128, 128, 0, s>>>(wf, gamma, b, alpha, gg, gb, gl, dSs, dSk, d.O, K);
+  passport_key_grad_gemv_kernel<<<(K + 127) / 128, 128, 0, s>>>(w, gamma, b, alpha, gg, gb, gl, dSs, dSk, d.O, d.C,
+                                                                d.kh * d.kw);
   PP_POST_LAUNCH();
   const int total = Bk * d.C * d.H * d.W;
   if (dskey) {

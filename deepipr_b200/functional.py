@@ -119,6 +119,14 @@ def prepare_weight(weight: torch.Tensor, spec: ConvSpec, need_dgrad: bool) -> Pr
     return PreparedWeight(wf, wd, weight._version, weight.data_ptr(), _weight_epoch)
 
 
+def master_weight(weight: torch.Tensor) -> torch.Tensor:
+    """The fp32 OIHW master weight as a dense tensor (no copy for an ordinary nn.Conv2d parameter)."""
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    return w
+
+
 def key_pool(key: torch.Tensor, spec: ConvSpec) -> torch.Tensor:
     """Pooled passport patch S (fp64 [kh*kw*C]) such that GAP(conv(W, key)) == W.view(O, -1) @ S."""
     require_cuda(key, "passport key")
@@ -137,7 +145,6 @@ def key_pool(key: torch.Tensor, spec: ConvSpec) -> torch.Tensor:
 @dataclass
 class AffineCtx:
     spec: ConvSpec
-    prepared: PreparedWeight
     S_skey: torch.Tensor
     S_key: torch.Tensor
     b: Optional[torch.Tensor]
@@ -153,6 +160,8 @@ class _PassportAffineFn(torch.autograd.Function):
     def forward(ctx, weight, actx: AffineCtx, skey=None, key=None):
         dev = weight.device
         O = actx.spec.O
+        # the fp32 OIHW master weight itself (not the bf16 operand copy): sign(gamma) must be the reference's
+        w = master_weight(weight)
         gamma = torch.empty(O, dtype=torch.float32, device=dev)
         beta = torch.empty(O, dtype=torch.float32, device=dev)
         has_b = actx.b is not None
@@ -160,11 +169,11 @@ class _PassportAffineFn(torch.autograd.Function):
         acc = torch.zeros((), dtype=torch.float32, device=dev) if has_b else None
         d, _ = make_desc(actx.spec, 1, actx.spec.kh, actx.spec.kw)
         L.check(L.load().pp_passport_affine_fwd(
-            C.byref(d), L.ptr(actx.prepared.wf), L.ptr(actx.S_skey), L.ptr(actx.S_key), L.ptr(actx.b),
+            C.byref(d), L.ptr(w), L.ptr(actx.S_skey), L.ptr(actx.S_key), L.ptr(actx.b),
             float(actx.alpha), L.ptr(gamma), L.ptr(beta), L.ptr(loss), L.ptr(acc), _stream()),
             "pp_passport_affine_fwd")
         ctx.actx = actx
-        ctx.save_for_backward(gamma)
+        ctx.save_for_backward(gamma, w if actx.key_shape is not None else None)
         ctx.wshape = weight.shape
         if has_b:
             ctx.mark_non_differentiable(acc)
@@ -174,7 +183,7 @@ class _PassportAffineFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_gamma, g_beta, g_loss=None, g_acc=None):
         actx = ctx.actx
-        (gamma,) = ctx.saved_tensors
+        gamma, w = ctx.saved_tensors
         dev = gamma.device
         dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dev)
 
@@ -199,7 +208,7 @@ class _PassportAffineFn(torch.autograd.Function):
             dskey = torch.empty(actx.key_shape, dtype=torch.float32, device=dev) if want_s else None
             dkey = torch.empty(actx.key_shape, dtype=torch.float32, device=dev) if want_k else None
             L.check(L.load().pp_passport_key_grad(
-                C.byref(dk), int(Bk), L.ptr(actx.prepared.wf), L.ptr(gamma), L.ptr(actx.b), float(actx.alpha),
+                C.byref(dk), int(Bk), L.ptr(w), L.ptr(gamma), L.ptr(actx.b), float(actx.alpha),
                 L.ptr(g_gamma), L.ptr(g_beta), L.ptr(g_loss), L.ptr(scratch), L.ptr(dskey), L.ptr(dkey), _stream()),
                 "pp_passport_key_grad")
         return dw, None, dskey, dkey
@@ -216,8 +225,8 @@ def passport_affine(weight, actx: AffineCtx, skey=None, key=None):
 
 
 def signature_verify(entries, want_gamma=False):
-    """Batched ownership verification: ``entries`` = [(PreparedWeight, S_skey fp64 [K], b fp32 [O])] for every
-    passport layer (all on one device).  Returns (matched int32 [n] device tensor, O list, gamma list or None);
+    """Batched ownership verification: ``entries`` = [(weight fp32 [O,C,kh,kw], S_skey fp64 [K], b fp32 [O])] for
+    every passport layer (all on one device).  Returns (matched int32 [n] device tensor, O list, gamma list or None);
     detection of layer i = matched[i] / O[i]  (trainer_private.py:37-71).  One kernel launch per 64 layers."""
     if not entries:
         return None, [], ([] if want_gamma else None)
@@ -230,14 +239,16 @@ def signature_verify(entries, want_gamma=False):
     for start in range(0, n, L.PP_SIG_MAX_LAYERS):
         chunk = entries[start:start + L.PP_SIG_MAX_LAYERS]
         arr = (L.PPSigLayer * len(chunk))()
-        for i, (prep, S, b) in enumerate(chunk):
+        for i, (weight, S, b) in enumerate(chunk):
             require_cuda(S, "pooled skey")
+            require_cuda(weight, "conv weight")
             bf = b.detach().reshape(-1).float().contiguous()
-            keep.append(bf)
-            O, K = prep.wf.shape[0], prep.wf.numel() // prep.wf.shape[0]
+            w = master_weight(weight)
+            keep.extend((bf, w))
+            O, K = w.shape[0], w.numel() // w.shape[0]
             if S.numel() != K or bf.numel() != O:
                 raise RuntimeError(f"signature_verify: layer {start + i} has O={O} K={K} but |S|={S.numel()} |b|={bf.numel()}")
-            arr[i] = L.PPSigLayer(prep.wf.data_ptr(), S.data_ptr(), bf.data_ptr(), O, K, ofs, 0)
+            arr[i] = L.PPSigLayer(w.data_ptr(), S.data_ptr(), bf.data_ptr(), O, K, ofs, int(w.shape[1]))
             ofs += O
         L.check(L.load().pp_signature_verify(len(chunk), arr, C.c_void_p(matched[start:].data_ptr()), L.ptr(gamma),
                                              _stream()), "pp_signature_verify")

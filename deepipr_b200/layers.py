@@ -118,12 +118,19 @@ class _FusedConvMixin:
         self.__dict__.pop('_pp_keypool', None)
 
     def _prepared(self):
+        """bf16 operand copies of the conv weight (pp_weight_prep).
+
+        Tensor._version does not see edits made through ``.data`` (the idiom of the reference's pruning / flip attack
+        scripts: ``p.data.mul_(mask)``, ``w.data.copy_(...)``), so the cached copies are trusted only where every
+        writer is known: the parameter lives in a parallel.FlatParams (FlatSGD bumps the weight epoch on each step),
+        the module is in training mode and autograd is recording.  Everywhere else — evaluation, attack scripts,
+        stock optimizers — the copies are rebuilt on every forward (one tiny kernel)."""
         w = self.conv.weight
         cached = self.__dict__.get('_pp_prepared')
-        # In no-grad mode (evaluation / attack scripts that edit weight.data) always refresh: it is one tiny kernel.
-        if (cached is not None and torch.is_grad_enabled() and cached.version == w._version
-                and cached.data_ptr == w.data_ptr() and cached.epoch == F_.weight_epoch()
-                and cached.wf.device == w.device):
+        if (cached is not None and torch.is_grad_enabled() and self.training
+                and getattr(w, '_pp_flat_slot', None) is not None
+                and cached.version == w._version and cached.data_ptr == w.data_ptr()
+                and cached.epoch == F_.weight_epoch() and cached.wf.device == w.device):
             return cached
         prepared = F_.prepare_weight(w, self._spec(), need_dgrad=True)
         self.__dict__['_pp_prepared'] = prepared
@@ -322,7 +329,9 @@ class _PassportBase(nn.Module, _FusedConvMixin):
         sig = (key.data_ptr(), key._version, tuple(key.shape), skey.data_ptr(), skey._version, tuple(skey.shape),
                str(key.device))
         cached = self.__dict__.get('_pp_keypool')
-        if cached is not None and cached[0] == sig:
+        # as for the weights: ``key.data.copy_()`` is invisible to _version, so outside a recording training step the
+        # pooled keys are rebuilt every time (two tiny kernels)
+        if cached is not None and cached[0] == sig and torch.is_grad_enabled() and self.training:
             return cached[1], cached[2]
         spec = self._spec()
         S_skey, S_key = F_.key_pool(skey, spec), F_.key_pool(key, spec)
@@ -338,7 +347,7 @@ class _PassportBase(nn.Module, _FusedConvMixin):
         alpha = loss_module.alpha if loss_module is not None else 0.0
         # passport_attack_3.py turns the keys into Parameters: differentiate through the pooled-key identity
         keys_need_grad = torch.is_grad_enabled() and (key.requires_grad or skey.requires_grad)
-        actx = F_.AffineCtx(self._spec(), self._prepared(), S_skey, S_key,
+        actx = F_.AffineCtx(self._spec(), S_skey, S_key,
                             None if b is None else b.detach().reshape(-1).float().contiguous(), float(alpha),
                             tuple(key.shape) if keys_need_grad else None)
         if keys_need_grad:

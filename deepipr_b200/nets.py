@@ -104,11 +104,8 @@ class BasicUnit(nn.Module):
         out = _call(self.convbnrelu_1, x, force_passport, ind)
         out = _call(self.convbn_2, out, force_passport, ind)
         sc = x if isinstance(self.shortcut, nn.Sequential) else _call(self.shortcut, x, force_passport, ind)
-        # F.relu(out + shortcut) (resnet_passport_private.py:78-85).  On the GPU: one fused kernel.  The else branch
-        # exists only because the test-suite's CPU oracle re-uses this wiring with its own (torch) block classes.
-        if out.is_cuda:
-            return F_.add_relu(out, sc)
-        return F.relu(out + sc)
+        # F.relu(out + shortcut) (resnet_passport_private.py:78-85): one fused kernel
+        return F_.add_relu(out, sc)
 
     def set_intermediate_keys(self, pre, x, y=None):
         def step(mine, theirs, a, b):

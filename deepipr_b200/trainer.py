@@ -48,7 +48,7 @@ def test_signature(model):
             m._check_conv()
             S_skey, _ = m._pooled_keys()
             names.append(tag)
-            entries.append((m._prepared(), S_skey, m.b))
+            entries.append((m.weight, S_skey, m.b))
         matched, Os, _ = F_.signature_verify(entries)
         if entries:
             det = (matched.float() / torch.tensor(Os, dtype=torch.float32, device=matched.device)).tolist()

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 9
+#define PP_ABI_VERSION 10
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -89,18 +89,20 @@ int pp_workspace_bytes(const PPConvDesc* d, int which, size_t* bytes);
 int pp_weight_prep(const PPConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream);
 
 /* S[t*C + c] = mean over key batch and output positions of the (zero padded) key patch
- * element (tap t, channel c), key rounded to bf16, accumulated in fp64.
+ * element (tap t, channel c); the fp32 key is NOT rounded, accumulation is fp64.
  * With it  GAP(conv(W, key)) == W[O, kh*kw*C] @ S  (SURVEY 7.3), which replaces the two
  * batch-1 cuDNN convs + means of get_scale / get_bias (passportconv2d.py:146-152,167-173).
  * key_nchw: fp32 [Bk, C, H, W] exactly as the module's `key` / `skey` buffers store it. */
 int pp_key_pool(const PPConvDesc* d, int Bk, const float* key_nchw, double* S, void* stream);
 
-/* gamma = Wf @ S_skey, beta = Wf @ S_key (fp64 accumulate, fp32 out), plus
+/* gamma = W @ S_skey, beta = W @ S_key with W the fp32 OIHW MASTER weight read as [O, C*kh*kw] (fp64 accumulate,
+ * fp32 out) — not the bf16 operand copy: sign(gamma) is the embedded signature and has to be the one the
+ * reference's fp32 get_scale() (passportconv2d.py:142-158) produces on the same weight and key.  Plus
  * SignLoss.add (models/losses/sign_loss.py:25-28,32-54):
  *   sign_loss = alpha * sum(relu(0.1 - b*gamma)) + 1e-5 * sum(gamma^2)
  *   sign_acc  = mean(sign(b) == sign(gamma))
  * b_sign may be NULL (then sign_loss/sign_acc are not written). */
-int pp_passport_affine_fwd(const PPConvDesc* d, const void* w_fprop, const double* S_skey,
+int pp_passport_affine_fwd(const PPConvDesc* d, const float* w_oihw, const double* S_skey,
                            const double* S_key, const float* b_sign, float alpha, float* gamma,
                            float* beta, float* sign_loss, float* sign_acc, void* stream);
 
@@ -116,7 +118,7 @@ int pp_passport_affine_bwd(const PPConvDesc* d, const double* S_skey, const doub
 /* Gradient of pp_passport_affine_fwd w.r.t. the passport keys themselves (needed when an attack turns `key` /
  * `skey` into Parameters: passport_attack_3.py:232-270).  d describes the geometry with H,W = key size.
  *   scratch: 2 * kh*kw*C doubles;  dskey_nchw / dkey_nchw: fp32 [Bk,C,H,W] (either may be NULL). */
-int pp_passport_key_grad(const PPConvDesc* d, int Bk, const void* w_fprop, const float* gamma, const float* b_sign,
+int pp_passport_key_grad(const PPConvDesc* d, int Bk, const float* w_oihw, const float* gamma, const float* b_sign,
                          float alpha, const float* g_gamma, const float* g_beta, const float* g_loss,
                          double* scratch, float* dskey_nchw, float* dkey_nchw, void* stream);
 
@@ -124,20 +126,21 @@ int pp_passport_key_grad(const PPConvDesc* d, int Bk, const void* w_fprop, const
  * TesterPrivate.test_signature (experiments/trainer_private.py:37-71; also tester of passport_attack_1.py:112-170):
  *   signbit = m.get_scale(ind=1).view(-1).sign();  detection = (signbit == m.b).float().mean()
  * layers: HOST array of nlayers (<= PP_SIG_MAX_LAYERS) entries whose pointers are device pointers:
- *   w_fprop bf16 [O, K] (pp_weight_prep), S_skey fp64 [K] (pp_key_pool of skey), b_sign fp32 [O] (+-1), K = kh*kw*C.
+ *   w_oihw fp32 [O, C, kh, kw] (the master weight), S_skey fp64 [K] (pp_key_pool of skey), b_sign fp32 [O] (+-1),
+ *   K = kh*kw*C, C = input channels.
  * matched: device int32 [nlayers], overwritten with the number of channels whose sign(gamma) equals b
  *   (detection = matched / O).  gamma_out: NULL or device fp32 buffer; layer i writes its gamma at
  *   gamma_out[layers[i].gamma_offset ...].  The arithmetic is that of pp_passport_affine_fwd, so the bits are
  *   identical to the per-layer path. */
 #define PP_SIG_MAX_LAYERS 64
 typedef struct PPSigLayer {
-  const void* w_fprop;
+  const float* w_oihw;
   const double* S_skey;
   const float* b_sign;
   int32_t O;
   int32_t K;
   int32_t gamma_offset;
-  int32_t reserved;
+  int32_t C;
 } PPSigLayer;
 int pp_signature_verify(int nlayers, const PPSigLayer* layers, int32_t* matched, float* gamma_out, void* stream);
 

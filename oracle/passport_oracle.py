@@ -21,9 +21,13 @@ of the reference itself, generated in the build container by tests/golden/make_g
 /root/reference read-only) and committed under tests/golden/*.pt; tests/test_oracle_golden.py checks every
 function here against them.
 
-`round_bf16=True` makes every block round its conv operands (input activation, weight, passport keys) to
+`round_bf16=True` makes every block round the operands of its batch convolution (input activation, weight) to
 bf16 before the fp32 computation — the "fp32 accumulate on bf16-rounded operands" model the CUDA path is
-compared with (parity definition).
+compared with (parity definition).  The passport affine (gamma, beta = GAP(conv(W, skey / key)))
+is NOT rounded: the CUDA path evaluates it from the fp32 master weight and the fp32 keys, because sign(gamma) is
+the signature and has to match the reference's fp32 get_scale() bit for bit.  Block outputs and residual joins ARE
+rounded in this mode — activations are bf16 tensors on the CUDA path ("bf16 activations", BASELINE.json north_star),
+each produced by one rounding of an fp32 result — so that whole-network logits can be held to 1e-3.
 """
 import copy
 
@@ -157,7 +161,7 @@ class OracleConvBlock(_OracleBlockBase):
             if self.bn.weight is not None:
                 zn = zn * self.bn.weight.view(1, -1, 1, 1) + self.bn.bias.view(1, -1, 1, 1)
             z = zn
-        return F.relu(z) if self.has_relu else z
+        return bf16_round(F.relu(z) if self.has_relu else z, self.round_bf16)
 
 
 class OraclePassportBlock(_OracleBlockBase):
@@ -193,7 +197,7 @@ class OraclePassportBlock(_OracleBlockBase):
         if use_public:
             return self.scale.view(1, -1, 1, 1)
         stride, pad = self._conv_args()
-        scale = key_affine(self._w(), bf16_round(self.skey, self.round_bf16), stride, pad).view(1, -1, 1, 1)
+        scale = key_affine(self.weight, self.skey, stride, pad).view(1, -1, 1, 1)     # never rounded (see header)
         if self.sign_loss is not None:
             self.sign_loss.reset()
             self.sign_loss.add(scale)
@@ -204,14 +208,49 @@ class OraclePassportBlock(_OracleBlockBase):
         if use_public:
             return self.bias.view(1, -1, 1, 1)
         stride, pad = self._conv_args()
-        return key_affine(self._w(), bf16_round(self.key, self.round_bf16), stride, pad).view(1, -1, 1, 1)
+        return key_affine(self.weight, self.key, stride, pad).view(1, -1, 1, 1)
 
     def forward(self, x, force_passport=False, ind=0):
         stride, pad = self._conv_args()
         gamma = self.get_scale(force_passport, ind)
         beta = self.get_bias(force_passport, ind)
-        return passport_forward(bf16_round(x, self.round_bf16), self._w(), gamma.reshape(-1), beta.reshape(-1), stride,
-                                pad, self._norm_kind(), self.has_relu, **self._norm_args())
+        y = passport_forward(bf16_round(x, self.round_bf16), self._w(), gamma.reshape(-1), beta.reshape(-1), stride,
+                             pad, self._norm_kind(), self.has_relu, **self._norm_args())
+        return bf16_round(y, self.round_bf16)
+
+
+def _call_block(block, x, force_passport, ind):
+    kind = getattr(block, 'KIND', None)
+    if kind == 'private':
+        return block(x, force_passport, ind)
+    if kind == 'v1':
+        return block(x, force_passport)
+    return block(x)
+
+
+class OracleBasicUnit(nn.Module):
+    """Residual unit: BasicPrivateBlock.forward (models/resnet_passport_private.py:67-86), BasicPassportBlock.forward
+    (models/resnet_passport.py:66-85), BasicBlock.forward (models/resnet_normal.py:22-27):
+    out = relu(convbn_2(convbnrelu_1(x)) + shortcut(x))."""
+
+    @classmethod
+    def from_children(cls, convbnrelu_1, convbn_2, shortcut, round_bf16):
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.convbnrelu_1, self.convbn_2, self.shortcut = convbnrelu_1, convbn_2, shortcut
+        self.round_bf16 = round_bf16
+        return self
+
+    def forward(self, x, force_passport=False, ind=0):
+        out = _call_block(self.convbnrelu_1, x, force_passport, ind)
+        out = _call_block(self.convbn_2, out, force_passport, ind)
+        if isinstance(self.shortcut, nn.Sequential):
+            sc = x
+            for m in self.shortcut:          # empty for the identity shortcut
+                sc = m(sc)
+        else:
+            sc = _call_block(self.shortcut, x, force_passport, ind)
+        return bf16_round(F.relu(out + sc), self.round_bf16)
 
 
 def mirror(model, round_bf16=False):
@@ -243,6 +282,10 @@ def mirror(model, round_bf16=False):
                 setattr(parent, name, repl)
             else:
                 walk(child)
+                kids = dict(child.named_children())
+                if {'convbnrelu_1', 'convbn_2', 'shortcut'} <= set(kids):      # a residual unit of the product wiring
+                    setattr(parent, name, OracleBasicUnit.from_children(kids['convbnrelu_1'], kids['convbn_2'],
+                                                                        kids['shortcut'], round_bf16))
 
     walk(out)
     return out.cpu()

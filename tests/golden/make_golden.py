@@ -218,36 +218,65 @@ def model_case():
     out['logits'] = logits
     out['loss'], out['sign_loss'] = loss.detach().clone(), sign_loss.detach().clone()
     out['grad_norms'] = {k: p.grad.double().norm().item() for k, p in model.named_parameters() if p.grad is not None}
+    # the signature itself: gamma of every passport layer on the INITIAL weights (bit-identical on both sides) ...
+    def all_gammas():
+        with torch.no_grad():
+            return {n: m.get_scale(ind=1).reshape(-1).clone() for n, m in model.named_modules()
+                    if isinstance(m, PassportPrivateBlock)}
+    out['gammas_init'] = all_gammas()
+    out['b'] = {n: m.b.clone() for n, m in model.named_modules() if isinstance(m, PassportPrivateBlock)}
     opt.step()
+    out['gammas_after_step'] = all_gammas()          # ... and after the reference's own SGD step
     out['param_sums_after'] = {k: v.double().sum().item() for k, v in model.state_dict().items()}
     sig = quiet(TesterPrivate(model, torch.device('cpu'), verbose=False).test_signature)
     out['signature'] = sig
     # keys generated lazily by the forward (key_type='random'): store them so the replay can be checked
     out['keys'] = {k: v.clone() for k, v in model.state_dict().items()
                    if k.endswith('key_private') and 'layer4.1.convbn_2' in k}
+    # checksums of every lazily generated key (all five layers must replay, not just the stored one)
+    out['key_sums'] = {k: v.double().sum().item() for k, v in model.state_dict().items() if k.endswith('key_private')}
     torch.save(out, os.path.join(HERE, 'resnet18_private_model.pt'))
     print('model: loss', float(loss), 'sign', float(sign_loss))
 
 
 if __name__ == '__main__':
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--only', default='', help='comma list of fixture names to (re)generate; default: all')
+    only = set(filter(None, ap.parse_args().only.split(',')))
     torch.set_num_threads(8)
     bn = {'norm_type': 'bn', 'key_type': 'random', 'sign_loss': 0.1}
     none = {'norm_type': 'none', 'key_type': 'random', 'sign_loss': 0.1}
-    block_case('v1_bn_train', 'v1', 64, 64, 3, 1, 1, bn, N=4, H=8)
-    block_case('v1_bn_eval', 'v1', 64, 64, 3, 1, 1, bn, N=4, H=8, training=False, seed=11)
-    block_case('v1_none_s2_norelu', 'v1', 64, 128, 3, 2, 1, none, N=3, H=8, relu=False, seed=12)
-    block_case('v1_bn_1x1_s2', 'v1', 64, 128, 1, 2, 0, bn, N=4, H=8, seed=13)
-    block_case('v1_bn_keybatch2', 'v1', 64, 64, 3, 1, 1, bn, N=2, H=4, seed=14, key_batch=2)
-    block_case('private_bn_train_2pass', 'private', 64, 64, 3, 1, 1, bn, N=4, H=8, seed=15, ind_passes=(0, 1))
-    block_case('private_bn_force', 'private', 64, 64, 3, 1, 1, bn, N=2, H=4, seed=16, ind_passes=(0,),
-               force_passport=True)
-    block_case('private_gn_2pass', 'private', 64, 64, 3, 1, 1, {'norm_type': 'gn', 'key_type': 'random',
-                                                                'sign_loss': 0.1}, N=2, H=4, seed=17,
-               ind_passes=(0, 1))
-    block_case('conv_bn_train', 'conv', 64, 64, 3, 1, 1, bn, N=4, H=8, seed=18)
-    block_case('conv_bn_s2', 'conv', 64, 128, 3, 2, 1, bn, N=4, H=8, seed=19)
-    block_case('conv_none', 'conv', 64, 64, 3, 1, 1, none, N=2, H=8, seed=20)
-    block_case('conv_stem', 'conv', 3, 64, 3, 1, 1, bn, N=4, H=8, seed=21)
-    block_case('conv_bn_eval', 'conv', 64, 64, 3, 1, 1, bn, N=2, H=8, seed=22, training=False)
-    host_logic_case()
-    model_case()
+    gn = {'norm_type': 'gn', 'key_type': 'random', 'sign_loss': 0.1}
+    cases = [
+        ('v1_bn_train', lambda n: block_case(n, 'v1', 64, 64, 3, 1, 1, bn, N=4, H=8)),
+        ('v1_bn_eval', lambda n: block_case(n, 'v1', 64, 64, 3, 1, 1, bn, N=4, H=8, training=False, seed=11)),
+        ('v1_none_s2_norelu', lambda n: block_case(n, 'v1', 64, 128, 3, 2, 1, none, N=3, H=8, relu=False, seed=12)),
+        ('v1_bn_1x1_s2', lambda n: block_case(n, 'v1', 64, 128, 1, 2, 0, bn, N=4, H=8, seed=13)),
+        ('v1_bn_keybatch2', lambda n: block_case(n, 'v1', 64, 64, 3, 1, 1, bn, N=2, H=4, seed=14, key_batch=2)),
+        ('private_bn_train_2pass', lambda n: block_case(n, 'private', 64, 64, 3, 1, 1, bn, N=4, H=8, seed=15,
+                                                        ind_passes=(0, 1))),
+        ('private_bn_force', lambda n: block_case(n, 'private', 64, 64, 3, 1, 1, bn, N=2, H=4, seed=16,
+                                                  ind_passes=(0,), force_passport=True)),
+        ('private_gn_2pass', lambda n: block_case(n, 'private', 64, 64, 3, 1, 1, gn, N=2, H=4, seed=17,
+                                                  ind_passes=(0, 1))),
+        ('conv_bn_train', lambda n: block_case(n, 'conv', 64, 64, 3, 1, 1, bn, N=4, H=8, seed=18)),
+        ('conv_bn_s2', lambda n: block_case(n, 'conv', 64, 128, 3, 2, 1, bn, N=4, H=8, seed=19)),
+        ('conv_none', lambda n: block_case(n, 'conv', 64, 64, 3, 1, 1, none, N=2, H=8, seed=20)),
+        ('conv_stem', lambda n: block_case(n, 'conv', 3, 64, 3, 1, 1, bn, N=4, H=8, seed=21)),
+        ('conv_bn_eval', lambda n: block_case(n, 'conv', 64, 64, 3, 1, 1, bn, N=2, H=8, seed=22, training=False)),
+        # operands NOT pre-rounded to bf16: the reference's plain fp32 inputs.  The CUDA path rounds the operands of
+        # the batch convolution itself, but gamma / beta / sign(gamma) come from the fp32 master weight and keys and
+        # must match these bit for bit in sign.
+        ('v1_bn_train_f32ops', lambda n: block_case(n, 'v1', 64, 64, 3, 1, 1, bn, N=4, H=8, seed=31, round_ops=False)),
+        ('v1_bn_s2_f32ops', lambda n: block_case(n, 'v1', 128, 256, 3, 2, 1, bn, N=4, H=8, seed=32, round_ops=False)),
+        ('private_bn_2pass_f32ops', lambda n: block_case(n, 'private', 128, 128, 3, 1, 1, bn, N=4, H=4, seed=33,
+                                                         ind_passes=(0, 1), round_ops=False)),
+        ('private_1x1_s2_keybatch2_f32ops', lambda n: block_case(n, 'private', 64, 128, 1, 2, 0, bn, N=2, H=8, seed=34,
+                                                                 ind_passes=(0, 1), round_ops=False, key_batch=2)),
+        ('host_logic', lambda n: host_logic_case()),
+        ('resnet18_private_model', lambda n: model_case()),
+    ]
+    for name, fn in cases:
+        if not only or name in only:
+            fn(name)

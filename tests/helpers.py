@@ -18,6 +18,12 @@ BLOCK_FIXTURES = [
 ]
 
 
+#: fixtures whose operands were NOT pre-rounded to bf16 (the reference's plain fp32 inputs)
+F32OPS_FIXTURES = [
+    "v1_bn_train_f32ops", "v1_bn_s2_f32ops", "private_bn_2pass_f32ops", "private_1x1_s2_keybatch2_f32ops",
+]
+
+
 def load_golden(name):
     return torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
 

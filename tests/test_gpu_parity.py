@@ -16,8 +16,8 @@ from deepipr_b200 import _lib as L
 from deepipr_b200 import functional as F_
 from deepipr_b200 import layers, nets
 from oracle import passport_oracle as po
-from tests.helpers import (BLOCK_FIXTURES, bf16r, load_golden, product_block_from_fixture, quiet, rel_l2, run_block,
-                           seed_all)
+from tests.helpers import (BLOCK_FIXTURES, F32OPS_FIXTURES, bf16r, load_golden, product_block_from_fixture, quiet,
+                           rel_l2, run_block, seed_all)
 
 pytestmark = pytest.mark.gpu
 
@@ -64,6 +64,45 @@ def test_block_matches_reference_golden(name):
                 gamma, beta = m.get_scale(True).reshape(-1).cpu(), m.get_bias(True).reshape(-1).cpu()
         assert rel_l2(gamma, g["gamma"]) < VEC_TOL and rel_l2(beta, g["beta"]) < VEC_TOL
         assert torch.equal(torch.sign(gamma), torch.sign(g["gamma"])), "signature bits differ from the reference"
+
+
+@pytest.mark.parametrize("name", F32OPS_FIXTURES)
+def test_block_matches_reference_golden_unrounded_operands(name):
+    """The reference's plain fp32 inputs (nothing pre-rounded to bf16).  gamma / beta come from the fp32 master weight
+    and the fp32 keys, so they match the reference to fp32 accuracy and sign(gamma) — the signature — bit for bit;
+    the batch convolution rounds x and W to bf16, which shows in y and the gradients only."""
+    g = load_golden(name)
+    block = product_block_from_fixture(g)
+    oracle = po.mirror(block, round_bf16=True)
+    oracle.train(g["cfg"]["training"])
+    ref = run_block(oracle, g, "cpu")
+    m = block.cuda()
+    out = run_block(m, g, "cuda")
+    for k, y in enumerate(g["y"]):
+        assert rel_l2(out["y"][k], bf16r(ref["y"][k])) < ACT_TOL, f"y[{k}] vs the bf16-operand oracle"
+        assert rel_l2(out["y"][k], y) < 8e-3, f"y[{k}] vs the reference's fp32 run"   # 3 bf16 roundings (x, W, y)
+    assert abs(float(out["sign_loss"]) - float(g["sign_loss"])) <= VEC_TOL * max(1.0, abs(float(g["sign_loss"])))
+    assert abs(float(out["sign_acc"]) - float(g["sign_acc"])) < 1e-6
+    assert rel_l2(out["dx"], ref["dx"]) < GRAD_TOL and rel_l2(out["dx"], g["dx"]) < 1.2e-2
+    for key, gref in g["grads"].items():
+        mine = _grad(out, key)
+        assert mine is not None, key
+        assert rel_l2(mine, _grad(ref, key)) < GRAD_TOL, key
+        assert rel_l2(mine, gref) < 1.2e-2, key
+    m.eval()
+    with torch.no_grad():
+        if g["cfg"]["kind"] == "private":
+            gamma, beta = m.get_scale(ind=1).reshape(-1).cpu(), m.get_bias(ind=1).reshape(-1).cpu()
+        else:
+            gamma, beta = m.get_scale(True).reshape(-1).cpu(), m.get_bias(True).reshape(-1).cpu()
+    assert rel_l2(gamma, g["gamma"]) < VEC_TOL and rel_l2(beta, g["beta"]) < VEC_TOL
+    assert torch.equal(torch.sign(gamma), torch.sign(g["gamma"])), "signature bits differ from the reference"
+    from deepipr_b200.trainer import test_signature, test_signature_per_layer
+    holder = torch.nn.Sequential(m)
+    want = (torch.sign(g["gamma"]) == g["state"]["b"]).float().mean().item()
+    for fn in (test_signature, test_signature_per_layer):
+        (det,) = fn(holder).values()
+        assert det == want, fn.__name__
 
 
 GEOMS = [  # N, C, H, O, k, s, p
@@ -298,14 +337,40 @@ def test_resnet18_private_step_matches_reference_golden_and_oracle():
     for ind in range(2):
         assert rel_l2(preds[ind].float().cpu(), gm["logits"][ind]) < 3e-2
     assert abs(loss.item() - gm["loss"].item()) < 2e-2 * gm["loss"].item()
-    assert abs(sign_loss.item() - gm["sign_loss"].item()) < 1e-3 * gm["sign_loss"].item()
+    assert abs(sign_loss.item() - gm["sign_loss"].item()) < VEC_TOL * gm["sign_loss"].item()    # fp32 weights and keys
     gn = {k: p.grad.double().norm().item() for k, p in model.named_parameters()}
     for k in ("linear.weight", "layer4.1.convbn_2.weight", "layer4.0.convbnrelu_1.scale", "convbnrelu_1.conv.weight"):
         assert abs(gn[k] - gm["grad_norms"][k]) < 6e-2 * gm["grad_norms"][k], k
+    # The signature on IDENTICAL weights and keys (the lazily created keys replay the reference's numpy stream, the
+    # parameters its torch stream): every bit of every passport layer equals the reference's fp32 get_scale().
+    from deepipr_b200.trainer import test_signature
+    blocks = {n: m for n, m in model.named_modules() if getattr(m, "KIND", None) == "private"}
+    assert set(blocks) == set(gm["gammas_init"])
+    for k, v in gm["key_sums"].items():
+        assert abs(model.state_dict()[k].double().sum().item() - v) < 1e-9 * max(1.0, abs(v)), k
+    with torch.no_grad():
+        for n, m in blocks.items():
+            gam = m.get_scale(ind=1).reshape(-1).cpu()
+            assert rel_l2(gam, gm["gammas_init"][n]) < VEC_TOL, n
+            assert torch.equal(gam.sign(), gm["gammas_init"][n].sign()), f"signature bits differ at init in {n}"
+    sig0 = test_signature(model)
+    for n in blocks:
+        assert sig0["private_" + n] == (gm["gammas_init"][n].sign() == gm["b"][n]).float().mean().item(), n
+    model.train()
     opt.step()   # the golden signature was read after the reference's optimizer step
-    sig = __import__("deepipr_b200.trainer", fromlist=["x"]).test_signature(model)
-    # the reference ran on fp32 keys/weights, this path rounds them to bf16: a few near-zero gammas may flip
-    assert sig == pytest.approx(gm["signature"], abs=0.02), "signature detection differs from the reference"
+    # After one SGD step the two weight sets differ by lr x (bf16-operand gradient noise), ~1e-5 on gamma: every bit
+    # whose reference gamma is not inside that band must agree, and the detection rates with them.
+    sig = test_signature(model)
+    with torch.no_grad():
+        for n, m in blocks.items():
+            gam = m.get_scale(ind=1).reshape(-1).cpu()
+            ref = gm["gammas_after_step"][n]
+            assert (gam - ref).abs().max().item() < 2e-4, n
+            decided = ref.abs() > 2e-4
+            assert torch.equal(gam.sign()[decided], ref.sign()[decided]), f"signature bits differ after the step in {n}"
+            flips = int((gam.sign() != ref.sign()).sum())
+            assert flips <= int((~decided).sum()), n
+            assert abs(sig["private_" + n] - gm["signature"]["private_" + n]) <= flips / ref.numel() + 1e-9, n
 
 
 def test_resnet18_private_trajectory_and_signature_vs_oracle():
@@ -348,6 +413,46 @@ def test_resnet18_private_trajectory_and_signature_vs_oracle():
         decided = gam_o.abs() > 0.05 * gam_o.abs().median()
         assert torch.equal(gam_g.sign()[decided], gam_o.sign()[decided]), f"signature bits differ in {ng}"
         assert (gam_g.sign() != gam_o.sign()).sum().item() <= 3, ng
+
+
+def _fix_keys(model, kind, hw):
+    with torch.no_grad():
+        for mod in model.modules():
+            if getattr(mod, "KIND", None) == kind:
+                c = mod.conv.in_channels
+                h = hw(mod)
+                mod.set_key(torch.rand(1, c, h, h) * 2 - 1, torch.rand(1, c, h, h) * 2 - 1)     # plain fp32 keys
+
+
+@pytest.mark.parametrize("net", ["resnet18_private", "alexnet_v1"])
+def test_whole_network_logits_within_1e3_of_the_bf16_activation_oracle(net):
+    """north_star: "within 1e-3 relative on bf16 activations/logits".  The oracle runs the reference's arithmetic with
+    the CUDA path's storage model — conv operands and every activation tensor rounded to bf16 once, fp32 everywhere
+    else — so the only differences left are fp32 summation order (rare 1-ulp flips of a bf16 activation).  Checked on
+    the logits of every pass, in training mode (batch statistics) and in evaluation mode (running statistics)."""
+    seed_all(6)
+    if net == "resnet18_private":
+        pk = nets.passport_kwargs_from_config(nets.resnet18_passport_config(), "bn", "random", 0.1)
+        model = quiet(nets.ResNet18, "private", 100, pk)                       # BASELINE config 3: CIFAR-100
+        _fix_keys(model, "private", lambda m: 8 if m.conv.stride[0] == 2 else 4)
+        inds = (0, 1)
+    else:
+        pk = nets.passport_kwargs_from_config(nets.alexnet_passport_config(), "bn", "random", 0.1)
+        model = quiet(nets.AlexNetCifar, "v1", 3, 10, pk)
+        _fix_keys(model, "v1", lambda m: 8)
+        inds = (0,)
+    x = bf16r(torch.randn(32, 3, 32, 32))
+    oracle = po.mirror(model, round_bf16=True)
+    model = model.cuda()
+    for training in (True, False):
+        oracle.train(training)
+        model.train(training)
+        with torch.no_grad():
+            for ind in inds:
+                want = oracle(x, ind=ind) if net == "resnet18_private" else oracle(x)
+                got = model(x.cuda(), ind=ind) if net == "resnet18_private" else model(x.cuda())
+                err = rel_l2(got.float().cpu(), want)
+                assert err < ACT_TOL, (net, training, ind, err)
 
 
 def test_alexnet_v1_step_vs_oracle():
@@ -603,7 +708,7 @@ def test_batched_signature_verification_equals_per_layer_path():
     for k in looped:
         assert batched[k] == looped[k], k
     blocks = [m for m in model.modules() if isinstance(m, layers.PassportPrivateBlock)]
-    entries = [(m._prepared(), m._pooled_keys()[0], m.b) for m in blocks]
+    entries = [(m.weight, m._pooled_keys()[0], m.b) for m in blocks]
     matched, Os, gammas = F_.signature_verify(entries, want_gamma=True)
     with torch.no_grad():
         for m, g, o, c in zip(blocks, gammas, Os, matched.tolist()):
