@@ -21,7 +21,19 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
-static int g_sm_count = -1, g_cc_major = -1, g_cc_minor = -1;
+// per-device attributes (a process may drive several devices; cached by ordinal)
+struct DevInfo { int sm = -1, cc_major = -1, cc_minor = -1; };
+static DevInfo g_dev[kMaxDevices];
+static std::mutex g_dev_mu;
+
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return dev;
+}
 
 // ---------------------------------------------------------------- launch counter + kernel profiling
 static std::atomic<long long> g_launches{0};
@@ -48,35 +60,43 @@ void prof_end(int kind, cudaStream_t s) {
   if (!g_prof[kind].empty()) cudaEventRecord(g_prof[kind].back().stop, s);
 }
 
-static int query_device() {
-  if (g_sm_count >= 0) return PP_OK;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) {
-    cudaGetLastError();
+static int query_device(DevInfo* out) {
+  const int dev = current_device();
+  if (dev < 0) {
     set_error("no CUDA device (libpassport_sm100 has no CPU path)");
     return PP_ENODEVICE;
   }
-  int sm = 0, maj = 0, min = 0;
-  if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+  if (dev < kMaxDevices) {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (g_dev[dev].sm >= 0) { *out = g_dev[dev]; return PP_OK; }
+  }
+  DevInfo di;
+  if (cudaDeviceGetAttribute(&di.sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&di.cc_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&di.cc_minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
     cudaGetLastError();
     set_error("cannot query CUDA device attributes");
     return PP_ENODEVICE;
   }
-  g_sm_count = sm; g_cc_major = maj; g_cc_minor = min;
+  if (dev < kMaxDevices) {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    g_dev[dev] = di;
+  }
+  *out = di;
   return PP_OK;
 }
 
 int device_sm_count() {
-  if (query_device() != PP_OK) return 0;
-  return g_sm_count;
+  DevInfo di;
+  if (query_device(&di) != PP_OK) return 0;
+  return di.sm;
 }
 
 int check_device() {
-  PP_TRY(query_device());
-  PP_REQUIRE(g_cc_major == 10, PP_ENODEVICE, "device is sm_%d%d; this library is built for sm_100a only", g_cc_major,
-             g_cc_minor);
+  DevInfo di;
+  PP_TRY(query_device(&di));
+  PP_REQUIRE(di.cc_major == 10, PP_ENODEVICE, "device is sm_%d%d; this library is built for sm_100a only", di.cc_major,
+             di.cc_minor);
   return PP_OK;
 }
 
@@ -351,10 +371,11 @@ int pp_version(void) { return PP_ABI_VERSION; }
 const char* pp_last_error(void) { return get_error(); }
 
 int pp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
-  PP_TRY(query_device());
-  if (sm_count) *sm_count = g_sm_count;
-  if (cc_major) *cc_major = g_cc_major;
-  if (cc_minor) *cc_minor = g_cc_minor;
+  DevInfo di;
+  PP_TRY(query_device(&di));
+  if (sm_count) *sm_count = di.sm;
+  if (cc_major) *cc_major = di.cc_major;
+  if (cc_minor) *cc_minor = di.cc_minor;
   return PP_OK;
 }
 

@@ -38,6 +38,19 @@ const char* get_error();
     }                                \
   } while (0)
 
+// cudaFuncSetAttribute is a per-DEVICE setting: remember it per device ordinal, not per process (a process may
+// drive several GPUs, e.g. under nn.DataParallel).  `kernel` is passed in parentheses (template commas).
+constexpr int kMaxDevices = 64;
+#define PP_SET_MAX_SMEM_ONCE(kernel, bytes)                                                                  \
+  do {                                                                                                      \
+    static bool done_[pp::kMaxDevices] = {};                                                                \
+    const int dev_ = pp::current_device();                                                                  \
+    if (dev_ < 0 || dev_ >= pp::kMaxDevices || !done_[dev_]) {                                              \
+      PP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));   \
+      if (dev_ >= 0 && dev_ < pp::kMaxDevices) done_[dev_] = true;                                          \
+    }                                                                                                       \
+  } while (0)
+
 #define PP_TRY(expr)            \
   do {                          \
     int _s = (expr);            \
@@ -86,6 +99,7 @@ enum { PROF_TAPGEMM = 0, PROF_WGRAD = 1, PROF_AFFINE = 2, PROF_REDUCE = 3, PROF_
 void prof_begin(int kind, double flops, int c, int nout, int taps, cudaStream_t s);
 void prof_end(int kind, cudaStream_t s);
 
+int current_device();   // ordinal of the calling thread's current CUDA device (-1: none)
 int device_sm_count();
 int check_device();  // PP_OK iff current device is sm_100
 

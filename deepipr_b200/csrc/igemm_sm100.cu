@@ -571,12 +571,7 @@ static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, cons
   p.out = e.out; p.out_f32 = e.out_f32; p.scale = e.scale; p.shift = e.shift; p.relu = e.relu;
   p.stats_partial = e.stats_partial;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  PP_SET_MAX_SMEM_ONCE((tapgemm_kernel<BN, RESB>), Cfg::kSmemBytes);
   PP_REQUIRE(e.stats_partial == nullptr || g.Nout <= kMaxStatsN, PP_EUNSUPPORTED,
              "fused column statistics support Nout <= %d (Nout=%d)", kMaxStatsN, g.Nout);
   const int grid = tapgemm_tcgen05_grid(g);
@@ -974,11 +969,7 @@ static int launch_pxn(const TapGemm& g, PxnPlan& pl, const void* act, const void
     d.dbg = dbg;
     d.m64 = (g.Nout == 64) ? m64 : 0;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(pxn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
+  PP_SET_MAX_SMEM_ONCE((pxn_kernel), 232448);
   prof_begin(PROF_TAPGEMM, 2.0 * (double)d.M * g.Nout * g.ntaps * g.C, g.C, g.Nout, g.ntaps, s);
   pxn_kernel<<<pl.grid, kThreads, pl.smem_bytes, s>>>(tmAct, tmW, d);
   prof_end(PROF_TAPGEMM, s);
@@ -1244,12 +1235,7 @@ static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, 
   p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
   for (int t = 0; t < g.ntaps; ++t) { p.tap_dh[t] = g.tap_dh[t]; p.tap_dw[t] = g.tap_dw[t]; }
   p.partial = partial;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  PP_SET_MAX_SMEM_ONCE((wgrad_kernel<BN>), Cfg::kSmemBytes);
   const int m_tiles = (p.Ktot + 127) / 128;
   dim3 grid(m_tiles * p.n_tiles, splits);
   prof_begin(PROF_WGRAD, 2.0 * (double)M * O * g.ntaps * g.C, g.C, O, g.ntaps, s);
@@ -1501,11 +1487,7 @@ static int launch_wgrad_om(const TapGemm& g, const void* x, const void* dz, int 
   p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
   for (int t = 0; t < g.ntaps; ++t) { p.tap_dh[t] = g.tap_dh[t]; p.tap_dw[t] = g.tap_dw[t]; }
   p.partial = partial;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_om_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOmSmemBytes));
-    attr_set = true;
-  }
+  PP_SET_MAX_SMEM_ONCE((wgrad_om_kernel), kOmSmemBytes);
   dim3 grid(paired ? 2 : (p.nslabs + 3) / 4, splits);
   prof_begin(PROF_WGRAD, 2.0 * (double)M * O * g.ntaps * g.C, g.C, O, g.ntaps, s);
   wgrad_om_kernel<<<grid, kThreads, kOmSmemBytes, s>>>(tmX, tmDz, tmDzS, p);

@@ -637,18 +637,10 @@ static int column_reduce_launch(int mode, const __nv_bfloat16* dy, const void* z
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   if (mode == 0) {
-    static bool attr0 = false;
-    if (!attr0) {
-      cudaFuncSetAttribute(column_reduce_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      attr0 = true;
-    }
+    PP_SET_MAX_SMEM_ONCE((column_reduce_kernel<0>), 64 * 1024);
     column_reduce_kernel<0><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, relu, partial);
   } else {
-    static bool attr1 = false;
-    if (!attr1) {
-      cudaFuncSetAttribute(column_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-      attr1 = true;
-    }
+    PP_SET_MAX_SMEM_ONCE((column_reduce_kernel<1>), 64 * 1024);
     column_reduce_kernel<1><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, relu, partial);
   }
   PP_POST_LAUNCH();

@@ -24,6 +24,12 @@ def require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise RuntimeError(
             f"deepipr_b200: {what} is on {t.device}; the passport kernels are sm_100a CUDA only (no CPU fallback)")
+    # the library launches on the calling thread's CURRENT device and on torch's current stream of that device
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(
+            f"deepipr_b200: {what} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+            "run one process per GPU (torchrun) or wrap the call in torch.cuda.device(...) — nn.DataParallel-style "
+            "multi-device threads are not supported")
 
 
 @dataclass(frozen=True)

@@ -111,6 +111,9 @@ class GradBuckets:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.overlap = overlap
+        self._avg_op = None
+        if dist.is_initialized() and dist.get_backend(process_group) == "nccl":
+            self._avg_op = dist.ReduceOp.AVG
         # buckets in reverse parameter order (gradients become ready roughly back to front)
         self.buckets = []            # (start, end) element ranges of flat_grad
         self.bucket_of = [0] * len(flat.params)
@@ -131,6 +134,8 @@ class GradBuckets:
         self._next = 0               # first bucket not yet handed to the communicator
         self._works = []
         self._hooks = []
+        self._ready = [False] * len(flat.params)   # parameter i reported its gradient in the current step
+        self._accumulate = False     # no_sync(): gradients accumulate locally, nothing is counted or reduced
         if overlap and self.world > 1:
             for i, p in enumerate(flat.params):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
@@ -144,7 +149,32 @@ class GradBuckets:
             self.bucket_of[i] = idx
         self.buckets.append((start, end, list(members)))
 
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward passes inside it only add into the flat gradient
+        buffer (no bucket is counted or all-reduced).  The first backward OUTSIDE it, followed by finish(), reduces
+        the accumulated sums — the contract of torch DDP.no_sync()."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            prev, self._accumulate = self._accumulate, True
+            try:
+                yield self
+            finally:
+                self._accumulate = prev
+        return ctx()
+
     def _param_ready(self, i):
+        if self._accumulate:
+            return
+        if self._ready[i]:
+            # A second backward before finish() (gradient accumulation, retain_graph): this parameter's bucket may
+            # already be divided by the world size and in flight, so adding an un-reduced local gradient on top would
+            # make the ranks diverge silently.  Refuse loudly instead.
+            raise RuntimeError(
+                "deepipr_b200.GradBuckets: a parameter reported a second gradient before finish(); run all but the "
+                "last backward of a step inside GradBuckets.no_sync() and call finish() once per optimizer step")
+        self._ready[i] = True
         b = self.bucket_of[i]
         self._pending[b] -= 1
         # collectives must be issued in the same order on every rank: launch strictly in bucket order
@@ -154,6 +184,12 @@ class GradBuckets:
 
     def _make_hook(self, i):
         def hook(p):
+            if self._accumulate:
+                view = self.flat.grad_view(i)
+                if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                    view.add_(p.grad)
+                    p.grad = view
+                return
             if self.flat.is_direct(i):
                 return          # FlatParams.direct_done() reports this parameter (see FlatParams.is_direct)
             view = self.flat.grad_view(i)
@@ -167,12 +203,20 @@ class GradBuckets:
         start, end, _ = self.buckets[b]
         chunk = self.flat.flat_grad[start:end]
         if self.world > 1:
-            chunk.div_(self.world)   # pre-scale: SUM of pre-divided grads == mean (gloo has no AVG)
-            self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if self._avg_op is not None:     # NCCL: the mean is taken inside the collective (no pre-scaling launch)
+                self._works.append(dist.all_reduce(chunk, op=self._avg_op, group=self.group, async_op=True))
+            else:
+                chunk.div_(self.world)       # gloo has no AVG: SUM of pre-divided gradients == mean
+                self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def finish(self):
-        """Call after backward(): reduce whatever the hooks have not launched yet and wait for everything."""
+        """Call after the last backward() of a step: reduce whatever the hooks have not launched yet and wait."""
         if self.world > 1:
+            # a parameter that received no gradient this step (p.grad is None after an external
+            # zero_grad(set_to_none=True)) must contribute zeros, not last step's values still sitting in the flat buffer
+            for i, p in enumerate(self.flat.params):
+                if p.grad is None:
+                    self.flat.grad_view(i).zero_()
             self.flat.ensure_grad_views()
             while self._next < len(self.buckets):   # no-overlap mode, or parameters that got no gradient this step
                 self._launch(self._next)
@@ -182,6 +226,7 @@ class GradBuckets:
         self._works = []
         self._next = 0
         self._pending = [len(m) for (_, _, m) in self.buckets]
+        self._ready = [False] * len(self.flat.params)
 
     def remove_hooks(self):
         for h in self._hooks:
@@ -204,7 +249,11 @@ def broadcast_state(module, src=0, group=None):
 
 
 class FlatSGD(torch.optim.Optimizer):
-    """SGD(momentum, weight_decay) over FlatParams: one fused kernel launch per step (pp_sgd_step)."""
+    """SGD(momentum, weight_decay) over FlatParams: one fused kernel launch per step (pp_sgd_step).
+
+    Differences from torch.optim.SGD, by construction of the flat buffer: a parameter that received no gradient is
+    treated as having a zero gradient (weight decay and momentum still apply to it; torch skips it), and the update
+    also runs over the zero padding between parameters (which stays zero)."""
 
     def __init__(self, flat: FlatParams, lr=0.01, momentum=0.9, weight_decay=1e-4):
         self.flat = flat
@@ -212,6 +261,29 @@ class FlatSGD(torch.optim.Optimizer):
         super().__init__(flat.params, defaults)
         self._buf = torch.zeros_like(flat.flat)
         self._steps = 0
+
+    def add_param_group(self, param_group):
+        if getattr(self, "param_groups", None):
+            raise ValueError("FlatSGD updates ONE flat buffer with one (lr, momentum, weight_decay): a second param "
+                             "group is not supported (build a second FlatParams + FlatSGD instead)")
+        super().add_param_group(param_group)
+
+    def state_dict(self):
+        """torch layout plus the flat momentum buffer and the step count (momentum lives outside Optimizer.state)."""
+        sd = super().state_dict()
+        sd["flat_momentum"] = self._buf.clone()
+        sd["flat_steps"] = self._steps
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        buf, steps = state_dict.pop("flat_momentum", None), state_dict.pop("flat_steps", 0)
+        super().load_state_dict(state_dict)
+        if buf is not None:
+            if buf.numel() != self._buf.numel():
+                raise ValueError("FlatSGD.load_state_dict: momentum buffer size differs from this FlatParams")
+            self._buf.copy_(buf.to(self._buf.device))
+        self._steps = int(steps)
 
     def zero_grad(self, set_to_none=False):
         self.flat.zero_grad()
@@ -224,6 +296,8 @@ class FlatSGD(torch.optim.Optimizer):
                 loss = closure()
         F_.require_cuda(self.flat.flat, "FlatSGD parameters")
         self.flat.ensure_grad_views()
+        if len(self.param_groups) != 1:
+            raise ValueError("FlatSGD supports exactly one param group")
         g = self.param_groups[0]
         L.check(L.load().pp_sgd_step(
             C.c_size_t(self.flat.numel), L.ptr(self.flat.flat), L.ptr(self.flat.flat_grad), L.ptr(self._buf),

@@ -183,3 +183,80 @@ def test_directly_accumulated_gradients_shared_bucket():
 
 def test_directly_accumulated_gradients_many_buckets():
     _run_direct(bucket_bytes=6000, want_buckets=2)
+
+
+# ---- gradient accumulation / repeated backward: a second backward before finish() must not add
+# un-reduced gradients on top of buckets that are already divided and in flight
+def _accum_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _model(seed=100)
+        flat = FlatParams(model.parameters())
+        buckets = GradBuckets(flat, bucket_bytes=1024, overlap=True)
+        g = torch.Generator().manual_seed(7)
+        X = torch.randn(16, 12, generator=g)
+        Y = torch.randint(0, 5, (16,), generator=g)
+        xs, ys = X[rank * 8:(rank + 1) * 8], Y[rank * 8:(rank + 1) * 8]
+        ce = torch.nn.functional.cross_entropy
+        # (1) two backward passes without no_sync(): refused, not silently wrong
+        flat.zero_grad()
+        ce(model(xs[:4]), ys[:4]).backward()
+        try:
+            ce(model(xs[4:]), ys[4:]).backward()
+            refused = False
+        except RuntimeError as e:
+            refused = "no_sync" in str(e)
+        buckets.finish()
+        # (2) the supported way: all but the last micro-batch inside no_sync()
+        flat.zero_grad()
+        with buckets.no_sync():
+            (0.5 * ce(model(xs[:4]), ys[:4])).backward()
+        (0.5 * ce(model(xs[4:]), ys[4:])).backward()
+        buckets.finish()
+        accum = flat.flat_grad.clone()
+        # (3) a parameter without a gradient after zero_grad(set_to_none=True) contributes zeros, not stale values
+        opt = torch.optim.SGD(flat.params, lr=0.1)
+        flat.flat_grad.fill_(123.0)
+        opt.zero_grad()                              # set_to_none=True
+        head = list(model.children())[-1]
+        ce(head(torch.randn(4, 32, generator=g)), ys[:4]).backward()     # only the last layer gets a gradient
+        buckets.finish()
+        first_w = flat.grad_view(0).clone()
+        out[rank] = dict(refused=refused, accum=accum, first_w=first_w, offsets=list(flat.offsets))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_accumulation_no_sync_and_second_backward_is_refused():
+    port = _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_accum_worker, args=(2, port, out), nprocs=2, join=True)
+    model = _model(seed=100)
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(16, 12, generator=g)
+    Y = torch.randint(0, 5, (16,), generator=g)
+    torch.nn.functional.cross_entropy(model(X), Y).backward()      # mean over the global batch of 16
+    for rank in (0, 1):
+        r = out[rank]
+        assert r["refused"], "a second backward before finish() must raise"
+        for p, o in zip(model.parameters(), r["offsets"]):
+            assert torch.allclose(r["accum"][o:o + p.numel()].view_as(p), p.grad, rtol=1e-5, atol=1e-6)
+        assert r["first_w"].abs().sum() == 0, "stale gradient of a parameter that got no gradient was reduced"
+
+
+def test_flat_sgd_refuses_a_second_param_group_and_round_trips_its_state():
+    from deepipr_b200.parallel import FlatSGD
+    import pytest
+    ps = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    flat = FlatParams(ps)
+    opt = FlatSGD(flat, lr=0.1, momentum=0.9, weight_decay=1e-4)
+    with pytest.raises(ValueError, match="param group"):
+        opt.add_param_group({"params": [torch.nn.Parameter(torch.randn(2))]})
+    opt._buf.normal_()
+    opt._steps = 7
+    sd = opt.state_dict()
+    opt2 = FlatSGD(FlatParams([torch.nn.Parameter(p.detach().clone()) for p in ps]), lr=0.5)
+    opt2.load_state_dict(sd)
+    assert opt2._steps == 7 and torch.equal(opt2._buf, opt._buf) and opt2.param_groups[0]["lr"] == 0.1
