@@ -1,17 +1,22 @@
 #!/usr/bin/env python
-"""Benchmark of the passport-layer training path (contract: see the task brief / DESIGN.md "Measurement").
+"""Benchmark of the passport-layer training path (contract: the task brief / DESIGN.md "Measurement").
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps 3 --warmup 1        # CPU arm: the oracle port of the reference trainer
+    python bench.py --impl reference --steps 20 --warmup 5       # the UNMODIFIED reference trainer on the host cores
+    python bench.py --config v1_imagenet | v2_cifar100 | v1_alexnet | v2_cifar10     # the other BASELINE configs
 
-Workload: one TrainerPrivate-style optimisation step (public + private forward, one backward, SGD) of ResNet-18 with
-passport layers in layer4 (passport_configs/resnet18_passport.json) on synthetic CIFAR-10-shaped tensors, bf16
-activations, per-GPU batch 1184 = 8 x 148 SMs (weak scaling).  One JSON line on stdout (rank 0).
+Default workload (BASELINE.json metric "images/sec ResNet18-passport CIFAR10 train", configs[3]): one
+TrainerPrivate step — public + private forward, one backward, SGD — of ResNet-18 with passport layers in layer4
+(passport_configs/resnet18_passport.json) on synthetic CIFAR-10-shaped tensors, V3: every step appends 2 trigger-set
+images (experiments/trainer_private.py:135-146), bf16 activations, per-GPU batch 1024, weak scaling.
+One JSON line on stdout (rank 0).
 """
 import argparse
+import contextlib
 import ctypes as C
+import io
 import json
 import os
 import statistics
@@ -25,18 +30,37 @@ sys.path.insert(0, ROOT)
 
 METRIC = "images/sec ResNet18-passport CIFAR10 train"
 UNIT = "images/s"
-WORKLOAD = "ResNet18 V2 private-passport (layer4 x5 passport convs) CIFAR10-shaped TrainerPrivate step"
-PER_GPU_BATCH = 1184                # 8 images per SM (148 SMs): every conv's tile count is a multiple of the SM count
-CPU_BATCH = 64                     # reference default batch (train_v1.py:15); bounded CPU sample
-GFLOP_PER_IMAGE_STEP = 6.665       # 2 forwards, 3x fwd FLOPs each
+
+#: the BASELINE.json configurations (2..5) + the round-1 workload; gflop = algorithmic GFLOP per image-step
+CONFIGS = {
+    "v3_cifar10_trigger": dict(net="resnet18", scheme="private", classes=10, img=32, batch=1024, trigger=True,
+                               gflop=6.665, dtype="bf16",
+                               workload="ResNet18 V3 private-passport + trigger set (layer4: 5 passport convs), "
+                                        "CIFAR10-shaped TrainerPrivate step (BASELINE configs[3])"),
+    "v2_cifar10": dict(net="resnet18", scheme="private", classes=10, img=32, batch=1024, trigger=False, gflop=6.665,
+                       dtype="bf16", workload="ResNet18 V2 private-passport, CIFAR10-shaped TrainerPrivate step "
+                                              "(round-1 workload)"),
+    "v2_cifar100": dict(net="resnet18", scheme="private", classes=100, img=32, batch=1024, trigger=False, gflop=6.665,
+                        dtype="bf16", workload="ResNet18 V2 private-passport CIFAR100-shaped TrainerPrivate step "
+                                               "(BASELINE configs[2])"),
+    "v1_imagenet": dict(net="resnet18", scheme="v1", classes=1000, img=224, batch=256, trigger=False, gflop=10.884,
+                        dtype="bf16", workload="ResNet18 V1 passport ImageNet-1k-shaped Trainer step, 7x7/s2 stem + "
+                                               "max-pool, lr_configs/imagenet.json schedule (BASELINE configs[4])"),
+    "v1_alexnet": dict(net="alexnet", scheme="v1", classes=10, img=32, batch=1024, trigger=False, gflop=1.323,
+                       dtype="bf16", workload="AlexNet V1 passport (features 4/5/6) CIFAR10-shaped Trainer step "
+                                              "(BASELINE configs[1])"),
+}
+DEFAULT_CONFIG = "v3_cifar10_trigger"
+CPU_SAMPLE_BATCH = 256             # images of the per-step batch the CPU arms process (bounded sample, see below)
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return dict(tflops=d.get("bf16_tflops_sustained", 1409.4), hbm=d.get("hbm_gbs", 6437.3), src="measured")
-    return dict(tflops=1590.0, hbm=6650.0, src="fallback")
+        return dict(tflops=d.get("bf16_tflops_sustained", 1393.0), tflops_burst=d.get("bf16_tflops", 1665.0),
+                    hbm=d.get("hbm_gbs", 6540.0), src="measured")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback")
 
 
 class ClockSampler:
@@ -79,82 +103,195 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(num_classes=10, seed=0, blocks=None):
-    import contextlib
-    import io
+def _seed(seed):
     import random
     import numpy as np
     import torch
-    from deepipr_b200 import nets
     torch.manual_seed(seed); random.seed(seed); np.random.seed(seed)
-    pk = nets.passport_kwargs_from_config(nets.resnet18_passport_config(), "bn", "random", 0.1)
+
+
+def build_model(num_classes=None, seed=0, blocks=None, config=None):
+    """The product network of a config (deepipr_b200.nets wiring), passports fixed up front (key_type='random'
+    semantics: U(-1,1), passportconv2d.py:198-207) so the lazily-created-key branch is not in the timed region."""
+    import numpy as np
+    import torch
+    from deepipr_b200 import nets
+    cfg = CONFIGS[config or "v2_cifar10"]
+    classes = num_classes if num_classes is not None else cfg["classes"]
+    _seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):
-        model = nets.ResNet18("private", num_classes, pk)
-    # fixed passports (key_type='random' semantics: U(-1,1), passportconv2d.py:198-207), set up front so the
-    # lazily-created-key branch is not part of the timed region
+        if cfg["net"] == "alexnet":
+            pk = nets.passport_kwargs_from_config(nets.alexnet_passport_config(), "bn", "random", 0.1)
+            model = nets.AlexNetCifar(cfg["scheme"], 3, classes, pk)
+        else:
+            pk = nets.passport_kwargs_from_config(nets.resnet18_passport_config(), "bn", "random", 0.1)
+            model = nets.ResNet18(cfg["scheme"], classes, pk)
+    imagenet = cfg["img"] == 224
     for m in model.modules():
-        if getattr(m, "KIND", None) == "private":
+        if getattr(m, "KIND", None) in ("private", "v1"):
             c = m.conv.in_channels
-            h = 8 if m.conv.stride[0] == 2 else 4
+            if cfg["net"] == "alexnet":
+                h = 8
+            else:
+                wide = cfg["img"] // (16 if imagenet else 4)              # input of layer4.0.convbnrelu_1 / shortcut
+                h = wide if m.conv.stride[0] == 2 else wide // 2
             m.set_key(torch.tensor(np.random.uniform(-1, 1, (1, c, h, h)), dtype=torch.float32),
                       torch.tensor(np.random.uniform(-1, 1, (1, c, h, h)), dtype=torch.float32))
     return model
 
 
-def cpu_reference_run(steps, warmup, batch=CPU_BATCH):
-    """The reference's CPU trainer for this path, as restated by the oracle (oracle/passport_oracle.py):
-    TrainerPrivate.train step on the box's host cores, all threads."""
+def synthetic_batches(cfg, batch, n, device=None, seed=1234):
     import torch
-    from oracle import passport_oracle as po
-    torch.set_num_threads(os.cpu_count() or 1)
-    model = po.mirror(build_model(), round_bf16=False).train()
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
-    g = torch.Generator().manual_seed(1234)
-    x = torch.randn(batch, 3, 32, 32, generator=g)
-    t = torch.randint(0, 10, (batch,), generator=g)
-    for _ in range(warmup):
-        po.train_step(model, opt, x, t, private=True)
+    g = torch.Generator(device=device or "cpu").manual_seed(seed)
+    return [(torch.randn(batch, 3, cfg["img"], cfg["img"], device=device, generator=g),
+             torch.randint(0, cfg["classes"], (batch,), device=device, generator=g)) for _ in range(n)]
+
+
+def trigger_batches(n=50, device=None, seed=4321):
+    """prepare_wm: 100 trigger images, batch 2, CIFAR labels (dataset.py:168-193)."""
+    import torch
+    g = torch.Generator(device=device or "cpu").manual_seed(seed)
+    return [(torch.randn(2, 3, 32, 32, device=device, generator=g), torch.randint(0, 10, (2,), device=device,
+                                                                                  generator=g)) for _ in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# baseline arms: the UNMODIFIED reference (oracle/_ref bundle or checkout), never the product path
+# ------------------------------------------------------------------------------------------------------------------
+def reference_trainer(cfg, device, channels_last=False):
+    """(model, trainer, kind): the reference's own model class, SGD and Trainer / TrainerPrivate
+    (experiments/classification_private.py:48-62), built from its passport_configs/*.json."""
+    import torch
+    from oracle import ref_bundle
+    mods = ref_bundle.import_reference(patched=False)
+    ref = ref_bundle.locate()
+    name = "alexnet_passport.json" if cfg["net"] == "alexnet" else "resnet18_passport.json"
+    pcfg = json.load(open(os.path.join(ref, "passport_configs", name)))
+    pk = mods["experiments.utils"].construct_passport_kwargs_from_dict(
+        {"passport_config": pcfg, "norm_type": "bn", "key_type": "random", "sl_ratio": 0.1})
+    _seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if cfg["net"] == "alexnet":
+            model = mods["models.alexnet_passport"].AlexNetPassport(3, cfg["classes"], pk)
+        elif cfg["scheme"] == "private":
+            model = mods["models.resnet_passport_private"].ResNet18Private(num_classes=cfg["classes"],
+                                                                           passport_kwargs=pk)
+        else:
+            model = mods["models.resnet_passport"].ResNet18Passport(num_classes=cfg["classes"], passport_kwargs=pk)
+    model = model.to(device)
+    if channels_last:
+        model = model.to(memory_format=torch.channels_last)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    if cfg["scheme"] == "private":
+        trainer = mods["experiments.trainer_private"].TrainerPrivate(model, opt, None, device)
+    else:
+        trainer = mods["experiments.trainer"].Trainer(model, opt, None, device)
+    return model, trainer
+
+
+def reference_run(cfg, steps, warmup, device, batch, autocast=False, channels_last=False):
+    """images/s of the reference's own trainer.train() over `steps` minibatches (after `warmup`), on `device`."""
+    import torch
+    model, trainer = reference_trainer(cfg, device, channels_last)
+    data = synthetic_batches(cfg, batch, 4, device=None)
+    if str(device) != "cpu":
+        data = [(x.to(device), t.to(device)) for x, t in data]
+        if channels_last:
+            data = [(x.contiguous(memory_format=torch.channels_last), t) for x, t in data]
+    wm = trigger_batches(8) if cfg["trigger"] else None
+    if wm is not None and str(device) != "cpu":
+        wm = [(x.to(device), t.to(device)) for x, t in wm]
+    ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if autocast else contextlib.nullcontext
+
+    def epoch(n):
+        loader = [data[i % 4] for i in range(n)]
+        with contextlib.redirect_stdout(io.StringIO()), ctx():
+            return trainer.train(0, loader, wm)
+
+    epoch(max(1, warmup))
+    if str(device) != "cpu":
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        po.train_step(model, opt, x, t, private=True)
+    epoch(steps)
+    if str(device) != "cpu":
+        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    return dict(value=steps * batch / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"{steps} TrainerPrivate steps at batch {batch} (reference default), fp32, "
-                       f"{warmup} warm-up, oracle port of experiments/trainer_private.py:148-177"), dt / steps
+    per_step = batch + (2 if cfg["trigger"] else 0)
+    return steps * per_step / dt, dt / steps
 
 
+def cpu_reference_arm(cfg, steps, warmup):
+    import torch
+    from oracle import ref_bundle
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = min(CPU_SAMPLE_BATCH, cfg["batch"]) if cfg["img"] == 32 else 16
+    if ref_bundle.available():
+        value, sec = reference_run(cfg, steps, warmup, torch.device("cpu"), sample)
+        kind, what = "reference", "the unmodified reference (oracle/_ref bundle): its model class, torch.optim.SGD and " \
+                                  "Trainer/TrainerPrivate.train"
+    else:                                    # no bundle on this machine: the oracle port of the same loop
+        from oracle import passport_oracle as po
+        model = po.mirror(build_model(config=_config_name(cfg)), round_bf16=False).train()
+        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        data = synthetic_batches(cfg, sample, 4)
+        for i in range(max(1, warmup)):
+            po.train_step(model, opt, *data[i % 4], private=cfg["scheme"] == "private")
+        t0 = time.perf_counter()
+        for i in range(steps):
+            po.train_step(model, opt, *data[i % 4], private=cfg["scheme"] == "private")
+        sec = (time.perf_counter() - t0) / steps
+        value, kind, what = sample / sec, "port", "oracle port of experiments/trainer_private.py:148-177"
+    return dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind=kind,
+                sample=f"{steps} steps (+{max(1, warmup)} warm-up) of {what}; each step a bounded sample of the "
+                       f"workload's per-step batch: {sample} of {cfg['batch']} images"
+                       f"{' + 2 trigger images' if cfg['trigger'] else ''}, fp32, device=cpu"), sec
+
+
+def _config_name(cfg):
+    return next(k for k, v in CONFIGS.items() if v is cfg)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch")
+    ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=3)
-    ap.add_argument("--legs", default="value,e2e,roofline,shared",
-                    help="comma list of legs: value (always), e2e, roofline, shared, torch_eager")
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--graph", action="store_true", help="run the value / e2e legs through the CUDA-graph step")
+    ap.add_argument("--legs", default="value,e2e,roofline,eager,dropin,small_batch,configs,shared",
+                    help="comma list: value (always), e2e, roofline, eager (the reference on this GPU), dropin (the "
+                         "reference's trainer on the patched blocks), small_batch (batch 64 / 256, eager vs CUDA "
+                         "graph), configs (short lines of the other BASELINE configs), shared (trunk CSE)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = CONFIGS[args.config]
+    B = args.batch or cfg["batch"]
+    per_step = B + (2 if cfg["trigger"] else 0)           # images a rank processes per step
 
-    config = {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1),
-              "parallelism": f"dp{max(world, 1)}", "passport_layers": "layer4 (5 convs)", "norm": "bn",
+    config = {"workload": cfg["workload"], "name": args.config, "per_gpu_batch": B,
+              "trigger_images_per_step_per_gpu": 2 if cfg["trigger"] else 0,
+              "global_batch": per_step * max(world, 1), "parallelism": f"dp{max(world, 1)}",
+              "passport_layers": "features 4/5/6" if cfg["net"] == "alexnet" else "layer4 (5 convs)", "norm": "bn",
+              "classes": cfg["classes"], "image": cfg["img"],
               "optimizer": "SGD(0.01, momentum 0.9, wd 1e-4), fused flat step",
-              "l2": "per-step working set (~7 GB of activations at batch 1184) >> 126 MB L2; no explicit flush"}
+              "l2": "per-step working set (GBs of activations) >> 126 MB L2; 4 rotating input batches; no explicit flush"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
-        cb, sec_per_step = cpu_reference_run(steps, max(1, min(args.warmup, 1)))
+        cb, sec_per_step = cpu_reference_arm(cfg, args.steps, args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": steps, "warmup": 1, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, per_gpu_batch=CPU_BATCH, global_batch=CPU_BATCH, parallelism="cpu"),
-                "cpu_baseline": cb,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -163,7 +300,7 @@ def main():
     import torch.distributed as dist
     from deepipr_b200 import _lib as L
     from deepipr_b200.parallel import FlatParams, FlatSGD, GradBuckets, broadcast_state
-    from deepipr_b200.trainer import StepRunner, accuracy, test_signature
+    from deepipr_b200.trainer import GraphedStepRunner, StepRunner, Trainer, TrainerPrivate, test_signature
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
@@ -171,24 +308,13 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own logging (NCCL_DEBUG=VERSION/INFO on the box prints
-        # "NCCL version ..." there) goes to stderr
+        # stdout carries exactly one JSON line: NCCL's own logging goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
-
-    model = build_model().to(dev).train()
-    broadcast_state(model)
-    flat = FlatParams(model.parameters())
-    opt = FlatSGD(flat, lr=0.01, momentum=0.9, weight_decay=1e-4)
-    buckets = GradBuckets(flat) if world > 1 else None
-    runner = StepRunner(model, opt, private=True, buckets=buckets, autocast=True)
-
-    B = args.batch
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    dev_batches = [(torch.randn(B, 3, 32, 32, device=dev, generator=g),
-                    torch.randint(0, 10, (B,), device=dev, generator=g)) for _ in range(4)]
-    host_batches = [(x.cpu().pin_memory(), t.cpu().pin_memory()) for x, t in dev_batches]
+    legs = set(args.legs.split(","))
+    pk = peaks()
+    private = cfg["scheme"] == "private"
 
     def barrier():
         if world > 1:
@@ -202,9 +328,43 @@ def main():
             return t.item()
         return ms
 
-    # ---------------- leg 1: inputs resident in HBM
+    def make_runner(config_name, batch, graph=False, ddp=True):
+        """model + flat SGD + (graphed) step runner for one config; inputs resident in HBM."""
+        c = CONFIGS[config_name]
+        model = build_model(config=config_name).to(dev).train()
+        if world > 1 and ddp:
+            broadcast_state(model)
+        flat = FlatParams(model.parameters())
+        opt = FlatSGD(flat, lr=0.01, momentum=0.9, weight_decay=1e-4)
+        buckets = GradBuckets(flat) if (world > 1 and ddp) else None
+        runner = StepRunner(model, opt, private=c["scheme"] == "private", buckets=buckets, autocast=True)
+        data = synthetic_batches(c, batch, 4, device=dev, seed=1234 + rank)
+        if c["trigger"]:
+            wm = trigger_batches(4, device=dev, seed=4321 + rank)
+            data = [(torch.cat([x, wm[i][0]]), torch.cat([t, wm[i][1]])) for i, (x, t) in enumerate(data)]
+        step = runner.step
+        if graph:
+            graphed = GraphedStepRunner(runner, *data[0])
+            step = graphed.step
+        return model, opt, runner, data, step
+
+    def timed(step, data, steps, warmup):
+        for i in range(warmup):
+            step(*data[i % len(data)])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(*data[i % len(data)])
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---------------- leg 1 (`value`): inputs resident in HBM
+    use_graph = args.graph and world == 1
+    model, opt, runner, dev_batches, step = make_runner(args.config, B, graph=use_graph)
     for i in range(args.warmup):
-        runner.step(*dev_batches[i % 4])
+        step(*dev_batches[i % 4])
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -213,214 +373,281 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        runner.step(*dev_batches[i % 4])
+        step(*dev_batches[i % 4])
     e1.record()
     barrier()
     launches = int(lib.pp_launch_count(0))
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    value = args.steps * B * world / (ms_total * 1e-3)
+    value = args.steps * per_step * world / (ms_total * 1e-3)
+    if use_graph:       # a replay launches the captured kernels without passing through the library's counter
+        launches = None
 
-    legs = set(args.legs.split(","))
-
-    # ---------------- leg 2: end to end through the public step API with host (pinned) buffers
-    # Inputs come from pinned host memory every step; the copy of step i+1 is issued on a side stream while step i
-    # computes (what DataLoader(pin_memory=True) + .to(device, non_blocking=True) gives the reference loop,
-    # trainer_private.py:149-151), so all K copies are inside the timed region but off the critical path.
-    copy_stream = torch.cuda.Stream(device=dev)
-
-    def prefetch(i):
-        x, t = host_batches[i % 4]
-        with torch.cuda.stream(copy_stream):
-            xd = x.to(dev, non_blocking=True)
-            td = t.to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return xd, td, ev
-
-    def e2e_loop(n):
-        out = (None,) * 4
-        nxt = prefetch(0)
-        for i in range(n):
-            xd, td, ev = nxt
-            main = torch.cuda.current_stream()
-            main.wait_event(ev)
-            xd.record_stream(main)
-            td.record_stream(main)
-            if i + 1 < n:
-                nxt = prefetch(i + 1)
-            loss, sign_loss, preds = runner.step(xd, td)
-            # the reference loop's host reads: two accuracies + loss + sign loss (trainer_private.py:163-177)
-            out = (accuracy(preds[0], td)[0].item(), accuracy(preds[1], td)[0].item(), sign_loss.item(), loss.item())
-        return out
-
-    last = (None,) * 4
-    ms_e2e, e2e_value = None, None
+    # ---------------- leg 2 (`e2e`): the public trainer API on HOST buffers.  deepipr_b200.trainer.TrainerPrivate.train
+    # (the call a user makes, same signature as experiments/trainer_private.py:118) over a loader of pinned host
+    # batches + the trigger-set loader: every step copies its inputs host->device (prefetched on a side stream, as
+    # DataLoader(pin_memory=True) + .to(non_blocking=True) allows) and reads the step's metrics back (16 bytes).
+    ms_e2e, e2e_value, last = None, None, None
+    trainer_cls = TrainerPrivate if private else Trainer
+    host = synthetic_batches(cfg, B, 4, device=None, seed=1234 + rank)
+    host = [(x.pin_memory(), t.pin_memory()) for x, t in host]
+    wm_host = [(x.pin_memory(), t.pin_memory()) for x, t in trigger_batches(8, seed=4321 + rank)] \
+        if cfg["trigger"] else None
+    h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8 + \
+        ((wm_host[0][0].numel() * 4 + wm_host[0][1].numel() * 8) if wm_host else 0)
     if "e2e" in legs:
-        e2e_loop(max(3, args.warmup // 2))
+        trainer = trainer_cls(model, opt, None, dev, buckets=runner.buckets, autocast=True, use_graph=use_graph)
+        trainer.log_every = 1
+        seen = []
+        trainer.on_log = lambda n, vals: seen.append(vals)
+        trainer.train(0, [host[i % 4] for i in range(max(3, args.warmup // 2))], wm_host)
         barrier()
         e0.record()
-        last = e2e_loop(args.steps)
+        trainer.train(1, [host[i % 4] for i in range(args.steps)], wm_host)
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-        e2e_value = args.steps * B * world / (ms_e2e * 1e-3)
-    h2d = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 8
+        e2e_value = args.steps * per_step * world / (ms_e2e * 1e-3)
+        n = len(seen)
+        last = {"loss": seen[-1][0] / args.steps, "sign_loss_sum": seen[-1][1], "acc_pass0": seen[-1][2] / args.steps,
+                "acc_pass1": seen[-1][3] / args.steps, "metric_reads": n}
     d2h = 4 * 4
 
-    # ---------------- leg 3: per-kernel roofline of the dominant kernel (CUDA events on its stream)
-    roof = None
-    roof_w = None
-    roof_hbm = None
-    if "roofline" in legs:
-        # every rank runs the steps (they contain the gradient all-reduce); only rank 0 records kernel events
+    # ---------------- leg 3 (`roofline`): per-kernel CUDA-event timing on the kernels' own stream
+    roof = roof_w = roof_hbm = roof_fused = None
+    if "roofline" in legs and not use_graph:
         if rank == 0:
             lib.pp_profile_enable(1)
         for i in range(3):
             runner.step(*dev_batches[i % 4])
         barrier()
         lib.pp_profile_enable(0)
-    if rank == 0 and "roofline" in legs:
-        pk = peaks()
+    if rank == 0 and "roofline" in legs and not use_graph:
         def read(kind, c=0, nout=0, taps=0):
             ms, fl, n = C.c_double(0), C.c_double(0), C.c_int(0)
             lib.pp_profile_read(kind, c, nout, taps, C.byref(ms), C.byref(fl), C.byref(n))
             return ms.value, fl.value, n.value
 
+        traffic_file = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+        ncu_traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
+        step_ms = ms_total / args.steps
         (ms0, fl0, n0), (ms1, fl1, n1) = read(0), read(1)
-        msp, flp, npl = read(0, 512, 512, 9)      # the 3x3 512->512 passport convs of layer4 (fprop + dgrad)
         if ms0 > 0:
             ach = fl0 / (ms0 * 1e-3) / 1e12
-            roof = {"kernel": "tapgemm_kernel (tcgen05 implicit-GEMM conv fprop+dgrad)", "bound": "tensor",
-                    "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                    "peak_source": pk["src"] + " bf16 sustained", "traffic": None,
+            roof = {"kernel": "pxn_kernel + tapgemm_kernel (tcgen05 implicit-GEMM conv, fprop + dgrad launches)",
+                    "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tflops"], "peak_source": pk["src"] + " bf16 sustained (kernel timed inside a step)",
+                    "traffic": ncu_traffic.get("tapgemm_total_bytes_per_launch"),
+                    "traffic_source": ncu_traffic.get("source"),
                     "launches_per_step": n0 // 3, "avg_launch_us": ms0 * 1e3 / max(n0, 1),
-                    "share_of_step": (ms0 / 3) / (ms_total / args.steps)}
+                    "share_of_step": (ms0 / 3) / step_ms}
+        msp, flp, npl = read(0, 512, 512, 9)      # the 3x3 512->512 passport convs of layer4 (fprop + dgrad)
         if msp > 0 and roof is not None:
             ach = flp / (msp * 1e-3) / 1e12
-            # traffic: dram__bytes_read+write per launch from the ncu --set full capture of this geometry at batch
-            # 1184 (profiles/r1b_ncu_layer4_batch1184.txt: fprop 24.17 + 0.51 MB, dgrad 24.17 MB), scaled to this
-            # batch; algorithmic = x + W bytes (the fp32 z / bf16 dx tile stays in the 126 MB L2 for the next pass)
-            roof["passport_layer"] = {"geometry": "layer4 3x3 512->512 @4x4, fprop+dgrad launches", "achieved": ach,
+            roof["passport_layer"] = {"geometry": "layer4 3x3 512->512, fprop+dgrad launches", "achieved": ach,
                                       "frac": ach / pk["tflops"], "launches_per_step": npl // 3,
                                       "avg_launch_us": msp * 1e3 / max(npl, 1),
-                                      "traffic": 24.42e6 * B / 1184.0,
-                                      "algorithmic_bytes": 2.0 * (B * 16 * 512 + 512 * 4608)}
-        # the HBM-bound passes of the block: algorithmic bytes / CUDA-event time
+                                      "algorithmic_bytes": 2.0 * (per_step * 16 * 512 + 512 * 4608),
+                                      "traffic": ncu_traffic.get("passport_layer_bytes_per_launch")}
+        msf, flf, nf = read(5)
+        if msf > 0:
+            ach = flf / (msf * 1e-3) / 1e12
+            roof_fused = {"kernel": "passport_fused_kernel (conv + batch statistics + grid barrier + gamma/beta affine + "
+                                    "ReLU from TMEM, one launch per passport block forward)", "bound": "tensor",
+                          "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                          "launches_per_step": nf // 3, "avg_launch_us": msf * 1e3 / max(nf, 1),
+                          "share_of_step": (msf / 3) / step_ms,
+                          "traffic": ncu_traffic.get("passport_fused_bytes_per_launch")}
         hbm_parts, tot_ms, tot_b = {}, 0.0, 0.0
         for kind, name in ((2, "affine_apply (z->y)"), (3, "bwd reduce (dy,z)"), (4, "bwd dz (dy,z->dz)")):
             msk, byk, nk = read(kind)
             if msk > 0:
                 hbm_parts[name] = {"achieved": byk / (msk * 1e-3) / 1e9, "launches_per_step": nk // 3,
-                                   "avg_launch_us": msk * 1e3 / max(nk, 1),
-                                   "share_of_step": (msk / 3) / (ms_total / args.steps)}
+                                   "avg_launch_us": msk * 1e3 / max(nk, 1), "share_of_step": (msk / 3) / step_ms}
                 tot_ms += msk
                 tot_b += byk
         if tot_ms > 0:
             ach = tot_b / (tot_ms * 1e-3) / 1e9
             roof_hbm = {"kernel": "affine_apply + column_reduce<1> + bwd_dz (norm/affine/ReLU passes)", "bound": "hbm",
                         "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                        "peak_source": pk["src"] + " copy bandwidth",
-                        # dram bytes per launch at the layer1 geometry, batch 1184 (profiles/r1b_ncu_layer1_pointwise.txt)
-                        "traffic": {"geometry": "layer1 64ch 32x32, batch 1184",
-                                    "affine_apply": 421.5e6, "bwd_reduce": 469.4e6, "bwd_dz": 599.1e6,
-                                    "algorithmic": {"affine_apply": 465.6e6, "bwd_reduce": 465.6e6,
-                                                    "bwd_dz": 620.8e6}},
-                        "share_of_step": (tot_ms / 3) / (ms_total / args.steps), "per_kernel": hbm_parts,
-                        "note": "small layers (layer3/4) re-read z/dy from the 126 MB L2, so a per-kernel figure can "
-                                "exceed the HBM peak; the aggregate is dominated by layer1/2"}
+                        "peak_source": pk["src"] + " copy bandwidth", "traffic": ncu_traffic.get("hbm_passes"),
+                        "traffic_source": ncu_traffic.get("source"),
+                        "share_of_step": (tot_ms / 3) / step_ms, "per_kernel": hbm_parts,
+                        "note": "algorithmic bytes as launched (fp32 z); small layers (layer3/4) re-read z/dy from the "
+                                "126 MB L2, so a per-kernel figure can exceed the HBM peak"}
         if ms1 > 0:
             ach = fl1 / (ms1 * 1e-3) / 1e12
-            roof_w = {"kernel": "wgrad_kernel (tcgen05, MN-major)", "bound": "tensor", "achieved": ach,
+            roof_w = {"kernel": "wgrad_kernel / wgrad_om_kernel (tcgen05, MN-major)", "bound": "tensor", "achieved": ach,
                       "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                       "launches_per_step": n1 // 3, "avg_launch_us": ms1 * 1e3 / max(n1, 1),
-                      "share_of_step": (ms1 / 3) / (ms_total / args.steps)}
+                      "share_of_step": (ms1 / 3) / step_ms}
 
-    # ---------------- optional leg: the same step in stock PyTorch eager (cuDNN/cuBLAS, autocast bf16,
-    # channels_last) on this GPU — the oracle mirror moved to the device.  Informational only ("the honest bar",
-    # BASELINE.md §3a); not part of the default run.
-    torch_eager = None
-    if rank == 0 and "torch_eager" in legs:
-        import torch.nn.functional as TF
-        from oracle import passport_oracle as po
-        torch.backends.cudnn.benchmark = True                      # train_v1.py:8 / train_v23.py:8
-        ref = po.mirror(build_model(), round_bf16=False).to(dev).to(memory_format=torch.channels_last).train()
-        ropt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
-        rlosses = po.sign_loss_modules(ref)
-
-        def ref_step(x, t):
-            ropt.zero_grad()
-            for m in rlosses:
-                m.reset()
-            loss = torch.zeros((), device=dev)
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                for ind in range(2):
-                    loss = loss + TF.cross_entropy(ref(x, ind=ind).float(), t)
-            sl = torch.zeros((), device=dev)
-            for m in rlosses:
-                sl = sl + m.loss
-            (loss + sl).backward()
-            ropt.step()
-
-        xs = [(x.contiguous(memory_format=torch.channels_last), t) for x, t in dev_batches]
-        for i in range(max(3, args.warmup)):
-            ref_step(*xs[i % 4])
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(args.steps):
-            ref_step(*xs[i % 4])
-        e1.record()
-        torch.cuda.synchronize()
-        ms_ref = e0.elapsed_time(e1)
-        torch_eager = {"value": args.steps * B / (ms_ref * 1e-3), "unit": UNIT, "ms_per_step": ms_ref / args.steps,
-                       "what": "oracle mirror on cuda: torch eager + cuDNN, autocast bf16, channels_last, "
-                               "cudnn.benchmark, torch.optim.SGD(foreach); same batch, inputs resident"}
-        del ref, ropt
-
-    # ---------------- optional extra: the same step with the public/private passes sharing the passport-free
-    # trunk (nets.ResNet18.share_trunk, identical results up to summation order).  Reported separately; `value`
-    # above always executes both full passes like the reference does.
+    # ---------------- optional: public/private passes share the passport-free trunk (reported separately)
     shared = None
-    if "shared" in legs:
+    if "shared" in legs and private and cfg["net"] == "resnet18" and not use_graph:
         model.share_trunk = True
-        for i in range(3):
-            runner.step(*dev_batches[i % 4])
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            runner.step(*dev_batches[i % 4])
-        e1.record()
-        barrier()
-        ms_sh = max_over_ranks(e0.elapsed_time(e1))
-        shared = {"value": args.steps * B * world / (ms_sh * 1e-3), "unit": UNIT, "ms_per_step": ms_sh / args.steps,
+        ms_sh = timed(runner.step, dev_batches, max(5, args.steps // 2), 3)
+        n_sh = max(5, args.steps // 2)
+        shared = {"value": n_sh * per_step * world / (ms_sh * 1e-3), "unit": UNIT, "ms_per_step": ms_sh / n_sh,
                   "what": "public+private passes share the stem..layer3 forward/backward (common-subexpression "
-                          "elimination across the two model calls of trainer_private.py:159-161)"}
+                          "elimination across the two model calls of trainer_private.py:159-161); opt-in, not `value`"}
         model.share_trunk = False
 
     sig = test_signature(model) if rank == 0 else {}
     model.train()
+    del model, opt, runner, dev_batches, step
+    torch.cuda.empty_cache()
+
+    # ---------------- the other BASELINE configs, short lines (N=1 only; the scaling run repeats the default config)
+    configs_out = None
+    if "configs" in legs and world == 1:
+        configs_out = {}
+        for name in ("v2_cifar100", "v1_imagenet", "v1_alexnet"):
+            if name == args.config:
+                continue
+            c = CONFIGS[name]
+            try:
+                m2, o2, r2, d2, s2 = make_runner(name, c["batch"], ddp=False)
+                n2 = 8
+                ms2 = timed(s2, d2, n2, 3)
+                v2 = n2 * c["batch"] / (ms2 * 1e-3)
+                configs_out[name] = {"value": v2, "unit": UNIT, "ms_per_step": ms2 / n2, "per_gpu_batch": c["batch"],
+                                     "dtype": c["dtype"], "workload": c["workload"],
+                                     "conv_roofline_frac_whole_step": v2 * c["gflop"] * 1e9 / (pk["tflops"] * 1e12)}
+                del m2, o2, r2, d2, s2
+            except Exception as e:          # a config must not take the headline line down with it
+                configs_out[name] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+
+    # ---------------- throughput at the reference's own batch sizes (64: train_v1.py:15, 256: training.sh:4):
+    # ~650 launches per step make the eager step host-bound there; the CUDA-graph replay is the fix
+    small = None
+    if "small_batch" in legs and world == 1:
+        small = {}
+        for b in (64, 256):
+            row = {}
+            for mode in ("eager", "graph"):
+                try:
+                    m2, o2, r2, d2, s2 = make_runner(args.config, b, graph=(mode == "graph"), ddp=False)
+                    n2 = 20
+                    ms2 = timed(s2, d2, n2, 5)
+                    row[mode] = {"value": n2 * (b + (2 if cfg["trigger"] else 0)) / (ms2 * 1e-3), "unit": UNIT,
+                                 "ms_per_step": ms2 / n2}
+                    del m2, o2, r2, d2, s2
+                except Exception as e:
+                    row[mode] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
+            small[f"batch_{b}"] = row
+
+    # ---------------- the reference itself on this GPU (stock PyTorch eager + cuDNN): "the honest bar"
+    eager = None
+    multi_dev = torch.cuda.device_count() > 1     # the reference trainers wrap nn.DataParallel when they see >1 GPU
+    if rank == 0 and world == 1 and "eager" in legs:
+        from oracle import ref_bundle
+        if multi_dev:
+            eager = {"skipped": "more than one CUDA device visible: the reference would switch to nn.DataParallel"}
+        elif ref_bundle.available():
+            eager = {}
+            torch.backends.cudnn.benchmark = True                      # train_v1.py:8 / train_v23.py:8
+            for tag, kw in (("fp32_as_shipped", dict()),
+                            ("autocast_bf16_channels_last", dict(autocast=True, channels_last=True))):
+                try:
+                    n2 = max(3, min(args.steps, 6))
+                    v, sec = reference_run(cfg, n2, 2, dev, B, **kw)
+                    eager[tag] = {"value": v, "unit": UNIT, "ms_per_step": sec * 1e3, "steps": n2}
+                except Exception as e:
+                    eager[tag] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
+            eager["what"] = ("the UNMODIFIED reference (oracle/_ref bundle): its ResNet18Private, torch.optim.SGD and "
+                             "TrainerPrivate.train on cuda, same per-GPU batch, inputs resident; fp32_as_shipped = what "
+                             "`python train_v23.py` does (cuDNN TF32 convs by torch default); the second row wraps the "
+                             "same call in torch.autocast(bf16) with a channels_last model")
+        else:
+            eager = {"unavailable": "no reference bundle (oracle/_ref) on this machine"}
+
+    # ---------------- drop-in route: the reference's OWN TrainerPrivate + model files on the patched blocks
+    dropin = None
+    if rank == 0 and world == 1 and "dropin" in legs and not multi_dev:
+        from oracle import ref_bundle
+        if ref_bundle.available():
+            try:
+                dropin = dropin_run(cfg, B, dev, max(3, min(args.steps, 6)))
+            except Exception as e:
+                dropin = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and "e2e" in legs:
-        cpu_baseline, _ = cpu_reference_run(args.cpu_steps, 1)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_reference_arm(cfg, args.cpu_steps, 1)
 
     if rank == 0:
-        pk = peaks()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+                "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic", "config": config,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": (ms_e2e / args.steps) if ms_e2e else None},
-                "gpu_launches": launches,
-                "roofline": roof, "roofline_wgrad": roof_w, "roofline_hbm": roof_hbm,
-                "conv_roofline_frac_whole_step": (value / world) * GFLOP_PER_IMAGE_STEP * 1e9 / (pk["tflops"] * 1e12),
-                "cpu_baseline": cpu_baseline, "torch_eager_gpu": torch_eager, "value_shared_trunk": shared,
-                "sign_bit_accuracy": (sum(sig.values()) / len(sig)) if sig else None,
-                "last_step": {"acc_public": last[0], "acc_private": last[1], "sign_loss": last[2], "loss": last[3]}}
+                        "ms_per_step": (ms_e2e / args.steps) if ms_e2e else None,
+                        "api": "deepipr_b200.trainer.TrainerPrivate.train(epoch, loader of pinned host batches, "
+                               "trigger loader)"},
+                "gpu_launches": launches, "cuda_graph": use_graph,
+                "roofline": roof, "roofline_passport_fused": roof_fused, "roofline_wgrad": roof_w,
+                "roofline_hbm": roof_hbm,
+                "conv_roofline_frac_whole_step": (value / world) * cfg["gflop"] * 1e9 / (pk["tflops"] * 1e12),
+                "cpu_baseline": cpu_baseline, "torch_eager_gpu": eager, "reference_trainer_on_patched_blocks": dropin,
+                "small_batch": small, "configs": configs_out, "value_shared_trunk": shared,
+                "sign_bit_accuracy": (sum(sig.values()) / len(sig)) if sig else None, "last_step": last}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def dropin_run(cfg, B, dev, steps):
+    """INTEGRATION.md route A, timed: deepipr_b200.patch_reference(), then the reference's own model file and
+    TrainerPrivate.train (its loop, its F.cross_entropy / accuracy / .item() reads, torch.optim.SGD) drive the CUDA
+    path; wrapped in torch.autocast(bf16) so the blocks exchange bf16 activations."""
+    import torch
+    from deepipr_b200 import _lib as L
+    from oracle import ref_bundle
+    mods = ref_bundle.import_reference(patched=True)
+    ref = ref_bundle.locate()
+    name = "alexnet_passport.json" if cfg["net"] == "alexnet" else "resnet18_passport.json"
+    pcfg = json.load(open(os.path.join(ref, "passport_configs", name)))
+    pkw = mods["experiments.utils"].construct_passport_kwargs_from_dict(
+        {"passport_config": pcfg, "norm_type": "bn", "key_type": "random", "sl_ratio": 0.1})
+    _seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        if cfg["net"] == "alexnet":
+            model = mods["models.alexnet_passport"].AlexNetPassport(3, cfg["classes"], pkw)
+        elif cfg["scheme"] == "private":
+            model = mods["models.resnet_passport_private"].ResNet18Private(num_classes=cfg["classes"],
+                                                                           passport_kwargs=pkw)
+        else:
+            model = mods["models.resnet_passport"].ResNet18Passport(num_classes=cfg["classes"], passport_kwargs=pkw)
+    model = model.to(dev)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
+    tcls = mods["experiments.trainer_private"].TrainerPrivate if cfg["scheme"] == "private" \
+        else mods["experiments.trainer"].Trainer
+    trainer = tcls(model, opt, None, dev)
+    data = synthetic_batches(cfg, B, 4, device=dev)
+    wm = trigger_batches(8, device=dev) if cfg["trigger"] else None
+
+    def epoch(n):
+        with contextlib.redirect_stdout(io.StringIO()), torch.autocast("cuda", dtype=torch.bfloat16):
+            return trainer.train(0, [data[i % 4] for i in range(n)], wm)
+
+    epoch(2)
+    torch.cuda.synchronize()
+    L.load().pp_launch_count(1)
+    t0 = time.perf_counter()
+    res = epoch(steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    per_step = B + (2 if cfg["trigger"] else 0)
+    return {"value": steps * per_step / dt, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "steps": steps,
+            "library_launches": int(L.load().pp_launch_count(0)), "train_metrics": {k: float(v) for k, v in res.items()},
+            "what": "deepipr_b200.patch_reference(); the reference's models/resnet_passport_private.py + "
+                    "experiments/trainer_private.py TrainerPrivate.train + torch.optim.SGD, unchanged, under "
+                    "torch.autocast(bf16)"}
 
 
 if __name__ == "__main__":

@@ -10,7 +10,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpassport_sm100.so")
 
-PP_ABI_VERSION = 10
+PP_ABI_VERSION = 11
 PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL, PP_NORM_GN = 0, 1, 2, 3
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1
@@ -23,6 +23,7 @@ EXPORTS = (
     "pp_conv_block_fwd", "pp_conv_block_bwd", "pp_conv_fwd_raw", "pp_conv_dgrad", "pp_conv_wgrad",
     "pp_sgd_step", "pp_debug_last_timeout", "pp_launch_count", "pp_profile_enable", "pp_profile_read",
     "pp_add_relu_fwd", "pp_add_relu_bwd", "pp_passport_key_grad", "pp_signature_verify",
+    "pp_sgd_step_dev", "pp_ce_top1",
 )
 
 
@@ -71,6 +72,8 @@ _PROTOS = {
     "pp_conv_dgrad": (C.c_int, [_desc, _vp, _vp, _vp, _vp]),
     "pp_conv_wgrad": (C.c_int, [_desc, _vp, _vp, _fp, _vp, _sz, _vp]),
     "pp_sgd_step": (C.c_int, [_sz, _fp, _fp, _fp, _f, _f, _f, _i, _vp]),
+    "pp_sgd_step_dev": (C.c_int, [_sz, _fp, _fp, _fp, _fp, _vp]),
+    "pp_ce_top1": (C.c_int, [_i, _i, _vp, _i, _vp, _fp, _fp, _fp, _i, _vp]),
     "pp_add_relu_fwd": (C.c_int, [_sz, _vp, _vp, _vp, _vp]),
     "pp_add_relu_bwd": (C.c_int, [_sz, _vp, _vp, _vp, _vp]),
     "pp_debug_last_timeout": (C.c_int, []),

@@ -627,6 +627,23 @@ int pp_sgd_step(size_t n, float* param, const float* grad, float* momentum_buf, 
   return launch_sgd(n, param, grad, momentum_buf, lr, momentum, weight_decay, first_step, (cudaStream_t)stream);
 }
 
+int pp_sgd_step_dev(size_t n, float* param, const float* grad, float* momentum_buf, const float* hyper,
+                    void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(param && grad && momentum_buf && hyper, PP_EBADARG, "sgd (device hyper-parameters): NULL pointer");
+  if (n == 0) return PP_OK;
+  return launch_sgd_dev(n, param, grad, momentum_buf, hyper, (cudaStream_t)stream);
+}
+
+int pp_ce_top1(int N, int classes, const void* logits, int logits_bf16, const int64_t* target, float* loss,
+               float* top1, float* dlogits, int accumulate, void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(N > 0 && classes > 0, PP_EBADSHAPE, "ce_top1: N=%d classes=%d", N, classes);
+  PP_REQUIRE(logits && target && (loss || top1 || dlogits), PP_EBADARG, "ce_top1: NULL pointer");
+  return launch_ce_top1(N, classes, logits, logits_bf16, (const long long*)target, loss, top1, dlogits, accumulate,
+                        (cudaStream_t)stream);
+}
+
 int pp_add_relu_fwd(size_t n, const void* a, const void* b, void* y, void* stream) {
   PP_TRY(check_device());
   PP_REQUIRE(a && b && y, PP_EBADARG, "add_relu: NULL pointer");

@@ -182,5 +182,8 @@ int launch_gn_dz(const PPConvDesc& d, int HW, const __nv_bfloat16* dy, const voi
                  cudaStream_t s);
 int launch_sgd(size_t n, float* p, const float* g, float* buf, float lr, float mom, float wd, int first,
                cudaStream_t s);
+int launch_sgd_dev(size_t n, float* p, const float* g, float* buf, const float* hyper, cudaStream_t s);
+int launch_ce_top1(int N, int classes, const void* logits, int logits_bf16, const long long* target, float* loss,
+                   float* top1, float* dlogits, int accumulate, cudaStream_t s);
 
 }  // namespace pp

@@ -1094,4 +1094,105 @@ int launch_sgd(size_t n, float* p, const float* g, float* buf, float lr, float m
   return PP_OK;
 }
 
+// Same update with the hyper-parameters read from device memory: hyper = {lr, momentum, weight decay, first step}.
+// A CUDA-graph-captured training step bakes kernel ARGUMENTS into the graph; a learning-rate schedule or the
+// first-step flag then only needs a 16-byte copy into `hyper` before the replay, not a re-capture.
+__global__ void sgd_dev_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                               const float* __restrict__ hyper) {
+  const float lr = hyper[0], mom = hyper[1], wd = hyper[2];
+  const bool first = hyper[3] != 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float w = p[i];
+    float d = g[i] + wd * w;
+    if (mom != 0.0f) {
+      const float m = first ? d : mom * buf[i] + d;
+      buf[i] = m;
+      d = m;
+    }
+    p[i] = w - lr * d;
+  }
+}
+
+int launch_sgd_dev(size_t n, float* p, const float* g, float* buf, const float* hyper, cudaStream_t s) {
+  sgd_dev_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, s>>>(n, p, g, buf, hyper);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-entropy (mean over the batch) + precision@1 + the gradient of the mean loss w.r.t. the logits, one launch
+// (experiments/trainer_private.py:161-168, trainer.py:28-43,139-142: F.cross_entropy(pred, target) and
+// accuracy(pred, target)[0] — two softmax kernels, a topk, a transpose/compare/sum chain and their backward in eager).
+// One block; a warp per row, lanes over classes; per-warp partials are combined in a fixed order (deterministic).
+//   metrics[0] (+)= mean_n(logsumexp(l[n,:]) - l[n,t[n]])      metrics[1] (+)= 100/N * #{n: argmax_c l[n,c] == t[n]}
+//   dlogits[n,c]   = (softmax(l[n,:])[c] - [c == t[n]]) / N
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(1024) ce_top1_kernel(int N, int Ccls, const void* __restrict__ logits,
+                                                       const long long* __restrict__ target,
+                                                       float* __restrict__ loss_out, float* __restrict__ top1_out,
+                                                       float* __restrict__ dlogits, int accumulate) {
+  __shared__ double s_loss[32];
+  __shared__ int s_hit[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  double loss = 0.0;
+  int hits = 0;
+  const float invN = 1.0f / (float)N;
+  for (int n = warp; n < N; n += nwarps) {
+    const size_t base = (size_t)n * Ccls;
+    auto ld = [&](int c) -> float {
+      if (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(logits)[base + c]);
+      return reinterpret_cast<const float*>(logits)[base + c];
+    };
+    float mx = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int c = lane; c < Ccls; c += 32) {
+      const float v = ld(c);
+      if (v > mx) { mx = v; arg = c; }          // first maximum within the lane's strided walk
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, off);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+      if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }     // ties: lowest class index
+    }
+    float sum = 0.0f;
+    for (int c = lane; c < Ccls; c += 32) sum += __expf(ld(c) - mx);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    const int t = (int)target[n];
+    const float lse = mx + logf(sum);
+    if (dlogits) {
+      const float inv = invN / sum;
+      for (int c = lane; c < Ccls; c += 32)
+        dlogits[base + c] = __expf(ld(c) - mx) * inv - (c == t ? invN : 0.0f);
+    }
+    if (lane == 0) {
+      loss += (double)(lse - ld(t));
+      hits += (arg == t) ? 1 : 0;
+    }
+  }
+  if (lane == 0) { s_loss[warp] = loss; s_hit[warp] = hits; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = 0.0;
+    int h = 0;
+    for (int w = 0; w < nwarps; ++w) { l += s_loss[w]; h += s_hit[w]; }
+    const float lm = (float)(l / (double)N);
+    const float acc = 100.0f * (float)h / (float)N;
+    if (loss_out) *loss_out = accumulate ? *loss_out + lm : lm;
+    if (top1_out) *top1_out = accumulate ? *top1_out + acc : acc;
+  }
+}
+
+int launch_ce_top1(int N, int classes, const void* logits, int logits_bf16, const long long* target, float* loss,
+                   float* top1, float* dlogits, int accumulate, cudaStream_t s) {
+  if (logits_bf16)
+    ce_top1_kernel<true><<<1, 1024, 0, s>>>(N, classes, logits, target, loss, top1, dlogits, accumulate);
+  else
+    ce_top1_kernel<false><<<1, 1024, 0, s>>>(N, classes, logits, target, loss, top1, dlogits, accumulate);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
 }  // namespace pp

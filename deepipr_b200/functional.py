@@ -295,6 +295,44 @@ def sign_loss(scale, b, alpha):
     return _SignLossFn.apply(scale, b, alpha)
 
 
+class _CeTop1Fn(torch.autograd.Function):
+    """F.cross_entropy(pred, target) + accuracy(pred, target)[0] and the logits gradient in one launch
+    (experiments/trainer_private.py:161-168, experiments/trainer.py:28-43)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        lg = logits.detach()
+        if lg.dtype not in (torch.float32, torch.bfloat16):
+            lg = lg.float()
+        lg = lg.contiguous()
+        tg = target.detach().to(torch.int64).contiguous()
+        N, classes = lg.shape
+        out = torch.empty(2, dtype=torch.float32, device=lg.device)
+        need = ctx.needs_input_grad[0]
+        dl = torch.empty((N, classes), dtype=torch.float32, device=lg.device) if need else None
+        L.check(L.load().pp_ce_top1(int(N), int(classes), L.ptr(lg), int(lg.dtype == torch.bfloat16), L.ptr(tg),
+                                    C.c_void_p(out.data_ptr()), C.c_void_p(out.data_ptr() + 4), L.ptr(dl), 0,
+                                    _stream()), "pp_ce_top1")
+        ctx.save_for_backward(dl)
+        ctx.dtype = logits.dtype
+        loss, top1 = out[0], out[1]
+        ctx.mark_non_differentiable(top1)
+        return loss, top1
+
+    @staticmethod
+    def backward(ctx, g_loss, g_top1=None):
+        (dl,) = ctx.saved_tensors
+        return (dl * g_loss).to(ctx.dtype), None
+
+
+def ce_top1(logits, target):
+    """(mean cross-entropy, precision@1 in percent) of [N, classes] logits — one fused kernel, no host read."""
+    require_cuda(logits, "logits")
+    if logits.dim() != 2:
+        raise RuntimeError(f"ce_top1 expects [N, classes] logits, got {tuple(logits.shape)}")
+    return _CeTop1Fn.apply(logits, target)
+
+
 @dataclass
 class BlockOpts:
     spec: ConvSpec

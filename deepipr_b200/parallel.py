@@ -261,6 +261,27 @@ class FlatSGD(torch.optim.Optimizer):
         super().__init__(flat.params, defaults)
         self._buf = torch.zeros_like(flat.flat)
         self._steps = 0
+        # optional: hyper-parameters in device memory, so that a CUDA-graph replay of step() follows lr schedules
+        self._hyper = None
+        self._hyper_host = None
+
+    def use_device_hyper(self, on=True):
+        """step() reads {lr, momentum, weight_decay, first-step flag} from a device buffer (pp_sgd_step_dev)."""
+        if on and self._hyper is None:
+            self._hyper = torch.zeros(4, dtype=torch.float32, device=self.flat.flat.device)
+            self._hyper_host = None
+        if not on:
+            self._hyper = None
+
+    def sync_hyper(self):
+        """Refresh the device copy of the hyper-parameters if they changed (16-byte copy; call before a replay)."""
+        if self._hyper is None:
+            return
+        g = self.param_groups[0]
+        vals = (float(g['lr']), float(g['momentum']), float(g['weight_decay']), float(self._steps == 0))
+        if vals != self._hyper_host:
+            self._hyper.copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=False)
+            self._hyper_host = vals
 
     def add_param_group(self, param_group):
         if getattr(self, "param_groups", None):
@@ -299,6 +320,15 @@ class FlatSGD(torch.optim.Optimizer):
         if len(self.param_groups) != 1:
             raise ValueError("FlatSGD supports exactly one param group")
         g = self.param_groups[0]
+        if self._hyper is not None:
+            if not torch.cuda.is_current_stream_capturing():
+                self.sync_hyper()
+            L.check(L.load().pp_sgd_step_dev(
+                C.c_size_t(self.flat.numel), L.ptr(self.flat.flat), L.ptr(self.flat.flat_grad), L.ptr(self._buf),
+                L.ptr(self._hyper), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pp_sgd_step_dev")
+            self._steps += 1
+            F_.bump_weight_epoch()
+            return loss
         L.check(L.load().pp_sgd_step(
             C.c_size_t(self.flat.numel), L.ptr(self.flat.flat), L.ptr(self.flat.flat_grad), L.ptr(self._buf),
             float(g['lr']), float(g['momentum']), float(g['weight_decay']), int(self._steps == 0),

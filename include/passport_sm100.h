@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 10
+#define PP_ABI_VERSION 11
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -191,6 +191,23 @@ int pp_add_relu_bwd(size_t n, const void* gy, const void* y, void* gx, void* str
  *   g' = g + wd*p;  buf = mom*buf + g' (buf = g' on the first step);  p -= lr*buf */
 int pp_sgd_step(size_t n, float* param, const float* grad, float* momentum_buf, float lr, float momentum,
                 float weight_decay, int first_step, void* stream);
+
+/* The same update with {lr, momentum, weight_decay, first_step} read from DEVICE memory (`hyper`, 4 floats): a
+ * CUDA-graph-captured step keeps following a learning-rate schedule without being re-captured. */
+int pp_sgd_step_dev(size_t n, float* param, const float* grad, float* momentum_buf, const float* hyper,
+                    void* stream);
+
+/* Loss / metric epilogue of one forward pass in ONE launch, forward and backward
+ * (experiments/trainer_private.py:161-168, experiments/trainer.py:28-43,139-142):
+ *   loss[0]  (+)= mean_n( logsumexp(logits[n,:]) - logits[n,target[n]] )         F.cross_entropy(pred, target)
+ *   top1[0]  (+)= 100/N * #{n : argmax_c logits[n,c] == target[n]}               accuracy(pred, target)[0]
+ *   dlogits[n,c] = (softmax(logits[n,:])[c] - [c == target[n]]) / N              d(mean loss)/d(logits), fp32
+ * logits: [N, classes] fp32 or bf16 (logits_bf16 != 0), row-major; target: int64 [N]; loss / top1 / dlogits may each
+ * be NULL; accumulate != 0 adds into loss / top1 (the V2 loop sums the loss of its two passes).  With it the trainer
+ * step needs no host read at all: the four numbers the reference prints are device scalars read once per step or
+ * per epoch. */
+int pp_ce_top1(int N, int classes, const void* logits, int logits_bf16, const int64_t* target, float* loss,
+               float* top1, float* dlogits, int accumulate, void* stream);
 
 /* Debug: after a kernel-side pipeline timeout the offending barrier id is recorded here. */
 int pp_debug_last_timeout(void);
