@@ -82,25 +82,44 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken inside [t_begin, t_end] (the timed region); if the region was shorter than the
+        sampling period, of the samples taken under load since start() (warm-up steps run the same kernels)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
+
+        def summarise(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2]))
+                    for name, v in zip(names, r[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                except Exception:
+                    pass
+            return sm, mx, reasons
+
+        window = [row for row in self.rows if t_begin is None or (t_begin <= row[0] <= (t_end or 1e18) + 0.1)]
+        scope = "timed region"
+        sm, mx, reasons = summarise(window)
+        if not sm:                                  # region shorter than one sampling period
+            loaded = []
+            for row in self.rows:
+                try:
+                    if float(row[1][3]) > 400.0:      # power draw: the device was running the step
+                        loaded.append(row)
+                except Exception:
+                    pass
+            sm, mx, reasons = summarise(loaded or self.rows)
+            scope = "warm-up + timed region (samples under load)"
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 def _seed(seed):
@@ -363,22 +382,24 @@ def main():
     # ---------------- leg 1 (`value`): inputs resident in HBM
     use_graph = args.graph and world == 1
     model, opt, runner, dev_batches, step = make_runner(args.config, B, graph=use_graph)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs a few hundred ms to deliver its first sample
     for i in range(args.warmup):
         step(*dev_batches[i % 4])
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     lib.pp_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for i in range(args.steps):
         step(*dev_batches[i % 4])
     e1.record()
     barrier()
+    t_end = time.time()
     launches = int(lib.pp_launch_count(0))
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     value = args.steps * per_step * world / (ms_total * 1e-3)
     if use_graph:       # a replay launches the captured kernels without passing through the library's counter
         launches = None
@@ -402,6 +423,7 @@ def main():
         trainer.on_log = lambda n, vals: seen.append(vals)
         trainer.train(0, [host[i % 4] for i in range(max(3, args.warmup // 2))], wm_host)
         barrier()
+        seen.clear()
         e0.record()
         trainer.train(1, [host[i % 4] for i in range(args.steps)], wm_host)
         e1.record()
@@ -628,8 +650,11 @@ def dropin_run(cfg, B, dev, steps):
     tcls = mods["experiments.trainer_private"].TrainerPrivate if cfg["scheme"] == "private" \
         else mods["experiments.trainer"].Trainer
     trainer = tcls(model, opt, None, dev)
-    data = synthetic_batches(cfg, B, 4, device=dev)
-    wm = trigger_batches(8, device=dev) if cfg["trigger"] else None
+    # channels_last batches: the blocks keep the memory format of their input, so this one line on the data side keeps
+    # the whole network in NHWC (with NCHW batches the route still works, with a layout conversion around each block)
+    data = [(x.contiguous(memory_format=torch.channels_last), t) for x, t in synthetic_batches(cfg, B, 4, device=dev)]
+    wm = [(x.contiguous(memory_format=torch.channels_last), t) for x, t in trigger_batches(8, device=dev)] \
+        if cfg["trigger"] else None
 
     def epoch(n):
         with contextlib.redirect_stdout(io.StringIO()), torch.autocast("cuda", dtype=torch.bfloat16):

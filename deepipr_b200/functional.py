@@ -417,7 +417,15 @@ class _ConvBlockFn(torch.autograd.Function):
             ctx.gdtype = None if gamma is None else gamma.dtype
             ctx.bdtype = None if beta is None else beta.dtype
         out_dtype = o.out_dtype or x.dtype
-        return y if out_dtype == torch.bfloat16 else y.to(out_dtype)
+        if out_dtype != torch.bfloat16:
+            y = y.to(out_dtype)
+        # The output keeps the memory format of the input: channels_last in -> channels_last out (no copy; what the
+        # nets of this package and autocast pipelines use), NCHW-contiguous in -> NCHW-contiguous out, because the
+        # reference's model files call .view() on block outputs (models/alexnet_passport.py: x.view(x.size(0), -1),
+        # passportconv2d.py:101 passport_candidates.view(b * c, h, w)) and a channels_last tensor is not viewable.
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            y = y.contiguous()
+        return y
 
     @staticmethod
     def backward(ctx, gy):

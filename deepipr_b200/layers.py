@@ -280,7 +280,7 @@ class _PassportBase(nn.Module, _FusedConvMixin):
         b, c, h, w = passport_candidates.size()
         if c == 3:  # network input: take one whole image
             return passport_candidates[random.randint(0, b - 1)].unsqueeze(0)
-        flat = passport_candidates.view(b * c, h, w)
+        flat = passport_candidates.contiguous().view(b * c, h, w)     # (also accepts channels_last candidates)
         taken = [False] * (b * c)
         chosen = []
         img = 0

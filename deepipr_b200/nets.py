@@ -85,6 +85,14 @@ def _call(block, x, force_passport, ind):
     return block(x)
 
 
+def _fp32_head(features, linear):
+    """Classifier head in fp32 on the (bf16) activations, also under autocast: F.adaptive_avg_pool2d + nn.Linear of
+    the reference nets (resnet_passport_private.py:176-179) are 0.1 % of the step, and keeping them out of bf16 means
+    the logits carry no rounding beyond that of the activations they are computed from."""
+    with torch.autocast('cuda', enabled=False):
+        return F.linear(features.float(), linear.weight.float(), None if linear.bias is None else linear.bias.float())
+
+
 class BasicUnit(nn.Module):
     """Two 3x3 blocks + (projected) shortcut; attribute names as BasicPrivateBlock / BasicPassportBlock / BasicBlock."""
     expansion = 1
@@ -177,6 +185,8 @@ class ResNet18(nn.Module):
         return n
 
     def _stem(self, x, force_passport, ind):
+        # blocks keep the memory format of their input: enter the NHWC pipeline once, on the 3-channel image
+        x = x.contiguous(memory_format=torch.channels_last)
         if isinstance(self.convbnrelu_1, nn.Sequential):
             return self.convbnrelu_1[1](_call(self.convbnrelu_1[0], x, force_passport, ind))
         return _call(self.convbnrelu_1, x, force_passport, ind)
@@ -224,8 +234,7 @@ class ResNet18(nn.Module):
             rest = self._units()
         for unit in rest:
             out = unit(out, force_passport, ind)
-        out = F.adaptive_avg_pool2d(out, (1, 1)).flatten(1)
-        return self.linear(out)
+        return _fp32_head(out.float().mean(dim=(2, 3)), self.linear)
 
     def set_intermediate_keys(self, pretrained_model, x, y=None):
         """Push passport candidates through a (normal) pretrained net, handing each passport layer its input
@@ -267,9 +276,10 @@ class AlexNetCifar(nn.Module):
         self.classifier = nn.Linear(4 * 4 * 256, num_classes)
 
     def forward(self, x, force_passport=False, ind=0):
+        x = x.contiguous(memory_format=torch.channels_last)
         for m in self.features:
             x = _call(m, x, force_passport, ind)
-        return self.classifier(x.reshape(x.size(0), -1))
+        return _fp32_head(x.float().reshape(x.size(0), -1), self.classifier)      # logical NCHW flatten order
 
     def set_intermediate_keys(self, pretrained_model, x, y=None):
         with torch.no_grad():

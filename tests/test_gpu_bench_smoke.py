@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 def test_bench_contract_small_batch():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--batch", "32", "--steps", "3", "--warmup", "3",
-                        "--cpu-steps", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--cpu-steps", "1", "--legs", "value,e2e,roofline,eager,dropin,shared"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, p.stdout[-1000:]
@@ -22,10 +23,29 @@ def test_bench_contract_small_batch():
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert key in d, key
     assert d["value"] > 0 and d["gpu_launches"] > 0 and d["n_gpus"] == 1 and d["steps"] == 3
-    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 32 * 3 * 32 * 32 * 4 + 32 * 8
+    # V3 default: 32 images + 2 trigger images per step, all copied from pinned host memory in the e2e leg
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 34 * 3 * 32 * 32 * 4 + 34 * 8
+    assert d["e2e"]["d2h_bytes_per_step"] == 16 and d["last_step"]["metric_reads"] == 3
     assert d["roofline"]["bound"] == "tensor" and 0 < d["roofline"]["frac"] < 1.5
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
-    assert d["config"]["workload"].startswith("ResNet18 V2")
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["workload"].startswith("ResNet18 V3") and d["config"]["trigger_images_per_step_per_gpu"] == 2
+    # the unmodified reference on this GPU, and its own trainer driving the patched blocks
+    assert d["torch_eager_gpu"]["fp32_as_shipped"]["value"] > 0
+    assert d["reference_trainer_on_patched_blocks"]["value"] > 0
+    assert d["reference_trainer_on_patched_blocks"]["library_launches"] > 100
+
+
+def test_bench_other_configs_and_graph_mode():
+    """BASELINE configs 2, 3 and 5 through --config, and the CUDA-graph step through --graph, at tiny batches."""
+    for extra in (["--config", "v1_alexnet"], ["--config", "v2_cifar100"], ["--config", "v1_imagenet", "--batch", "4"],
+                  ["--graph"]):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--batch", "16", "--steps", "2", "--warmup",
+                            "3", "--no-cpu-baseline", "--legs", "value,e2e", *extra], capture_output=True, text=True,
+                           timeout=600, cwd=ROOT)
+        assert p.returncode == 0, (extra, p.stderr[-2000:])
+        d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][0])
+        assert d["value"] > 0 and d["e2e"]["value"] > 0, extra
+        assert d["cuda_graph"] == ("--graph" in extra)
 
 
 def test_reference_arm_line():
@@ -34,7 +54,8 @@ def test_reference_arm_line():
     assert p.returncode == 0, p.stderr[-2000:]
     d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][0])
     assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["kind"] == "reference" and d["steps"] == 1 and d["warmup"] == 1
+    assert d["config"]["workload"].startswith("ResNet18 V3")
 
 
 def test_graft_smoke():

@@ -220,6 +220,8 @@ def test_reference_training_scripts_run_unchanged_on_the_patched_blocks(tmp_path
             assert abs(g[k] - w[k]) <= 100.0 / 8 + 1e-6, (k, g[k], w[k])
         elif "sign_loss" in k:
             _close(g[k], w[k], 2e-3, k)
+        elif k.startswith("wm_loss"):                     # eval-mode loss on the TWO trigger images after two SGD
+            _close(g[k], w[k], 0.25, k)                   # steps (running statistics barely started): chaotic
         else:
             _close(g[k], w[k], 5e-2, k)                   # cross-entropy after bf16-operand convs through 20 layers
     for k, v in want["param_abs_sums"].items():
