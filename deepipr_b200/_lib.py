@@ -10,7 +10,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpassport_sm100.so")
 
-PP_ABI_VERSION = 11
+PP_ABI_VERSION = 12
 PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL, PP_NORM_GN = 0, 1, 2, 3
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1
@@ -23,7 +23,8 @@ EXPORTS = (
     "pp_conv_block_fwd", "pp_conv_block_bwd", "pp_conv_fwd_raw", "pp_conv_dgrad", "pp_conv_wgrad",
     "pp_sgd_step", "pp_debug_last_timeout", "pp_launch_count", "pp_profile_enable", "pp_profile_read",
     "pp_add_relu_fwd", "pp_add_relu_bwd", "pp_passport_key_grad", "pp_signature_verify",
-    "pp_sgd_step_dev", "pp_ce_top1",
+    "pp_sgd_step_dev", "pp_ce_top1", "pp_passport_conv_fwd", "pp_passport_conv_bwd",
+    "pp_debug_fused",
 )
 
 
@@ -68,6 +69,10 @@ _PROTOS = {
     "pp_sign_loss_bwd": (C.c_int, [_i, _fp, _fp, _f, _fp, _fp, _vp]),
     "pp_conv_block_fwd": (C.c_int, [_desc, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp, _sz, _vp]),
     "pp_conv_block_bwd": (C.c_int, [_desc, _vp, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _vp, _sz, _vp]),
+    "pp_passport_conv_fwd": (C.c_int, [_desc, _vp, _vp, _fp, _dp, _dp, _fp, _fp, _fp, _f, _fp, _fp, _vp, _vp, _fp, _fp,
+                                       _fp, _fp, _fp, _fp, _vp, _sz, _vp]),
+    "pp_passport_conv_bwd": (C.c_int, [_desc, _vp, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _dp, _dp, _fp, _f, _fp, _vp, _fp,
+                                       _fp, _fp, _vp, _sz, _vp]),
     "pp_conv_fwd_raw": (C.c_int, [_desc, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pp_conv_dgrad": (C.c_int, [_desc, _vp, _vp, _vp, _vp]),
     "pp_conv_wgrad": (C.c_int, [_desc, _vp, _vp, _fp, _vp, _sz, _vp]),
@@ -77,6 +82,7 @@ _PROTOS = {
     "pp_add_relu_fwd": (C.c_int, [_sz, _vp, _vp, _vp, _vp]),
     "pp_add_relu_bwd": (C.c_int, [_sz, _vp, _vp, _vp, _vp]),
     "pp_debug_last_timeout": (C.c_int, []),
+    "pp_debug_fused": (C.c_int, [_i]),
     "pp_launch_count": (C.c_longlong, [_i]),
     "pp_profile_enable": (C.c_int, [_i]),
     "pp_profile_read": (C.c_int, [_i, _i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),

@@ -217,6 +217,7 @@ static size_t gn_partial_rows(const PPConvDesc& d, const Geo& geo) {
 struct FwdWs {
   float* ca; float* cb; float* partial;
   __nv_bfloat16* col; __nv_bfloat16* wpad;
+  unsigned int* barrier;   // grid-barrier counter of the single-kernel block
   size_t total;
 };
 static FwdWs carve_fwd(const PPConvDesc& d, const Geo& geo, void* base) {
@@ -232,6 +233,7 @@ static FwdWs carve_fwd(const PPConvDesc& d, const Geo& geo, void* base) {
   const int Kpad = col_kpad(d, geo);
   w.col = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * (size_t)Kpad * 2);
   w.wpad = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256((size_t)d.O * Kpad * 2);
+  w.barrier = reinterpret_cast<unsigned int*>(p + off); off += 256;
   w.total = off;
   return w;
 }
@@ -358,6 +360,26 @@ static int run_wgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
   if (tc) PP_TRY(wgrad_tcgen05(g, x, dz, d.O, wpartial, splits, s));
   else PP_TRY(wgrad_simt(g, x, dz, d.O, wpartial, splits, s));
   return launch_wgrad_finalize(d, wpartial, splits, geo.T * d.C, dw, s, accumulate);
+}
+
+// The block as ONE cooperative kernel when every output tile stays resident in TMEM (igemm_sm100.cu:
+// passport_fused_kernel).  Returns PP_OK with *done = true when it ran; *done = false means "not eligible, use the
+// kernel sequence".  Exactly one of (gamma_in/beta_in) or (w_oihw, Ss, Sk -> gamma_out/beta_out) describes the affine.
+static int try_fused_block(const PPConvDesc& d, const Geo& geo, const void* x, const void* wf, const FwdWs& ws,
+                           FusedArgs a, cudaStream_t s, bool* done) {
+  *done = false;
+  if (d.norm != PP_NORM_BN_TRAIN || !a.z || !d.z_f32 || d.algo == PP_ALGO_SIMT) return PP_OK;
+  if (stem_direct_supported(d) || col_kpad(d, geo)) return PP_OK;
+  TapGemm g;
+  plan_fprop(d, geo, g);
+  if (!passport_fused_supported(g)) return PP_OK;
+  a.partial = ws.partial;
+  a.barrier = ws.barrier;
+  a.eps = d.eps; a.momentum = d.momentum; a.relu = d.relu;
+  a.Cin = d.C; a.T = geo.T;
+  PP_TRY(passport_fused_tcgen05(g, x, wf, a, s));
+  *done = true;
+  return PP_OK;
 }
 
 }  // namespace pp
@@ -506,6 +528,15 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
     e.out = y; e.out_f32 = 0; e.scale = ws.ca; e.shift = ws.cb; e.relu = d->relu; e.stats_partial = nullptr;
     return run_fprop(*d, geo, x, w_fprop, e, nullptr, ws.col, ws.wpad, s);
   }
+  {
+    FusedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.y = y; fa.z = d->z_f32 ? (float*)z : nullptr; fa.gamma_in = gamma; fa.beta_in = beta;
+    fa.rmean = running_mean; fa.rvar = running_var; fa.save_mean = save_mean; fa.save_invstd = save_invstd;
+    bool done = false;
+    PP_TRY(try_fused_block(*d, geo, x, w_fprop, ws, fa, s, &done));
+    if (done) return PP_OK;
+  }
   TapEpilogue e;
   e.out = z; e.out_f32 = d->z_f32; e.scale = nullptr; e.shift = nullptr; e.relu = 0;
   const bool fused_stats = d->norm == PP_NORM_BN_TRAIN && d->O <= tapgemm_tcgen05_max_stats_width();
@@ -581,6 +612,63 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
   if (dw_oihw)
     PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s, d->flags & PP_FLAG_ACC_DW));
   return PP_OK;
+}
+
+int pp_passport_conv_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, const float* w_oihw,
+                         const double* S_skey, const double* S_key, const float* scale_pub, const float* bias_pub,
+                         const float* b_sign, float alpha, float* running_mean, float* running_var, void* y, void* z,
+                         float* gamma, float* beta, float* save_mean, float* save_invstd, float* sign_loss,
+                         float* sign_acc, void* workspace, size_t ws_bytes, void* stream) {
+  Geo geo;
+  PP_TRY(geo_of(d, &geo));
+  PP_TRY(check_device());
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool pub = scale_pub != nullptr && bias_pub != nullptr;
+  PP_REQUIRE(x && w_fprop && y, PP_EBADARG, "passport conv fwd: NULL pointer");
+  PP_REQUIRE(pub || (w_oihw && S_skey && S_key && gamma && beta), PP_EBADARG,
+             "passport conv fwd: the passport path needs w_oihw, S_skey, S_key and the gamma / beta buffers");
+  PP_REQUIRE((scale_pub == nullptr) == (bias_pub == nullptr), PP_EBADARG,
+             "passport conv fwd: scale_pub and bias_pub must both be given or both be NULL");
+  FwdWs ws = carve_fwd(*d, geo, workspace);
+  PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "fwd workspace too small: need %zu, got %zu", ws.total,
+             ws_bytes);
+  {
+    FusedArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.y = y; fa.z = (z && d->z_f32) ? (float*)z : nullptr;
+    if (pub) { fa.gamma_in = scale_pub; fa.beta_in = bias_pub; }
+    else {
+      fa.w_oihw = w_oihw; fa.Ss = S_skey; fa.Sk = S_key; fa.gamma_out = gamma; fa.beta_out = beta;
+      fa.b_sign = b_sign; fa.alpha = alpha; fa.sign_loss = sign_loss; fa.sign_acc = sign_acc;
+    }
+    fa.rmean = running_mean; fa.rvar = running_var; fa.save_mean = save_mean; fa.save_invstd = save_invstd;
+    bool done = false;
+    PP_TRY(try_fused_block(*d, geo, x, w_fprop, ws, fa, s, &done));
+    if (done) return PP_OK;
+  }
+  // kernel sequence: gamma / beta (+ sign loss) first, then the conv block
+  if (!pub)
+    PP_TRY(launch_passport_affine_fwd(*d, w_oihw, S_skey, S_key, b_sign, alpha, gamma, beta, sign_loss, sign_acc, s));
+  return pp_conv_block_fwd(d, x, w_fprop, pub ? scale_pub : gamma, pub ? bias_pub : beta, running_mean, running_var,
+                           z, y, save_mean, save_invstd, workspace, ws_bytes, stream);
+}
+
+int pp_passport_conv_bwd(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad, const void* z,
+                         const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                         const double* S_skey, const double* S_key, const float* b_sign, float alpha,
+                         const float* g_sign_loss, void* dx, float* dw_oihw, float* dgamma, float* dbeta,
+                         void* workspace, size_t ws_bytes, void* stream) {
+  PP_REQUIRE(d != nullptr, PP_EBADARG, "PPConvDesc is NULL");
+  PP_REQUIRE((S_skey == nullptr) == (S_key == nullptr), PP_EBADARG, "passport conv bwd: S_skey / S_key mismatch");
+  PP_REQUIRE(!S_skey || dw_oihw, PP_EBADARG, "passport conv bwd: the passport path needs dw_oihw");
+  PPConvDesc dd = *d;
+  dd.flags &= ~(PP_FLAG_ACC_DGAMMA | PP_FLAG_ACC_DBETA);     // dgamma / dbeta are consumed below, never accumulated
+  PP_TRY(pp_conv_block_bwd(&dd, dy, x, w_dgrad, z, gamma, beta, save_mean, save_invstd, dx, dw_oihw, dgamma, dbeta,
+                           workspace, ws_bytes, stream));
+  if (!S_skey) return PP_OK;                                  // public path: dgamma / dbeta ARE dscale / dbias
+  // rank-1 term of the weight gradient: gamma, beta are functions of W (passportconv2d.py:146-152, 167-173)
+  return launch_passport_affine_bwd(*d, S_skey, S_key, gamma, b_sign, alpha, dgamma, dbeta, g_sign_loss, dw_oihw,
+                                    /*accumulate=*/1, (cudaStream_t)stream);
 }
 
 int pp_conv_fwd_raw(const PPConvDesc* d, const void* x, const void* w_fprop, void* z, void* workspace,
@@ -661,6 +749,7 @@ int pp_add_relu_bwd(size_t n, const void* gy, const void* y, void* gx, void* str
 }
 
 int pp_debug_last_timeout(void) { return debug_last_timeout(); }
+int pp_debug_fused(int on) { return debug_fused(on); }
 
 long long pp_launch_count(int reset) {
   const long long v = g_launches.load();

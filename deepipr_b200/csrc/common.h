@@ -95,7 +95,7 @@ struct TapEpilogue {
 void count_launch();
 // optional per-kernel CUDA-event timing (bench.py roofline legs): the two tensor-core kernels (work = FLOPs) and the
 // three HBM-bound passes of the block (work = algorithmic bytes: affine z->y, backward reduce, dz)
-enum { PROF_TAPGEMM = 0, PROF_WGRAD = 1, PROF_AFFINE = 2, PROF_REDUCE = 3, PROF_DZ = 4, PROF_KINDS = 5 };
+enum { PROF_TAPGEMM = 0, PROF_WGRAD = 1, PROF_AFFINE = 2, PROF_REDUCE = 3, PROF_DZ = 4, PROF_FUSED = 5, PROF_KINDS = 6 };
 void prof_begin(int kind, double flops, int c, int nout, int taps, cudaStream_t s);
 void prof_end(int kind, cudaStream_t s);
 
@@ -109,6 +109,24 @@ bool tapgemm_tcgen05_supported(const TapGemm& g);
 int tapgemm_tcgen05_grid(const TapGemm& g);  // CTAs launched == rows of stats_partial written
 int tapgemm_tcgen05_max_stats_width();       // widest Nout for which the fused column statistics are available
 int debug_last_timeout();
+// the passport block as one cooperative kernel (conv + batch statistics + grid barrier + affine + ReLU from TMEM)
+struct FusedArgs {
+  void* y;                       // bf16 [rows, O]
+  float* z;                      // fp32 [rows, O] (saved for backward)
+  float* partial;                // [passport_fused_grid()][2][256]
+  unsigned int* barrier;         // 4 bytes of workspace
+  const float* gamma_in; const float* beta_in;     // given per-channel affine, or ...
+  const float* w_oihw; const double* Ss; const double* Sk; int Cin, T;   // ... derived from the passport
+  float* gamma_out; float* beta_out;
+  const float* b_sign; float alpha; float* sign_loss; float* sign_acc;
+  float* rmean; float* rvar; float* save_mean; float* save_invstd;
+  float eps, momentum;
+  int relu;
+};
+int debug_fused(int on);   // A/B switch of the single-kernel block: returns the previous setting, on < 0 only queries
+bool passport_fused_supported(const TapGemm& g);
+int passport_fused_grid(const TapGemm& g);
+int passport_fused_tcgen05(const TapGemm& g, const void* act, const void* B, const FusedArgs& a, cudaStream_t s);
 // wgrad: partial[split][Mo][T*C] (fp32) = sum over a slice of pixels of dz[m, o] * act_tap[m, c]
 int wgrad_tcgen05(const TapGemm& g /*fprop geometry of x*/, const void* x, const void* dz, int O, float* partial,
                   int splits, cudaStream_t s);

@@ -1007,6 +1007,520 @@ int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapE
 }
 
 // ------------------------------------------------------------------------------------------------
+// The passport block as ONE kernel (models/layers/passportconv2d.py:209-223 + :142-175, sign_loss.py:32-54):
+//
+//   gamma, beta = W . pool(skey), W . pool(key)       (fp32 master weight, fp64 accumulate; or given: public scale/bias)
+//   z = conv(x, W)                                    tcgen05, accumulators stay RESIDENT in TMEM
+//   mean, var over the batch                          per-CTA column sums -> global partials -> grid barrier
+//   y = relu(gamma * (z - mean) * invstd + beta)      straight from TMEM, bf16, 128-bit stores
+//   sign loss / sign accuracy, running statistics
+//
+// Batch-norm needs the statistics of ALL tiles before any output element exists, so a one-kernel block has to keep
+// every accumulator on chip until a grid-wide reduction has happened.  TMEM holds 512 fp32 columns per SM = two
+// 128 x 256 tiles; with one CTA per SM that is 2 * #SMs tiles (296 on B200): the passport layers of ResNet-18
+// (layer4: 512 output channels, 4x4 / 7x7 maps) fit up to 1184 CIFAR / 386 ImageNet images per GPU.  Launched
+// cooperatively (all CTAs co-resident), grid barrier = one atomic counter in the workspace.
+//
+//   warp 0      TMA producer (as tapgemm_kernel)
+//   warp 1      MMA issuer; local tile s accumulates into TMEM columns [256 s, 256 s + 256)
+//   warps 2..5  (a) gamma / beta rows of this CTA while the first tile is being computed,
+//               (b) pass 1 per tile: z (fp32, saved for backward) out, column sums of z and z^2,
+//               ---- grid barrier ----
+//               (c) all warps: fixed-order reduction of the partials -> a = gamma * invstd, b = beta - a * mean,
+//               (d) pass 2 per tile: y = relu(a z + b) from TMEM.
+// The z write of the first tile overlaps the second tile's main loop; after the barrier only y (2 bytes / element) is
+// written.  Against the multi-kernel path this removes the re-read of z (4 bytes / element), two launches
+// (bn_finalize, affine_apply) and, on the passport path, two more (gemv, sign loss).
+// ------------------------------------------------------------------------------------------------
+struct FusedDev {
+  TapGemmDev g;                 // conv geometry (epilogue fields unused)
+  __nv_bfloat16* y;             // [M, Nout] bf16
+  float* z;                     // [M, Nout] fp32 (saved for backward)
+  float* partial;               // [grid][2][256] per-CTA column sums
+  unsigned int* barrier;        // zeroed before the launch
+  const float* gamma_in;        // per-channel scale / bias given by the caller (public path, ConvBlock) ...
+  const float* beta_in;
+  const float* w_oihw;          // ... or derived here from the passport: fp32 master weight [O, C*T],
+  const double* Ss;             //     pooled skey / key patches [T*C]
+  const double* Sk;
+  int Cin, T;
+  float* gamma_out;             // [O] (written when derived; global because every CTA needs all of its columns)
+  float* beta_out;
+  const float* b_sign;          // SignLoss (NULL: none)
+  float alpha;
+  float* sign_loss;
+  float* sign_acc;
+  float* rmean; float* rvar;    // running statistics (may be NULL)
+  float* save_mean; float* save_invstd;
+  float eps, momentum;
+  int relu;
+  int n_tiles;                  // Nout / 256
+};
+
+constexpr int kFusedBN = 256;
+constexpr int kFusedStages = 4;
+constexpr int kFusedStageBytes = kBM * kBK * 2 + kFusedBN * kBK * 2;   // 48 KiB
+constexpr int kFusedSmemBytes = 1024 + kFusedStages * kFusedStageBytes + 2 * kFusedBN * 4 /*a, b*/ +
+                                4 * 2 * kFusedBN * 4 /*s_red*/ + 2 * kFusedBN * 4 /*s_acc*/ + 4 * 4096 /*staging*/ + 256;
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All CTAs of a cooperative launch.  Bounded like every other wait in this file.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(counter) < expected) {
+      if (clock64() - t0 > 4000000000LL) {
+        g_pp_timeout_code = 1500;
+        __threadfence_system();
+        printf("[passport_sm100] grid barrier timeout block=%d\n", (int)blockIdx.x);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ FusedDev p) {
+  constexpr int BN = kFusedBN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* s_a = reinterpret_cast<float*>(stage_base + kFusedStages * kFusedStageBytes);
+  float* s_b = s_a + BN;
+  float* s_red = s_b + BN;              // [4 warps][2][BN]
+  float* s_acc = s_red + 4 * 2 * BN;    // [2][BN] running per-CTA column sums
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_acc + 2 * BN);   // [4 warps][4 KiB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * 4096);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kFusedStages;
+  uint64_t* tfull = bars + 2 * kFusedStages;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+
+  const TapGemmDev& g = p.g;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = g.num_m_tiles * g.num_n_tiles;
+  const int kchunks = g.C / kBK;
+  const int ksteps = g.ntaps * kchunks;
+  const int grid = (int)gridDim.x;
+  const int nlocal = ((int)blockIdx.x + grid < num_tiles) ? 2 : 1;     // grid <= num_tiles <= 2 * grid
+  const int my_n_tile = (int)blockIdx.x % g.num_n_tiles;               // grid % num_n_tiles == 0: same for both tiles
+  const int n0 = my_n_tile * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kFusedStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    mbar_init(&tfull[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const int a_tiled = g.a_tiled;
+    for (int s = 0; s < nlocal; ++s) {
+      const int tile = (int)blockIdx.x + s * grid;
+      const int m_tile = tile / g.num_n_tiles;
+      const int m0 = m_tile * kBM;
+      const int img = m0 / g.PQ;
+      const int rem = m0 - img * g.PQ;
+      const int p0 = rem / g.Q;
+      const int q0 = rem - p0 * g.Q;
+      const int cw = g.base_w + q0 * g.step_w;
+      const int ch = g.base_h + p0 * g.step_h;
+      for (int t = 0; t < g.ntaps; ++t) {
+        const int dw = g.tap_dw[t];
+        const int dh = g.tap_dh[t];
+        const int kofs = g.tap_kofs[t];
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1, 1600 + stage);
+          if (elect_one()) {
+            uint8_t* sa = stage_base + stage * kFusedStageBytes;
+            uint8_t* sb = sa + kBM * kBK * 2;
+            mbar_arrive_expect_tx(&full[stage], kFusedStageBytes);
+            if (a_tiled) tma_load_4d(&tmA, &full[stage], sa, kc * kBK, cw + dw, ch + dh, img);
+            else tma_load_im2col_4d(&tmA, &full[stage], sa, kc * kBK, cw, ch, img, (uint16_t)dw, (uint16_t)dh);
+            tma_load_2d(&tmB, &full[stage], sb, kofs + kc * kBK, n0);
+          }
+          __syncwarp();
+          if (++stage == kFusedStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: tile s -> TMEM columns [256 s, 256 s + 256), never recycled =====================
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t stage0 = smem_u32(stage_base);
+    for (int s = 0; s < nlocal; ++s) {
+      const uint32_t d_tmem = tmem_base + s * BN;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full[stage], phase, 1700 + stage);
+        tc_fence_after();
+        const uint32_t sa = stage0 + stage * kFusedStageBytes;
+        const uint32_t sb = sa + kBM * kBK * 2;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+            tc_mma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);
+          if (ks == ksteps - 1) tc_commit(&tfull[s]);
+        }
+        __syncwarp();
+        if (++stage == kFusedStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps, part 1 =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int tid_e = ew * 32 + lane;
+    // (a) passport-derived gamma / beta for the channels this CTA owns (4 warps x 1 channel, strided over the grid);
+    //     hidden behind the first tile's main loop
+    if (p.w_oihw != nullptr) {
+      const int K = p.Cin * p.T;
+      for (int c = (int)blockIdx.x * 4 + ew; c < g.Nout; c += 4 * grid) {
+        const float* wrow = p.w_oihw + (size_t)c * K;
+        double gsum = 0.0, bsum = 0.0;
+        for (int i = lane; i < K; i += 32) {
+          const int ci = i / p.T;
+          const int k = (i - ci * p.T) * p.Cin + ci;
+          const double w = (double)__ldg(wrow + i);
+          gsum = fma(w, p.Ss[k], gsum);
+          bsum = fma(w, p.Sk[k], bsum);
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
+          bsum += __shfl_xor_sync(0xffffffffu, bsum, off);
+        }
+        if (lane == 0) {
+          p.gamma_out[c] = (float)gsum;
+          p.beta_out[c] = (float)bsum;
+        }
+      }
+    }
+    for (int i = tid_e; i < 2 * BN; i += 128) s_acc[i] = 0.0f;
+    // (b) pass 1: z out (fp32), column sums
+    for (int s = 0; s < nlocal; ++s) {
+      const int tile = (int)blockIdx.x + s * grid;
+      const int m_tile = tile / g.num_n_tiles;
+      const int m = m_tile * kBM + row;
+      const bool valid = m < g.M;
+      const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+      const long long out_row = (long long)m;
+      named_bar_sync(1, 128);   // s_acc zeroed / previous tile's s_red consumed
+      mbar_wait(&tfull[s], 0, 1800 + s);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + s * BN;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + j * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(raw[i]) : 0.0f;
+        {
+          float t1[32], t2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            t1[i] = v[i];
+            t2[i] = v[i] * v[i];
+          }
+          const float s1 = warp_column_sum(t1, lane);
+          const float s2 = warp_column_sum(t2, lane);
+          s_red[(ew * 2 + 0) * BN + j * 32 + lane] = s1;
+          s_red[(ew * 2 + 1) * BN + j * 32 + lane] = s2;
+        }
+        if (p.z != nullptr) {
+          float4* st = reinterpret_cast<float4*>(s_stage + ew * 4096);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st[lane * 8 + (i ^ (lane & 7))] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          __syncwarp();
+          float* obase = p.z + n0 + j * 32 + (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3);
+            const float4 val = st[r * 8 + ((lane & 7) ^ (r & 7))];
+            const long long orow = __shfl_sync(0xffffffffu, out_row, r);
+            if ((valid_mask >> r) & 1u) *reinterpret_cast<float4*>(obase + (size_t)orow * g.Nout) = val;
+          }
+          __syncwarp();
+        }
+      }
+      named_bar_sync(1, 128);
+      for (int i = tid_e; i < BN; i += 128) {
+        const float a1 = s_red[(0 * 2 + 0) * BN + i] + s_red[(1 * 2 + 0) * BN + i] + s_red[(2 * 2 + 0) * BN + i] +
+                         s_red[(3 * 2 + 0) * BN + i];
+        const float a2 = s_red[(0 * 2 + 1) * BN + i] + s_red[(1 * 2 + 1) * BN + i] + s_red[(2 * 2 + 1) * BN + i] +
+                         s_red[(3 * 2 + 1) * BN + i];
+        s_acc[i] += a1;            // column i is only ever touched by this thread
+        s_acc[BN + i] += a2;
+      }
+    }
+    named_bar_sync(1, 128);
+    float* dst = p.partial + (size_t)blockIdx.x * 2 * BN;
+    for (int i = tid_e; i < 2 * BN; i += 128) dst[i] = s_acc[i];
+  }
+
+  // ===================== grid-wide: every tile's statistics are in global memory =====================
+  tc_fence_before();
+  grid_barrier(p.barrier, (unsigned int)grid);
+  tc_fence_after();
+
+  // (c) all 192 threads: fixed-order reduction of the partial rows of the CTAs that share this CTA's 256 columns.
+  //     The pipeline stages are idle now: their memory holds the fp64 scratch.
+  {
+    double* sh = reinterpret_cast<double*>(stage_base);     // [3 groups][2 * BN]
+    const int grp = threadIdx.x / 64;                       // rows k == grp (mod 3)
+    const int l64 = threadIdx.x % 64;                       // float4 #l64 of sum z, float4 #l64 of sum z^2
+    const int nrows = grid / g.num_n_tiles;
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = grp; k < nrows; k += 3) {
+      const float4* rowp = reinterpret_cast<const float4*>(p.partial + (size_t)(my_n_tile + k * g.num_n_tiles) * 2 * BN);
+      const float4 u = __ldcg(rowp + l64);
+      const float4 w = __ldcg(rowp + 64 + l64);
+      acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
+      acc[4] += w.x; acc[5] += w.y; acc[6] += w.z; acc[7] += w.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sh[grp * 2 * BN + l64 * 4 + i] = acc[i];
+      sh[grp * 2 * BN + BN + l64 * 4 + i] = acc[4 + i];
+    }
+    __syncthreads();
+    const double n = (double)g.M;
+    for (int col = threadIdx.x; col < BN; col += kThreads) {
+      const double s1 = sh[col] + sh[2 * BN + col] + sh[4 * BN + col];
+      const double s2 = sh[BN + col] + sh[2 * BN + BN + col] + sh[4 * BN + BN + col];
+      const double mu = s1 / n;
+      double var = s2 / n - mu * mu;
+      if (var < 0.0) var = 0.0;
+      const float mean = (float)mu;
+      const float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
+      const int o = n0 + col;
+      const float gm = p.w_oihw ? __ldcg(p.gamma_out + o) : (p.gamma_in ? __ldg(p.gamma_in + o) : 1.0f);
+      const float bt = p.w_oihw ? __ldcg(p.beta_out + o) : (p.beta_in ? __ldg(p.beta_in + o) : 0.0f);
+      const float a = gm * invstd;
+      s_a[col] = a;
+      s_b[col] = bt - a * mean;
+      if ((int)blockIdx.x < g.num_n_tiles) {      // one CTA per column block owns the per-channel side effects
+        if (p.save_mean) p.save_mean[o] = mean;
+        if (p.save_invstd) p.save_invstd[o] = invstd;
+        if (p.rmean) {
+          const double unbiased = g.M > 1 ? var * (n / (n - 1.0)) : var;
+          p.rmean[o] = (1.0f - p.momentum) * p.rmean[o] + p.momentum * mean;
+          p.rvar[o] = (1.0f - p.momentum) * p.rvar[o] + p.momentum * (float)unbiased;
+        }
+      }
+    }
+    // SignLoss.add(gamma) (sign_loss.py:25-28, 53-54): the last CTA, fixed-order fp64 tree
+    if (p.b_sign != nullptr && (p.sign_loss || p.sign_acc) && (int)blockIdx.x == grid - 1) {
+      __syncthreads();                                       // sh is about to be reused
+      double h = 0.0, r = 0.0, a = 0.0;
+      for (int o = threadIdx.x; o < g.Nout; o += kThreads) {
+        const float gm = p.w_oihw ? __ldcg(p.gamma_out + o) : (p.gamma_in ? __ldg(p.gamma_in + o) : 1.0f);
+        const float bb = __ldg(p.b_sign + o);
+        const float hinge = fmaxf(-bb * gm + 0.1f, 0.0f);
+        h += (double)(p.alpha * hinge);
+        r += (double)(gm * gm);
+        const float sb = (bb > 0.f) - (bb < 0.f);
+        const float sg = (gm > 0.f) - (gm < 0.f);
+        a += (sb == sg) ? 1.0 : 0.0;
+      }
+      sh[threadIdx.x] = h;
+      sh[kThreads + threadIdx.x] = r;
+      sh[2 * kThreads + threadIdx.x] = a;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double hs = 0.0, rs = 0.0, as = 0.0;
+        for (int i = 0; i < kThreads; ++i) { hs += sh[i]; rs += sh[kThreads + i]; as += sh[2 * kThreads + i]; }
+        if (p.sign_loss) *p.sign_loss = (float)(hs + 0.00001 * rs);
+        if (p.sign_acc) *p.sign_acc = (float)(as / (double)g.Nout);
+      }
+    }
+    __syncthreads();
+  }
+
+  // (d) pass 2: y = relu(a z + b) straight from the resident accumulators
+  if (warp >= 2) {
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    for (int s = 0; s < nlocal; ++s) {
+      const int tile = (int)blockIdx.x + s * grid;
+      const int m_tile = tile / g.num_n_tiles;
+      const int m = m_tile * kBM + row;
+      const bool valid = m < g.M;
+      const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+      const long long out_row = (long long)m;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + s * BN;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + j * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(raw[i]), s_a[j * 32 + i], s_b[j * 32 + i]);
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        uint4* st = reinterpret_cast<uint4*>(s_stage + ew * 4096);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+          u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+          u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+          u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+          st[lane * 4 + (i ^ ((lane >> 1) & 3))] = u;
+        }
+        __syncwarp();
+        __nv_bfloat16* obase = p.y + n0 + j * 32 + (lane & 3) * 8;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int r = it * 8 + (lane >> 2);
+          const uint4 val = st[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
+          const long long orow = __shfl_sync(0xffffffffu, out_row, r);
+          if ((valid_mask >> r) & 1u) *reinterpret_cast<uint4*>(obase + (size_t)orow * g.Nout) = val;
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int g_fused_on = -1;     // -1: not decided yet (env PP_NO_FUSED=1 disables); pp_debug_fused() overrides
+static bool fused_enabled() {
+  if (g_fused_on < 0) { const char* e = getenv("PP_NO_FUSED"); g_fused_on = (e && e[0] == '1') ? 0 : 1; }
+  return g_fused_on == 1;
+}
+int debug_fused(int on) {
+  const int prev = fused_enabled() ? 1 : 0;
+  if (on >= 0) g_fused_on = on ? 1 : 0;
+  return prev;
+}
+
+// Can the block run as the single cooperative kernel?  (output channels in 256-wide column blocks, an identity
+// output mapping, and every tile resident in TMEM: tiles <= 2 * grid with grid a multiple of the column-block count)
+static int fused_grid_for(const TapGemm& g) {
+  if (!fused_enabled() || !tapgemm_tcgen05_supported(g)) return 0;
+  if (g.Nout % kFusedBN != 0 || !g.out_identity) return 0;
+  const long long M = (long long)g.N * g.P * g.Q;
+  const long long tiles = ((M + kBM - 1) / kBM) * (g.Nout / kFusedBN);
+  int sms = device_sm_count();
+  if (sms <= 0) return 0;
+  const int n_tiles = g.Nout / kFusedBN;
+  int grid = sms - sms % n_tiles;
+  if (tiles < grid) grid = (int)(tiles - tiles % n_tiles);
+  if (grid < n_tiles || tiles > 2LL * grid) return 0;
+  return grid;
+}
+
+bool passport_fused_supported(const TapGemm& g) { return fused_grid_for(g) > 0; }
+int passport_fused_grid(const TapGemm& g) { return fused_grid_for(g); }
+
+int passport_fused_tcgen05(const TapGemm& g, const void* act, const void* B, const FusedArgs& a, cudaStream_t s) {
+  PP_TRY(resolve_encoders());
+  const int grid = fused_grid_for(g);
+  PP_REQUIRE(grid > 0, PP_EUNSUPPORTED, "fused passport kernel: geometry not resident in TMEM (M=%d Nout=%d)",
+             g.N * g.P * g.Q, g.Nout);
+  CUtensorMap tmA, tmB;
+  int bw = 0, bh = 0, bn = 0;
+  const bool a_tiled = prefer_tiled() && tiled_box_for(g, kBM, &bw, &bh, &bn);
+  if (a_tiled) PP_TRY(make_map_tiled4d(&tmA, act, g, bw, bh, bn));
+  else PP_TRY(make_map_im2col(&tmA, act, g, kBM));
+  PP_TRY(make_map_2d(&tmB, B, (uint64_t)g.Nout, (uint64_t)g.Ktot, kFusedBN));
+  FusedDev p;
+  memset(&p, 0, sizeof(p));
+  TapGemmDev& d = p.g;
+  d.a_tiled = a_tiled ? 1 : 0;
+  d.M = g.N * g.P * g.Q;
+  d.P = g.P; d.Q = g.Q; d.PQ = g.P * g.Q;
+  d.base_h = g.base_h; d.base_w = g.base_w; d.step_h = g.step_h; d.step_w = g.step_w;
+  d.C = g.C; d.ntaps = g.ntaps; d.Nout = g.Nout;
+  d.num_m_tiles = (d.M + kBM - 1) / kBM;
+  d.num_n_tiles = g.Nout / kFusedBN;
+  d.out_identity = 1;
+  for (int t = 0; t < g.ntaps; ++t) {
+    d.tap_dh[t] = g.tap_dh[t]; d.tap_dw[t] = g.tap_dw[t]; d.tap_kofs[t] = g.tap_kofs[t];
+  }
+  p.y = (__nv_bfloat16*)a.y; p.z = a.z; p.partial = a.partial; p.barrier = a.barrier;
+  p.gamma_in = a.gamma_in; p.beta_in = a.beta_in;
+  p.w_oihw = a.w_oihw; p.Ss = a.Ss; p.Sk = a.Sk; p.Cin = a.Cin; p.T = a.T;
+  p.gamma_out = a.gamma_out; p.beta_out = a.beta_out;
+  p.b_sign = a.b_sign; p.alpha = a.alpha; p.sign_loss = a.sign_loss; p.sign_acc = a.sign_acc;
+  p.rmean = a.rmean; p.rvar = a.rvar; p.save_mean = a.save_mean; p.save_invstd = a.save_invstd;
+  p.eps = a.eps; p.momentum = a.momentum; p.relu = a.relu;
+  p.n_tiles = d.num_n_tiles;
+  PP_REQUIRE(!p.w_oihw || (p.Ss && p.Sk && p.gamma_out && p.beta_out), PP_EBADARG,
+             "fused passport kernel: pooled keys / gamma, beta buffers missing");
+  PP_SET_MAX_SMEM_ONCE((passport_fused_kernel), kFusedSmemBytes);
+  PP_CHECK_CUDA(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned int), s));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kFusedSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  prof_begin(PROF_FUSED, 2.0 * (double)d.M * g.Nout * g.ntaps * g.C, g.C, g.Nout, g.ntaps, s);
+  const cudaError_t err = cudaLaunchKernelEx(&cfg, passport_fused_kernel, tmA, tmB, p);
+  prof_end(PROF_FUSED, s);
+  if (err != cudaSuccess) {
+    set_error("cooperative launch of passport_fused_kernel failed: %s (grid %d)", cudaGetErrorString(err), grid);
+    return PP_ELAUNCH;
+  }
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight gradient, computed transposed:  D[(tap, c), o] = sum over pixels m of x_tap[m, c] * dz[m, o]
 //   A = x_tap : MN-major ((tap, c) contiguous per pixel row), two 64-wide slabs per CTA loaded in im2col mode
 //               (a slab is 64 channels of ONE tap, so C % 64 == 0 keeps slabs from straddling taps)

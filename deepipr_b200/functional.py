@@ -464,6 +464,116 @@ class _ConvBlockFn(torch.autograd.Function):
         return dx, (None if sw else dw), (None if sg else gg), (None if sb else gb), None, None
 
 
+@dataclass
+class PassportCtx:
+    """The passport of a block for the fused operator: pooled keys + signature."""
+    S_skey: torch.Tensor
+    S_key: torch.Tensor
+    b: Optional[torch.Tensor]          # fp32 [O] (+-1) or None (no sign loss fed)
+    alpha: float
+
+
+class _PassportConvFn(torch.autograd.Function):
+    """The passport block as ONE operator: gamma / beta from the passport, SignLoss.add, conv, batch-norm, affine, ReLU
+    (pp_passport_conv_fwd; one cooperative kernel where the output tiles fit in tensor memory) and its backward
+    (pp_passport_conv_bwd).  Reference: passportconv2d.py:142-175 + 209-223, passportconv2d_private.py:139-219,
+    sign_loss.py:32-54."""
+
+    @staticmethod
+    def forward(ctx, x, weight, prepared: PreparedWeight, o: BlockOpts, pc: PassportCtx):
+        spec = o.spec
+        N, Cx, H, W = x.shape
+        if Cx != spec.C:
+            raise RuntimeError(f"input has {Cx} channels, block expects {spec.C}")
+        P, Q = spec.out_hw(H, W)
+        dev = x.device
+        xc = to_nhwc_bf16(x.detach())
+        w = master_weight(weight)
+        need_grad = any(ctx.needs_input_grad[:2])
+        keep_z = need_grad or o.norm in (L.PP_NORM_BN_TRAIN, L.PP_NORM_GN)
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups)
+        y = torch.empty((N, spec.O, P, Q), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        z = torch.empty((N, P, Q, spec.O), dtype=torch.float32 if o.z_f32 else torch.bfloat16, device=dev) \
+            if keep_z else None
+        nstat = N * o.groups if o.norm == L.PP_NORM_GN else spec.O
+        save_mean = torch.empty(nstat, dtype=torch.float32, device=dev)
+        save_invstd = torch.empty(nstat, dtype=torch.float32, device=dev)
+        gamma = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        beta = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        has_b = pc.b is not None
+        stats = torch.zeros(2, dtype=torch.float32, device=dev) if has_b else None      # [sign loss, sign acc]
+        ws, nbytes = workspace(d, key, L.PP_WS_FWD, dev)
+        L.check(L.load().pp_passport_conv_fwd(
+            C.byref(d), L.ptr(xc), L.ptr(prepared.wf), L.ptr(w), L.ptr(pc.S_skey), L.ptr(pc.S_key), None, None,
+            L.ptr(pc.b), float(pc.alpha), L.ptr(o.running_mean), L.ptr(o.running_var), L.ptr(y), L.ptr(z),
+            L.ptr(gamma), L.ptr(beta), L.ptr(save_mean), L.ptr(save_invstd),
+            None if stats is None else C.c_void_p(stats.data_ptr()),
+            None if stats is None else C.c_void_p(stats.data_ptr() + 4),
+            L.ptr(ws), C.c_size_t(nbytes), _stream()), "pp_passport_conv_fwd")
+        if need_grad:
+            ctx.save_for_backward(xc, z, gamma, beta, save_mean, save_invstd)
+            ctx.prepared, ctx.o, ctx.pc = prepared, o, pc
+            ctx.x_dtype = x.dtype
+            ctx.xshape = (N, Cx, H, W)
+            ctx.wshape = weight.shape
+        out_dtype = o.out_dtype or x.dtype
+        if out_dtype != torch.bfloat16:
+            y = y.to(out_dtype)
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            y = y.contiguous()          # keep the input's memory format (see _ConvBlockFn.forward)
+        ctx.mark_non_differentiable(gamma, beta)
+        if has_b:
+            loss, acc = stats[0], stats[1]
+            ctx.mark_non_differentiable(acc)
+            return y, gamma, beta, loss, acc
+        return y, gamma, beta
+
+    @staticmethod
+    def backward(ctx, gy, g_gamma=None, g_beta=None, g_loss=None, g_acc=None):
+        xc, z, gamma, beta, save_mean, save_invstd = ctx.saved_tensors
+        o, spec, pc = ctx.o, ctx.o.spec, ctx.pc
+        N, Cx, H, W = ctx.xshape
+        dev = xc.device
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if gy is None:          # only the sign loss was used downstream
+            gy = torch.zeros((N, spec.O) + spec.out_hw(H, W), dtype=torch.bfloat16, device=dev)
+        gyc = to_nhwc_bf16(gy)
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, 0)
+        dx = torch.empty((N, Cx, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last) \
+            if need_dx else None
+        dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dev) if need_dw else None
+        dgamma = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(spec.O, dtype=torch.float32, device=dev)
+        gl = None if g_loss is None else g_loss.contiguous().float()
+        if need_dx and ctx.prepared.wd is None:
+            raise RuntimeError("deepipr_b200: dgrad weights were not prepared")
+        ws, nbytes = workspace(d, key, L.PP_WS_BWD, dev)
+        if need_dw:
+            L.check(L.load().pp_passport_conv_bwd(
+                C.byref(d), L.ptr(gyc), L.ptr(xc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(gamma), L.ptr(beta),
+                L.ptr(save_mean), L.ptr(save_invstd), L.ptr(pc.S_skey), L.ptr(pc.S_key), L.ptr(pc.b), float(pc.alpha),
+                L.ptr(gl), L.ptr(dx), L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), C.c_size_t(nbytes),
+                _stream()), "pp_passport_conv_bwd")
+        else:                   # frozen weight: plain block backward for dx
+            L.check(L.load().pp_conv_block_bwd(
+                C.byref(d), L.ptr(gyc), L.ptr(xc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(gamma), L.ptr(beta),
+                L.ptr(save_mean), L.ptr(save_invstd), L.ptr(dx), None, L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws),
+                C.c_size_t(nbytes), _stream()), "pp_conv_block_bwd")
+        if dx is not None and ctx.x_dtype != torch.bfloat16:
+            dx = dx.to(ctx.x_dtype)
+        return dx, dw, None, None, None
+
+
+def passport_conv(x, weight, prepared: PreparedWeight, opts: BlockOpts, pc: PassportCtx):
+    """Returns (y, gamma[O], beta[O], sign_loss or None, sign_acc or None)."""
+    require_cuda(x, "block input")
+    require_cuda(weight, "conv weight")
+    out = _PassportConvFn.apply(x, weight, prepared, opts, pc)
+    if len(out) == 3:
+        return out[0], out[1], out[2], None, None
+    return out
+
+
 def conv_block(x, weight, gamma, beta, prepared: PreparedWeight, opts: BlockOpts):
     require_cuda(x, "block input")
     require_cuda(weight, "conv weight")

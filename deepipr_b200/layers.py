@@ -361,6 +361,30 @@ class _PassportBase(nn.Module, _FusedConvMixin):
             loss_module._add_fused(gamma.view(1, -1, 1, 1), loss, acc)
         return gamma, beta
 
+    def _run_passport(self, x, loss_module, relu):
+        """The whole passport block as one operator (F_.passport_conv -> pp_passport_conv_fwd): gamma / beta from the
+        passport, the sign loss fed to ``loss_module`` exactly as get_scale() does, conv, norm, affine, ReLU.
+        Returns None when this call needs the composed path instead (keys being optimised, a norm module without a
+        kernel here)."""
+        F_.require_cuda(x, "passport block input")
+        self._check_conv()
+        norm = _norm_mode(self.bn)
+        key, skey = getattr(self, self._KEY), getattr(self, self._SKEY)
+        if norm is None or key is None or skey is None:
+            return None
+        if torch.is_grad_enabled() and (key.requires_grad or skey.requires_grad):
+            return None
+        S_skey, S_key = self._pooled_keys()
+        b = loss_module.b if loss_module is not None else None
+        pc = F_.PassportCtx(S_skey, S_key, None if b is None else b.detach().reshape(-1).float().contiguous(),
+                            float(loss_module.alpha) if loss_module is not None else 0.0)
+        o = self._bn_opts(norm, relu, self.z_f32, x)
+        y, gamma, beta, loss, acc = F_.passport_conv(x, self.weight, self._prepared(), o, pc)
+        if loss_module is not None:
+            loss_module.reset()
+            loss_module._add_fused(gamma.view(1, -1, 1, 1), loss, acc)
+        return y
+
     def _run(self, x, gamma, beta, relu):
         """conv -> norm -> gamma*x+beta -> relu with per-channel gamma/beta tensors of O elements."""
         F_.require_cuda(x, "passport block input")
@@ -434,6 +458,12 @@ class PassportBlock(_PassportBase):
 
     def forward(self, x, force_passport=False):
         self._maybe_random_key(x)
+        use_scale = self.scale is not None and not force_passport
+        use_bias = self.bias is not None and not force_passport
+        if not use_scale and not use_bias:                 # the plain passport path: one fused operator
+            y = self._run_passport(x, self.sign_loss, self.relu is not None)
+            if y is not None:
+                return y
         gamma, beta = self._affine(force_passport)
         return self._run(x, gamma, beta, self.relu is not None)
 
@@ -482,5 +512,11 @@ class PassportPrivateBlock(_PassportBase):
 
     def forward(self, x, force_passport=False, ind=0):
         self._maybe_random_key(x)
+        use_scale = self.scale is not None and not force_passport and ind == 0
+        use_bias = self.bias is not None and not force_passport and ind == 0
+        if not use_scale and not use_bias:                 # the private passport path: one fused operator
+            y = self._run_passport(x, self.sign_loss_private, True)
+            if y is not None:
+                return y
         gamma, beta = self._affine(force_passport, ind)
         return self._run(x, gamma, beta, True)

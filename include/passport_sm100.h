@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 11
+#define PP_ABI_VERSION 12
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -174,6 +174,45 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
                       const float* save_invstd, void* dx, float* dw_oihw, float* dgamma,
                       float* dbeta, void* workspace, size_t ws_bytes, void* stream);
 
+/* THE PASSPORT BLOCK, forward — PassportBlock.forward (models/layers/passportconv2d.py:209-223) including get_scale /
+ * get_bias (:142-175) and SignLoss.add (models/losses/sign_loss.py:32-54); PassportPrivateBlock.forward
+ * (models/layers/passportconv2d_private.py:205-219) for both values of `ind`:
+ *
+ *   gamma = GAP(conv(W, skey)), beta = GAP(conv(W, key))     or the public scale / bias (ind == 0, no sign loss)
+ *   sign_loss = alpha * sum(relu(0.1 - b * gamma)) + 1e-5 * sum(gamma^2);  sign_acc = mean(sign(b) == sign(gamma))
+ *   y = relu?( gamma * bn(conv(x, W)) + beta ),  running statistics updated in BN_TRAIN
+ *
+ * Where every output tile of the convolution fits in tensor memory (O % 256 == 0 and ceil(N*P*Q / 128) * O / 256 <=
+ * 2 * #SMs: ResNet-18 layer4 up to 1184 CIFAR / 386 ImageNet images per GPU), norm == PP_NORM_BN_TRAIN and z is kept
+ * in fp32, this is ONE cooperative kernel: TMA-staged tiles, tcgen05 contractions with the accumulators resident in
+ * TMEM, gamma / beta rows computed by the idle epilogue warps, per-CTA column statistics, a grid barrier, and
+ * y = relu(a z + b) written straight from TMEM with 128-bit stores.  Otherwise the same result is produced by the
+ * kernel sequence of pp_passport_affine_fwd + pp_conv_block_fwd.
+ *
+ *   w_fprop   bf16 operand copy (pp_weight_prep), w_oihw the fp32 master weight (gamma / beta are taken from it)
+ *   S_skey / S_key  pooled keys (pp_key_pool); ignored when scale_pub / bias_pub are given (both or neither)
+ *   gamma / beta    fp32 [O] outputs on the passport path (the backward needs gamma); untouched on the public path
+ *   sign_loss / sign_acc  device scalars, written on the passport path when b_sign != NULL (may be NULL)
+ *   other arguments as pp_conv_block_fwd. */
+int pp_passport_conv_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, const float* w_oihw,
+                         const double* S_skey, const double* S_key, const float* scale_pub, const float* bias_pub,
+                         const float* b_sign, float alpha, float* running_mean, float* running_var, void* y, void* z,
+                         float* gamma, float* beta, float* save_mean, float* save_invstd, float* sign_loss,
+                         float* sign_acc, void* workspace, size_t ws_bytes, void* stream);
+
+/* THE PASSPORT BLOCK, backward (autograd of the lines above):
+ *   dx = dgrad(W, dz);  dW = wgrad(x, dz) + (dgamma + g_sign_loss * dLsign/dgamma) (x) S_skey + dbeta (x) S_key
+ *   with dLsign/dgamma_o = -alpha b_o [0.1 - b_o gamma_o > 0] + 2e-5 gamma_o,  dgamma = sum dy_m zhat, dbeta = sum dy_m.
+ * Passport path: pass S_skey / S_key (and b_sign, alpha, the device scalar g_sign_loss = upstream gradient of the
+ * sign loss, NULL = 0); dgamma / dbeta are scratch outputs.  Public path (S_skey == S_key == NULL): gamma / beta are
+ * the public scale / bias and dgamma / dbeta their gradients (dscale, dbias).  PP_FLAG_ACC_DW in d->flags adds into
+ * dw_oihw.  Other arguments as pp_conv_block_bwd. */
+int pp_passport_conv_bwd(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad, const void* z,
+                         const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                         const double* S_skey, const double* S_key, const float* b_sign, float alpha,
+                         const float* g_sign_loss, void* dx, float* dw_oihw, float* dgamma, float* dbeta,
+                         void* workspace, size_t ws_bytes, void* stream);
+
 /* Building blocks exposed for tests / profiling (same kernels the two calls above use). */
 int pp_conv_fwd_raw(const PPConvDesc* d, const void* x, const void* w_fprop, void* z, void* workspace,
                     size_t ws_bytes, void* stream); /* z = conv(x,W), dtype per z_f32 */
@@ -211,6 +250,9 @@ int pp_ce_top1(int N, int classes, const void* logits, int logits_bf16, const in
 
 /* Debug: after a kernel-side pipeline timeout the offending barrier id is recorded here. */
 int pp_debug_last_timeout(void);
+/* A/B switch for tests and profiling: on = 0 makes every block take the kernel SEQUENCE even where the single
+ * cooperative kernel applies, on = 1 re-enables it, on < 0 only queries.  Returns the previous setting. */
+int pp_debug_fused(int on);
 
 /* Instrumentation used by bench.py.
  *   pp_launch_count   kernels launched by this library since the last reset (the "gpu_launches" claim)

@@ -1017,3 +1017,79 @@ def test_cuda_graph_step_follows_the_eager_trajectory():
     assert torch.allclose(met1, met0, rtol=1e-5, atol=1e-6)
     for k in bn0:
         assert torch.equal(bn1[k], bn0[k]) if not bn0[k].dtype.is_floating_point else rel_l2(bn1[k], bn0[k]) < 1e-6, k
+
+
+def _private_layer4(seed=7):
+    m = _make_block("private", 512, 512, 3, 1, 1, "bn", 4, seed=seed)
+    with torch.no_grad():
+        m.set_key(torch.rand(1, 512, 4, 4) * 2 - 1, torch.rand(1, 512, 4, 4) * 2 - 1)
+    return m
+
+
+def test_single_kernel_passport_block_equals_the_kernel_sequence_at_full_size():
+    """The one-kernel passport block (pp_passport_conv_fwd: conv + statistics + grid barrier + gamma/beta affine + ReLU
+    from TMEM) against the kernel sequence it replaces (PP debug switch), at the BASELINE geometry: layer4 512->512,
+    4x4 maps, per-GPU batch 1024 + 2 trigger images = 16416 rows = 258 tiles on 148 CTAs (two resident accumulators
+    on 110 of them, a ragged last tile), both passes of the private block, forward and backward."""
+    lib = L.load()
+    N = 1026
+    x = bf16r(torch.randn(N, 512, 4, 4, generator=torch.Generator().manual_seed(3)))
+    res = {}
+    try:
+        for fused in (1, 0):
+            lib.pp_debug_fused(fused)
+            m = _private_layer4().cuda().train()
+            lib.pp_launch_count(1)
+            out = _fwd_bwd(m, "private", x, "cuda", (0, 1))
+            out["launches"] = int(lib.pp_launch_count(0))
+            out["rm"], out["rv"] = m.bn.running_mean.clone().cpu(), m.bn.running_var.clone().cpu()
+            out["acc"] = float(m.sign_loss_private.acc)
+            res[fused] = out
+    finally:
+        lib.pp_debug_fused(1)
+    a, b = res[1], res[0]
+    # passport pass: gemv + sign loss + conv + finalize + affine -> 1 kernel; public pass: conv + finalize + affine -> 1
+    assert a["launches"] <= b["launches"] - 6, (a["launches"], b["launches"])
+    for k in range(2):
+        assert rel_l2(a["y"][k], b["y"][k]) < 2e-4, k           # same arithmetic; 1-ulp flips from the fp32 sum order
+        assert (a["y"][k] != b["y"][k]).float().mean().item() < 2e-3, k
+    assert abs(a["sl"] - b["sl"]) <= 1e-6 * max(1.0, abs(b["sl"])) and a["acc"] == b["acc"]
+    assert rel_l2(a["dx"], b["dx"]) < 1e-3
+    for key, gref in b["grads"].items():
+        assert rel_l2(a["grads"][key], gref) < 1e-3, key
+    assert rel_l2(a["rm"], b["rm"]) < 1e-5 and rel_l2(a["rv"], b["rv"]) < 1e-5
+    # oracle-free property of the fused output: per-channel batch moments of the pre-ReLU activation are (beta, gamma^2)
+    m = _make_block("v1", 512, 512, 3, 1, 1, "bn", 4, relu=False).cuda().train()
+    y = m(x.cuda()).float()
+    with torch.no_grad():
+        gamma, beta = m.get_scale(True).reshape(-1), m.get_bias(True).reshape(-1)
+    assert (y.mean(dim=(0, 2, 3)) - beta).abs().max().item() < 2e-3 * (1 + beta.abs().max().item())
+    assert rel_l2(y.var(dim=(0, 2, 3), unbiased=False), gamma * gamma) < 5e-3
+
+
+@pytest.mark.parametrize("geom", [(1026, 256, 8, 512, 3, 2, 1), (1026, 256, 8, 512, 1, 2, 0), (256, 512, 7, 512, 3, 1, 1),
+                                  (40, 256, 8, 256, 3, 1, 1), (3, 512, 4, 512, 3, 1, 1)])
+def test_single_kernel_block_other_geometries_vs_sequence(geom):
+    """Strided 3x3 and 1x1 passport layers of layer4.0, the ImageNet 7x7 map, one 256-wide column block, a tiny
+    batch: fused kernel == kernel sequence (forward outputs, statistics, gradients) for the V1 block."""
+    lib = L.load()
+    N, C, H, O, k, s, p = geom
+    x = bf16r(torch.randn(N, C, H, H, generator=torch.Generator().manual_seed(5)))
+    res = {}
+    try:
+        for fused in (1, 0):
+            lib.pp_debug_fused(fused)
+            m = _make_block("v1", C, O, k, s, p, "bn", H, seed=9).cuda().train()
+            lib.pp_launch_count(1)
+            res[fused] = _fwd_bwd(m, "v1", x, "cuda", (0,))
+            res[fused]["launches"] = int(lib.pp_launch_count(0))
+            res[fused]["rv"] = m.bn.running_var.clone().cpu()
+    finally:
+        lib.pp_debug_fused(1)
+    a, b = res[1], res[0]
+    assert a["launches"] < b["launches"], "the single-kernel path did not engage"
+    assert rel_l2(a["y"][0], b["y"][0]) < 2e-4
+    assert abs(a["sl"] - b["sl"]) <= 1e-6 * max(1.0, abs(b["sl"]))
+    assert rel_l2(a["dx"], b["dx"]) < 1e-3 and rel_l2(a["rv"], b["rv"]) < 1e-5
+    for key, gref in b["grads"].items():
+        assert rel_l2(a["grads"][key], gref) < 1e-3, key
