@@ -10,7 +10,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpassport_sm100.so")
 
-PP_ABI_VERSION = 12
+PP_ABI_VERSION = 13
 PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL, PP_NORM_GN = 0, 1, 2, 3
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1

@@ -66,7 +66,8 @@ constexpr int kMaxTaps = 49;  // up to 7x7 filters
 // The forward conv, the stride-1 data gradient and every phase of a strided data gradient are all
 // instances of this (see api.cu: plan_fprop / plan_dgrad_phase / plan_col).
 struct TapGemm {
-  // activation tensor, NHWC bf16
+  // activation tensor, NHWC bf16 — or NHWC fp32 read as TF32 when tf32 != 0 (PP_DTYPE_TF32; B is fp32 too then)
+  int tf32;
   int N, H, W, C;
   // traversal grid
   int P, Q;

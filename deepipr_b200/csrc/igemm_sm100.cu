@@ -61,13 +61,14 @@ static int resolve_encoders() {
   return PP_OK;
 }
 
-// 2-D row-major bf16 matrix [rows, cols]; box = box_rows x 64 columns (128 B), 128B swizzle.
-static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D row-major matrix [rows, cols] of bf16 (esz 2) or fp32 (esz 4); box = box_rows x 128 bytes, 128B swizzle.
+static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int esz = 2) {
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {cols * (uint64_t)esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+  CUresult r = g_encode_tiled(m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                              const_cast<void*>(ptr), dims, strides, box,
                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -78,15 +79,17 @@ static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
   return PP_OK;
 }
 
-// NHWC bf16 activation in im2col mode: 64 channels x `pixels` traversal positions per load.
+// NHWC activation (bf16, or fp32 when g.tf32) in im2col mode: 128 bytes of channels x `pixels` traversal positions.
 static int make_map_im2col(CUtensorMap* m, const void* ptr, const TapGemm& g, uint32_t pixels) {
+  const uint64_t esz = g.tf32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
-  cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * esz, (cuuint64_t)g.W * g.C * esz, (cuuint64_t)g.H * g.W * g.C * esz};
   int lower[2] = {g.base_w, g.base_h};
   int upper[2] = {g.upper_w, g.upper_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)g.step_w, (cuuint32_t)g.step_h, 1};
-  CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower,
-                               upper, 64, pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = g_encode_im2col(m, g.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                               const_cast<void*>(ptr), dims, strides, lower, upper, (cuuint32_t)(128 / esz), pixels, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeIm2col failed (%d) NHWC=%d,%d,%d,%d lower=%d,%d upper=%d,%d step=%d,%d", (int)r,
@@ -96,7 +99,7 @@ static int make_map_im2col(CUtensorMap* m, const void* ptr, const TapGemm& g, ui
   // Same driver workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp): on drivers <= 13.1 an
   // im2col descriptor of a tensor smaller than 128 KiB must have bit 21 of its second 64-bit word cleared.
   if (g_driver_version <= 13010) {
-    uint64_t bytes = (uint64_t)g.N * g.H * g.W * g.C * 2;
+    uint64_t bytes = (uint64_t)g.N * g.H * g.W * g.C * esz;
     if (bytes < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
   }
   return PP_OK;
@@ -119,11 +122,13 @@ static bool tiled_box_for(const TapGemm& g, int pixels, int* bw, int* bh, int* b
 }
 
 static int make_map_tiled4d(CUtensorMap* m, const void* ptr, const TapGemm& g, int bw, int bh, int bn) {
+  const uint64_t esz = g.tf32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
-  cuuint64_t strides[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint64_t strides[3] = {(cuuint64_t)g.C * esz, (cuuint64_t)g.W * g.C * esz, (cuuint64_t)g.H * g.W * g.C * esz};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / esz), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = g_encode_tiled(m, g.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                              const_cast<void*>(ptr), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -223,11 +228,16 @@ struct FwdCfg {
       1024 /*align slack*/ + kResBytes + kStages * kStageBytes + kScratch + 256 /*barriers*/;
 };
 
-template <int BN, bool RESB>
+// TF32: activations and weights are fp32 in memory and enter the tensor core as TF32 (tcgen05.mma kind::tf32, K = 8
+// per instruction).  A pipeline stage is still kBM (or BN) rows of ONE 128-byte swizzle row — 32 fp32 channels instead
+// of 64 bf16 ones — so shared-memory layout, descriptors and the 32-byte K advance are unchanged; only the channel
+// count per stage (kBKe), the instruction kind and its descriptor differ.
+template <int BN, bool RESB, bool TF32 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TapGemmDev p) {
   using Cfg = FwdCfg<BN, RESB>;
+  constexpr int kBKe = TF32 ? 32 : kBK;        // channels (elements) per pipeline stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_base = smem;                       // [ksteps][BN x 64] resident weight blocks (RESB only)
@@ -248,7 +258,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int kchunks = p.C / kBK;
+  const int kchunks = p.C / kBKe;
   const int ksteps = p.ntaps * kchunks;
 
   if (warp == 0 && lane == 0) {
@@ -284,7 +294,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_arrive_expect_tx(bres, (uint32_t)ksteps * Cfg::kStageB);
         for (int t = 0; t < p.ntaps; ++t)
           for (int kc = 0; kc < kchunks; ++kc)
-            tma_load_2d(&tmB, bres, res_base + (t * kchunks + kc) * Cfg::kStageB, p.tap_kofs[t] + kc * kBK, 0);
+            tma_load_2d(&tmB, bres, res_base + (t * kchunks + kc) * Cfg::kStageB, p.tap_kofs[t] + kc * kBKe, 0);
       }
       __syncwarp();
     }
@@ -315,9 +325,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               mbar_arrive(&full[stage]);
             } else {
               mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-              if (a_tiled) tma_load_4d(&tmA, &full[stage], sa, kc * kBK, cw + dw, ch + dh, img);
-              else tma_load_im2col_4d(&tmA, &full[stage], sa, kc * kBK, cw, ch, img, (uint16_t)dw, (uint16_t)dh);
-              if (!RESB) tma_load_2d(&tmB, &full[stage], sb, kofs + kc * kBK, n_tile * BN);
+              if (a_tiled) tma_load_4d(&tmA, &full[stage], sa, kc * kBKe, cw + dw, ch + dh, img);
+              else tma_load_im2col_4d(&tmA, &full[stage], sa, kc * kBKe, cw, ch, img, (uint16_t)dw, (uint16_t)dh);
+              if (!RESB) tma_load_2d(&tmB, &full[stage], sb, kofs + kc * kBKe, n_tile * BN);
             }
           }
           __syncwarp();
@@ -329,7 +339,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer =====================
     // Warp-uniform loop; one elected lane issues tcgen05.mma / tcgen05.commit (descriptors stay in uniform registers,
     // so the instructions issue back to back instead of through per-instruction election loops).
-    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    constexpr uint32_t idesc = TF32 ? make_idesc_tf32(kBM, BN, 0, 0) : make_idesc_bf16(kBM, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -352,7 +362,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            if (!(dbg & 8)) tc_mma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+            if (!(dbg & 8)) {
+              if (TF32) tc_mma_tf32(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+              else tc_mma_bf16(d_tmem, da, db, idesc, (ks | k) != 0 ? 1u : 0u);
+            }
           }
           tc_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (ks == ksteps - 1) tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
@@ -516,7 +529,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 bool tapgemm_tcgen05_supported(const TapGemm& g) {
-  if (g.C % 64 != 0 || g.Nout % 64 != 0) return false;
+  if (g.C % (g.tf32 ? 32 : 64) != 0 || g.Nout % 64 != 0) return false;
   if (g.ntaps < 1 || g.ntaps > kMaxTaps) return false;
   if (g.base_h < -128 || g.base_h > 127 || g.base_w < -128 || g.base_w > 127) return false;
   if (g.upper_h < -128 || g.upper_h > 127 || g.upper_w < -128 || g.upper_w > 127) return false;
@@ -541,7 +554,7 @@ static int pick_bn(const TapGemm& g) {
 
 int tapgemm_tcgen05_max_stats_width() { return kMaxStatsN; }
 
-template <int BN, bool RESB>
+template <int BN, bool RESB, bool TF32 = false>
 static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, const TapEpilogue& e, cudaStream_t s) {
   using Cfg = FwdCfg<BN, RESB>;
   CUtensorMap tmA, tmB;
@@ -549,7 +562,7 @@ static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, cons
   const bool a_tiled = prefer_tiled() && tiled_box_for(g, kBM, &bw, &bh, &bn);
   if (a_tiled) PP_TRY(make_map_tiled4d(&tmA, act, g, bw, bh, bn));
   else PP_TRY(make_map_im2col(&tmA, act, g, kBM));
-  PP_TRY(make_map_2d(&tmB, B, (uint64_t)g.Nout, (uint64_t)g.Ktot, BN));
+  PP_TRY(make_map_2d(&tmB, B, (uint64_t)g.Nout, (uint64_t)g.Ktot, BN, TF32 ? 4 : 2));
   TapGemmDev p;
   p.a_tiled = a_tiled ? 1 : 0;
   {
@@ -571,12 +584,12 @@ static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, cons
   p.out = e.out; p.out_f32 = e.out_f32; p.scale = e.scale; p.shift = e.shift; p.relu = e.relu;
   p.stats_partial = e.stats_partial;
 
-  PP_SET_MAX_SMEM_ONCE((tapgemm_kernel<BN, RESB>), Cfg::kSmemBytes);
+  PP_SET_MAX_SMEM_ONCE((tapgemm_kernel<BN, RESB, TF32>), Cfg::kSmemBytes);
   PP_REQUIRE(e.stats_partial == nullptr || g.Nout <= kMaxStatsN, PP_EUNSUPPORTED,
              "fused column statistics support Nout <= %d (Nout=%d)", kMaxStatsN, g.Nout);
   const int grid = tapgemm_tcgen05_grid(g);
   prof_begin(PROF_TAPGEMM, 2.0 * (double)p.M * g.Nout * g.ntaps * g.C, g.C, g.Nout, g.ntaps, s);
-  tapgemm_kernel<BN, RESB><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, p);
+  tapgemm_kernel<BN, RESB, TF32><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmA, tmB, p);
   prof_end(PROF_TAPGEMM, s);
   PP_POST_LAUNCH();
   return PP_OK;
@@ -884,7 +897,7 @@ static bool pxn_enabled() {
 static PxnPlan plan_pxn(const TapGemm& g) {
   PxnPlan pl;
   pl.ok = false;
-  if (!pxn_enabled()) return pl;
+  if (!pxn_enabled() || g.tf32) return pl;     // TF32 layers (AlexNet: 192 / 256 / 384 channels) take tapgemm_kernel
   if (g.step_h != 1 || g.step_w != 1) return pl;
   if (g.C % 64 != 0 || (g.Nout != 64 && g.Nout != 128)) return pl;
   if (g.Q > 256 || g.Q < 1) return pl;
@@ -996,6 +1009,13 @@ int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapE
   {
     PxnPlan pl = plan_pxn(g);
     if (pl.ok) return launch_pxn(g, pl, act, B, e, s);
+  }
+  if (g.tf32) {
+    switch (pick_bn(g)) {
+      case 256: return launch_tapgemm<256, false, true>(g, act, B, e, s);
+      case 128: return launch_tapgemm<128, false, true>(g, act, B, e, s);
+      default: return launch_tapgemm<64, false, true>(g, act, B, e, s);
+    }
   }
   switch (pick_bn(g)) {
     case 256: return launch_tapgemm<256, false>(g, act, B, e, s);
@@ -1208,17 +1228,29 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // (a) passport-derived gamma / beta for the channels this CTA owns (4 warps x 1 channel, strided over the grid);
     //     hidden behind the first tile's main loop
     if (p.w_oihw != nullptr) {
-      const int K = p.Cin * p.T;
+      const int K = p.Cin * p.T;                    // one OIHW row; the pooled patches use the same element order
+      const int n4 = K >> 2;                        // K % 4 == 0 (C % 64 == 0 on this path)
       for (int c = (int)blockIdx.x * 4 + ew; c < g.Nout; c += 4 * grid) {
-        const float* wrow = p.w_oihw + (size_t)c * K;
-        double gsum = 0.0, bsum = 0.0;
-        for (int i = lane; i < K; i += 32) {
-          const int ci = i / p.T;
-          const int k = (i - ci * p.T) * p.Cin + ci;
-          const double w = (double)__ldg(wrow + i);
-          gsum = fma(w, p.Ss[k], gsum);
-          bsum = fma(w, p.Sk[k], bsum);
+        const float4* r4 = reinterpret_cast<const float4*>(p.w_oihw + (size_t)c * K);
+        double g4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+        for (int i = lane; i < n4; i += 32) {
+          const float4 w = __ldg(r4 + i);
+          const double2 s0 = *reinterpret_cast<const double2*>(p.Ss + 4 * i);
+          const double2 s1 = *reinterpret_cast<const double2*>(p.Ss + 4 * i + 2);
+          const double2 k0 = *reinterpret_cast<const double2*>(p.Sk + 4 * i);
+          const double2 k1 = *reinterpret_cast<const double2*>(p.Sk + 4 * i + 2);
+          g4[0] = fma((double)w.x, s0.x, g4[0]);
+          g4[1] = fma((double)w.y, s0.y, g4[1]);
+          g4[2] = fma((double)w.z, s1.x, g4[2]);
+          g4[3] = fma((double)w.w, s1.y, g4[3]);
+          b4[0] = fma((double)w.x, k0.x, b4[0]);
+          b4[1] = fma((double)w.y, k0.y, b4[1]);
+          b4[2] = fma((double)w.z, k1.x, b4[2]);
+          b4[3] = fma((double)w.w, k1.y, b4[3]);
         }
+        double gsum = (g4[0] + g4[1]) + (g4[2] + g4[3]);      // same order as pointwise.cu:passport_row_dot, so the
+        double bsum = (b4[0] + b4[1]) + (b4[2] + b4[3]);      // bits equal those of the stand-alone GEMV kernel
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
           gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
@@ -1445,7 +1477,7 @@ int debug_fused(int on) {
 // Can the block run as the single cooperative kernel?  (output channels in 256-wide column blocks, an identity
 // output mapping, and every tile resident in TMEM: tiles <= 2 * grid with grid a multiple of the column-block count)
 static int fused_grid_for(const TapGemm& g) {
-  if (!fused_enabled() || !tapgemm_tcgen05_supported(g)) return 0;
+  if (!fused_enabled() || g.tf32 || !tapgemm_tcgen05_supported(g)) return 0;
   if (g.Nout % kFusedBN != 0 || !g.out_identity) return 0;
   const long long M = (long long)g.N * g.P * g.Q;
   const long long tiles = ((M + kBM - 1) / kBM) * (g.Nout / kFusedBN);

@@ -65,15 +65,16 @@ int launch_weight_prep(const PPConvDesc& d, const float* w, __nv_bfloat16* wf, _
 }
 
 // ---------------------------------------------------------------------------------------------
-// key pooling: S[t*C + c] = mean_{b,p,q} key[b, c, p*s - pad + r, q*s - pad + s'] (0 outside)
+// key pooling: S[c*T + t] = mean_{b,p,q} key[b, c, p*s - pad + r, q*s - pad + s'] (0 outside), t = r*kw + s'
+// — the element order of one row of the fp32 OIHW master weight, so that gamma = W[o, :] . S is a contiguous dot
 // ---------------------------------------------------------------------------------------------
 __global__ void key_pool_kernel(const float* __restrict__ key, double* __restrict__ S, int Bk, int C, int H, int W,
                                 int kh, int kw, int stride, int pad, int P, int Q) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int T = kh * kw;
   if (idx >= T * C) return;
-  const int c = idx % C;
-  const int t = idx / C;
+  const int t = idx % T;
+  const int c = idx / T;
   const int r = t / kw, sx = t % kw;
   double acc = 0.0;
   for (int b = 0; b < Bk; ++b) {
@@ -106,19 +107,43 @@ int launch_key_pool(const PPConvDesc& d, int Bk, const float* key, double* S, cu
 // signature, and must be the one the reference's fp32 get_scale() yields on the same inputs — the bf16 operand copy
 // the tensor-core convs use is too coarse for that (rounding W and the key flips ~0.1 % of the bits at init).
 // ---------------------------------------------------------------------------------------------
-// lane-strided dot products of OIHW row `row` (i = c*T + t) with pooled patches indexed [t*C + c]
+// Dot products of one OIHW weight row (K = C*T contiguous floats) with the pooled patches (same element order):
+// 128-bit weight loads, four independent fp64 accumulators per lane (the loads of an iteration do not wait for the
+// previous one), combined in a fixed order -> deterministic.
 __device__ __forceinline__ void passport_row_dot(const float* __restrict__ row, const double* __restrict__ Ss,
-                                                 const double* __restrict__ Sk, int C, int T, int lane, double& g,
+                                                 const double* __restrict__ Sk, int K, int lane, double& g,
                                                  double& b) {
-  const int K = C * T;
-  g = 0.0; b = 0.0;
-  for (int i = lane; i < K; i += 32) {
-    const int c = i / T;
-    const int k = (i - c * T) * C + c;
-    const double w = (double)row[i];
-    g = fma(w, Ss[k], g);
-    if (Sk) b = fma(w, Sk[k], b);
+  double g4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
+  if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const int n4 = K >> 2;
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) {
+      const float4 w = __ldg(r4 + i);
+      const double2 s0 = *reinterpret_cast<const double2*>(Ss + 4 * i);
+      const double2 s1 = *reinterpret_cast<const double2*>(Ss + 4 * i + 2);
+      g4[0] = fma((double)w.x, s0.x, g4[0]);
+      g4[1] = fma((double)w.y, s0.y, g4[1]);
+      g4[2] = fma((double)w.z, s1.x, g4[2]);
+      g4[3] = fma((double)w.w, s1.y, g4[3]);
+      if (Sk) {
+        const double2 k0 = *reinterpret_cast<const double2*>(Sk + 4 * i);
+        const double2 k1 = *reinterpret_cast<const double2*>(Sk + 4 * i + 2);
+        b4[0] = fma((double)w.x, k0.x, b4[0]);
+        b4[1] = fma((double)w.y, k0.y, b4[1]);
+        b4[2] = fma((double)w.z, k1.x, b4[2]);
+        b4[3] = fma((double)w.w, k1.y, b4[3]);
+      }
+    }
+  } else {
+    for (int i = lane; i < K; i += 32) {
+      const double w = (double)row[i];
+      g4[i & 3] = fma(w, Ss[i], g4[i & 3]);
+      if (Sk) b4[i & 3] = fma(w, Sk[i], b4[i & 3]);
+    }
   }
+  g = (g4[0] + g4[1]) + (g4[2] + g4[3]);
+  b = (b4[0] + b4[1]) + (b4[2] + b4[3]);
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     g += __shfl_xor_sync(0xffffffffu, g, off);
@@ -133,7 +158,7 @@ __global__ void passport_gemv_kernel(const float* __restrict__ w, const double* 
   const int lane = threadIdx.x & 31;
   if (warp >= O) return;
   double g, b;
-  passport_row_dot(w + (size_t)warp * C * T, Ss, Sk, C, T, lane, g, b);
+  passport_row_dot(w + (size_t)warp * C * T, Ss, Sk, C * T, lane, g, b);
   if (lane == 0) {
     gamma[warp] = (float)g;
     beta[warp] = (float)b;
@@ -155,7 +180,7 @@ __global__ void signature_verify_kernel(const __grid_constant__ SigBatch batch, 
   if (warp >= ly.O) return;
   const int K = ly.K;
   double g, unused;
-  passport_row_dot(ly.w_oihw + (size_t)warp * K, ly.S_skey, nullptr, ly.C, K / ly.C, lane, g, unused);
+  passport_row_dot(ly.w_oihw + (size_t)warp * K, ly.S_skey, nullptr, K, lane, g, unused);
   if (lane == 0) {
     const float gf = (float)g;
     const float sg = (float)((gf > 0.f) - (gf < 0.f));
@@ -249,7 +274,7 @@ int launch_passport_affine_fwd(const PPConvDesc& d, const float* w, const double
   return PP_OK;
 }
 
-// dW[o][c][t] (+)= (gg[o] + gl * dLsign/dgamma[o]) * Ss[t*C+c] + gb[o] * Sk[t*C+c]
+// dW[o][c][t] (+)= (gg[o] + gl * dLsign/dgamma[o]) * Ss[c*T+t] + gb[o] * Sk[c*T+t]
 __global__ void passport_affine_bwd_kernel(const double* __restrict__ Ss, const double* __restrict__ Sk,
                                            const float* __restrict__ gamma, const float* __restrict__ b, float alpha,
                                            const float* __restrict__ gg, const float* __restrict__ gb,
@@ -257,13 +282,12 @@ __global__ void passport_affine_bwd_kernel(const double* __restrict__ Ss, const 
                                            int O, int C, int T) {
   const size_t total = (size_t)O * C * T;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int t = (int)(i % T);
-    const int c = (int)((i / T) % C);
-    const int o = (int)(i / ((size_t)T * C));
+    const size_t K = (size_t)T * C;
+    const int o = (int)(i / K);
+    const int k = (int)(i - (size_t)o * K);              // position inside the OIHW row == index into S
     float cg = gg ? gg[o] : 0.0f;
     if (gl && b) cg += (*gl) * sign_loss_grad(gamma[o], b[o], alpha);
     const float cb = gb ? gb[o] : 0.0f;
-    const int k = t * C + c;
     const float v = (float)((double)cg * Ss[k] + (double)cb * Sk[k]);
     dw[i] = accumulate ? dw[i] + v : v;
   }
@@ -308,18 +332,17 @@ __device__ __forceinline__ bool reduce_partials_32x32(const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // gradients w.r.t. the passport keys (passport_attack_3.py:232-270 optimises them as Parameters):
 //   dS_s[k] = sum_o cg[o] * W[o,k],  dS_k[k] = sum_o cb[o] * W[o,k]     (cg includes the sign-loss term)
-//   dkey[b,c,h,w] = 1/(Bk*P*Q) * sum over taps (r,s) that read pixel (h,w) of dS[(r,s), c]
+//   dkey[b,c,h,w] = 1/(Bk*P*Q) * sum over taps (r,s) that read pixel (h,w) of dS[c, (r,s)]
 // ---------------------------------------------------------------------------------------------
 __global__ void passport_key_grad_gemv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
                                               const float* __restrict__ b, float alpha,
                                               const float* __restrict__ gg, const float* __restrict__ gb,
                                               const float* __restrict__ gl, double* __restrict__ dSs,
                                               double* __restrict__ dSk, int O, int C, int T) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;   // k = t*C + c (pooled-patch order)
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;   // k = c*T + t: OIHW row order, shared by W rows and S
   const int K = C * T;
   if (k >= K) return;
-  const int t = k / C;
-  const int i = (k - t * C) * T + t;                      // the same element in the OIHW row
+  const int i = k;
   double as = 0.0, ak = 0.0;
   for (int o = 0; o < O; ++o) {
     float cg = gg ? gg[o] : 0.0f;
@@ -348,7 +371,7 @@ __global__ void key_unpool_kernel(const double* __restrict__ dS, float* __restri
     for (int sx = 0; sx < kw; ++sx) {
       const int wp = w + pad - sx;
       if (wp < 0 || wp % stride != 0 || wp / stride >= Q) continue;
-      acc += dS[(r * kw + sx) * C + c];
+      acc += dS[c * (kh * kw) + r * kw + sx];
     }
   }
   dkey[idx] = (float)(acc / ((double)Bk * P * Q));

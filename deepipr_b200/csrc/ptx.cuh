@@ -133,6 +133,19 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], fp32 bit patterns read as TF32 (the low 13 mantissa bits are ignored), fp32
+// accumulate, one CTA.  K = 8 per instruction (32 bytes of a 128-byte swizzle row, as for bf16).
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -176,6 +189,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          | (static_cast<uint32_t>(b_mn_major) << 16) // [16]    B major
          | (static_cast<uint32_t>(N >> 3) << 17)     // [17,23) N >> 3
          | (static_cast<uint32_t>(M >> 4) << 24);    // [24,29) M >> 4
+}
+
+// Instruction descriptor for kind::tf32, tf32 x tf32 -> fp32 (format code 2 for A and B).
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

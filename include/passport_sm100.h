@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 12
+#define PP_ABI_VERSION 13
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -88,8 +88,9 @@ int pp_workspace_bytes(const PPConvDesc* d, int which, size_t* bytes);
  * Replaces the implicit weight read of nn.Conv2d (passportconv2d.py:18,218). */
 int pp_weight_prep(const PPConvDesc* d, const float* w_oihw, void* w_fprop, void* w_dgrad, void* stream);
 
-/* S[t*C + c] = mean over key batch and output positions of the (zero padded) key patch
- * element (tap t, channel c); the fp32 key is NOT rounded, accumulation is fp64.
+/* S[c*T + t] (T = kh*kw, t = r*kw + s: the element order of one row of the OIHW weight) = mean over key batch and
+ * output positions of the (zero padded) key patch element (channel c, tap t); the fp32 key is NOT rounded,
+ * accumulation is fp64.
  * With it  GAP(conv(W, key)) == W[O, kh*kw*C] @ S  (SURVEY 7.3), which replaces the two
  * batch-1 cuDNN convs + means of get_scale / get_bias (passportconv2d.py:146-152,167-173).
  * key_nchw: fp32 [Bk, C, H, W] exactly as the module's `key` / `skey` buffers store it. */
@@ -107,7 +108,7 @@ int pp_passport_affine_fwd(const PPConvDesc* d, const float* w_oihw, const doubl
                            float* beta, float* sign_loss, float* sign_acc, void* stream);
 
 /* Gradient of the above w.r.t. the fp32 OIHW weight (rank-1 update):
- *   dW[o,c,r,s] = (g_gamma[o] + g_loss * dLsign/dgamma[o]) * S_skey[(r,s),c] + g_beta[o] * S_key[(r,s),c]
+ *   dW[o,c,r,s] = (g_gamma[o] + g_loss * dLsign/dgamma[o]) * S_skey[c,(r,s)] + g_beta[o] * S_key[c,(r,s)]
  * g_gamma / g_beta / g_loss may each be NULL (treated as 0); g_loss is a device scalar.
  * accumulate != 0 adds into dw_oihw instead of overwriting it. */
 int pp_passport_affine_bwd(const PPConvDesc* d, const double* S_skey, const double* S_key,

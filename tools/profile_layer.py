@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--kind", default="private", choices=["private", "v1", "conv"])
+    ap.add_argument("--no-fused", action="store_true", help="kernel sequence instead of the single-kernel block")
     args = ap.parse_args()
     import torch
     from deepipr_b200 import _lib as L
@@ -52,6 +53,8 @@ def main():
     P = (H + 2 * p - k) // s + 1
     gy = torch.randn(args.batch, O, P, P, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     lib = L.load()
+    if args.no_fused:
+        lib.pp_debug_fused(0)
 
     def step():
         if args.kind == "private":
@@ -78,7 +81,7 @@ def main():
     out = {"layer": args.layer, "batch": args.batch, "kind": args.kind, "ms_per_block_step": e0.elapsed_time(e1) / args.iters}
     flops = 2.0 * args.batch * P * P * O * Ci * k * k
     out["block_tflops_3x"] = 3 * flops / (out["ms_per_block_step"] * 1e-3) / 1e12
-    for kind, name in ((0, "tapgemm"), (1, "wgrad")):
+    for kind, name in ((0, "tapgemm"), (1, "wgrad"), (5, "passport_fused")):
         ms, fl, n = C.c_double(0), C.c_double(0), C.c_int(0)
         lib.pp_profile_read(kind, 0, 0, 0, C.byref(ms), C.byref(fl), C.byref(n))
         if n.value:
