@@ -46,9 +46,15 @@ CONFIGS = {
     "v1_imagenet": dict(net="resnet18", scheme="v1", classes=1000, img=224, batch=256, trigger=False, gflop=10.884,
                         dtype="bf16", workload="ResNet18 V1 passport ImageNet-1k-shaped Trainer step, 7x7/s2 stem + "
                                                "max-pool, lr_configs/imagenet.json schedule (BASELINE configs[4])"),
+    # fp32 tensors end to end, contractions on tcgen05 kind::tf32 (PP_DTYPE_TF32) — what train_v1.py's fp32 run gets
+    # from cuDNN on a GPU; the TF32 tensor peak is half the bf16 one
     "v1_alexnet": dict(net="alexnet", scheme="v1", classes=10, img=32, batch=1024, trigger=False, gflop=1.323,
-                       dtype="bf16", workload="AlexNet V1 passport (features 4/5/6) CIFAR10-shaped Trainer step "
-                                              "(BASELINE configs[1])"),
+                       dtype="tf32", workload="AlexNet V1 passport (features 4/5/6) CIFAR10-shaped Trainer step, fp32 "
+                                              "activations / TF32 tensor cores (BASELINE configs[1])"),
+    "v1_alexnet_bf16": dict(net="alexnet", scheme="v1", classes=10, img=32, batch=1024, trigger=False, gflop=1.323,
+                            dtype="bf16", workload="AlexNet V1 passport (features 4/5/6) CIFAR10-shaped Trainer step "
+                                                   "under autocast(bf16) (not a BASELINE config: precision below the "
+                                                   "reference's fp32)"),
 }
 DEFAULT_CONFIG = "v3_cifar10_trigger"
 CPU_SAMPLE_BATCH = 256             # images of the per-step batch the CPU arms process (bounded sample, see below)
@@ -61,6 +67,12 @@ def peaks():
         return dict(tflops=d.get("bf16_tflops_sustained", 1393.0), tflops_burst=d.get("bf16_tflops", 1665.0),
                     hbm=d.get("hbm_gbs", 6540.0), src="measured")
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback")
+
+
+def tensor_peak(pk, dtype):
+    """Tensor-core peak (TFLOP/s) for a config's arithmetic: the measured sustained bf16 figure; kind::tf32 runs at half
+    the bf16 rate on this part (8 instead of 16 k per instruction at the same issue cost)."""
+    return pk["tflops"] * (0.5 if dtype == "tf32" else 1.0)
 
 
 class ClockSampler:
@@ -350,13 +362,16 @@ def main():
     def make_runner(config_name, batch, graph=False, ddp=True):
         """model + flat SGD + (graphed) step runner for one config; inputs resident in HBM."""
         c = CONFIGS[config_name]
+        from deepipr_b200 import layers as _layers
+        _layers.set_precision("tf32" if c["dtype"] == "tf32" else "bf16")
         model = build_model(config=config_name).to(dev).train()
         if world > 1 and ddp:
             broadcast_state(model)
         flat = FlatParams(model.parameters())
         opt = FlatSGD(flat, lr=0.01, momentum=0.9, weight_decay=1e-4)
         buckets = GradBuckets(flat) if (world > 1 and ddp) else None
-        runner = StepRunner(model, opt, private=c["scheme"] == "private", buckets=buckets, autocast=True)
+        runner = StepRunner(model, opt, private=c["scheme"] == "private", buckets=buckets,
+                            autocast=c["dtype"] == "bf16")
         data = synthetic_batches(c, batch, 4, device=dev, seed=1234 + rank)
         if c["trigger"]:
             wm = trigger_batches(4, device=dev, seed=4321 + rank)
@@ -417,7 +432,8 @@ def main():
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8 + \
         ((wm_host[0][0].numel() * 4 + wm_host[0][1].numel() * 8) if wm_host else 0)
     if "e2e" in legs:
-        trainer = trainer_cls(model, opt, None, dev, buckets=runner.buckets, autocast=True, use_graph=use_graph)
+        trainer = trainer_cls(model, opt, None, dev, buckets=runner.buckets, autocast=cfg["dtype"] == "bf16",
+                              use_graph=use_graph)
         trainer.log_every = 1
         seen = []
         trainer.on_log = lambda n, vals: seen.append(vals)
@@ -535,11 +551,14 @@ def main():
                 v2 = n2 * c["batch"] / (ms2 * 1e-3)
                 configs_out[name] = {"value": v2, "unit": UNIT, "ms_per_step": ms2 / n2, "per_gpu_batch": c["batch"],
                                      "dtype": c["dtype"], "workload": c["workload"],
-                                     "conv_roofline_frac_whole_step": v2 * c["gflop"] * 1e9 / (pk["tflops"] * 1e12)}
+                                     "conv_roofline_frac_whole_step":
+                                         v2 * c["gflop"] * 1e9 / (tensor_peak(pk, c["dtype"]) * 1e12)}
                 del m2, o2, r2, d2, s2
             except Exception as e:          # a config must not take the headline line down with it
                 configs_out[name] = {"error": repr(e)[:300]}
             torch.cuda.empty_cache()
+        from deepipr_b200 import layers as _layers
+        _layers.set_precision("tf32" if cfg["dtype"] == "tf32" else "bf16")
 
     # ---------------- throughput at the reference's own batch sizes (64: train_v1.py:15, 256: training.sh:4):
     # ~650 launches per step make the eager step host-bound there; the CUDA-graph replay is the fix
@@ -614,7 +633,8 @@ def main():
                 "gpu_launches": launches, "cuda_graph": use_graph,
                 "roofline": roof, "roofline_passport_fused": roof_fused, "roofline_wgrad": roof_w,
                 "roofline_hbm": roof_hbm,
-                "conv_roofline_frac_whole_step": (value / world) * cfg["gflop"] * 1e9 / (pk["tflops"] * 1e12),
+                "conv_roofline_frac_whole_step":
+                    (value / world) * cfg["gflop"] * 1e9 / (tensor_peak(pk, cfg["dtype"]) * 1e12),
                 "cpu_baseline": cpu_baseline, "torch_eager_gpu": eager, "reference_trainer_on_patched_blocks": dropin,
                 "small_batch": small, "configs": configs_out, "value_shared_trunk": shared,
                 "sign_bit_accuracy": (sum(sig.values()) / len(sig)) if sig else None, "last_step": last}

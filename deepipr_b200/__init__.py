@@ -13,7 +13,7 @@ import types
 __all__ = ["patch_reference", "layers", "functional", "nets", "trainer", "parallel"]
 
 
-def patch_reference(conv_block=True):
+def patch_reference(conv_block=True, precision=None):
     """Make the reference's own import paths resolve to this package's blocks, so that its models/,
     experiments/ and train_v1.py / train_v23.py run unchanged (call BEFORE importing reference code):
 
@@ -22,8 +22,13 @@ def patch_reference(conv_block=True):
 
     conv_block=False leaves models.layers.conv2d.ConvBlock to the reference (needed for its CPU-only
     plumbing runs such as AlexNet-normal on CPU; the fused blocks here have no CPU path).
+    precision='tf32' runs fp32 inputs through the tcgen05 kind::tf32 kernels with fp32 activations (what the
+    reference's fp32 scripts get from cuDNN: train_v1.py / train_v23.py without autocast); the default 'bf16' converts
+    block inputs to bf16 (layers.set_precision).
     """
     from . import layers
+    if precision is not None:
+        layers.set_precision(precision)
 
     def module(name, **attrs):
         m = types.ModuleType(name)

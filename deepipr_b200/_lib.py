@@ -14,6 +14,7 @@ PP_ABI_VERSION = 13
 PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL, PP_NORM_GN = 0, 1, 2, 3
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1
+PP_DTYPE_BF16, PP_DTYPE_TF32 = 0, 1
 PP_FLAG_ACC_DW, PP_FLAG_ACC_DGAMMA, PP_FLAG_ACC_DBETA = 1, 2, 4
 
 #: every symbol include/passport_sm100.h declares (tests check the .so exports all of them)
@@ -35,7 +36,7 @@ class PPConvDesc(C.Structure):
         ("stride", C.c_int32), ("pad", C.c_int32),
         ("norm", C.c_int32), ("relu", C.c_int32), ("z_f32", C.c_int32),
         ("eps", C.c_float), ("momentum", C.c_float),
-        ("algo", C.c_int32), ("groups", C.c_int32), ("flags", C.c_int32),
+        ("algo", C.c_int32), ("groups", C.c_int32), ("flags", C.c_int32), ("dtype", C.c_int32),
     ]
 
 

@@ -119,12 +119,21 @@ static int geo_of(const PPConvDesc* d, Geo* g) {
   g->T = d->kh * d->kw;
   g->rows = (size_t)d->N * g->P * g->Q;
   PP_REQUIRE(g->rows < (1ull << 31), PP_EBADSHAPE, "too many output pixels");
+  PP_REQUIRE(d->dtype == PP_DTYPE_BF16 || d->dtype == PP_DTYPE_TF32, PP_EBADARG, "unknown dtype %d", d->dtype);
+  PP_REQUIRE(d->dtype != PP_DTYPE_TF32 || d->norm != PP_NORM_GN, PP_EUNSUPPORTED,
+             "group / instance norm blocks are bf16-only (PP_DTYPE_TF32 requested)");
+  PP_REQUIRE(d->dtype != PP_DTYPE_TF32 || d->algo != PP_ALGO_SIMT, PP_EUNSUPPORTED,
+             "the SIMT reference kernels are bf16-only (PP_DTYPE_TF32 requested)");
   return PP_OK;
 }
+
+static inline bool is_tf32(const PPConvDesc& d) { return d.dtype == PP_DTYPE_TF32; }
+static inline size_t act_esz(const PPConvDesc& d) { return is_tf32(d) ? 4 : 2; }   // bytes per x / y / dy / dx / dz element
 
 // forward conv as a tap-GEMM over x (models/layers/passportconv2d.py:18,218)
 static void plan_fprop(const PPConvDesc& d, const Geo& geo, TapGemm& g) {
   memset(&g, 0, sizeof(g));
+  g.tf32 = is_tf32(d) ? 1 : 0;
   g.N = d.N; g.H = d.H; g.W = d.W; g.C = d.C;
   g.P = geo.P; g.Q = geo.Q;
   g.base_h = -d.pad; g.base_w = -d.pad;
@@ -162,6 +171,7 @@ static int plan_dgrad_phase(const PPConvDesc& d, const Geo& geo, int ph, int pw,
   int bh = es_h[0], bw = es_w[0];
   for (int i = 1; i < nh; ++i) bh = es_h[i] < bh ? es_h[i] : bh;
   for (int i = 1; i < nw; ++i) bw = es_w[i] < bw ? es_w[i] : bw;
+  g.tf32 = is_tf32(d) ? 1 : 0;
   g.N = d.N; g.H = geo.P; g.W = geo.Q; g.C = d.O;  // activation of this GEMM is dz
   g.P = Hph; g.Q = Wpw;
   g.base_h = bh; g.base_w = bw; g.step_h = 1; g.step_w = 1;
@@ -191,15 +201,17 @@ static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 // Small-C convolutions (C*kh*kw padded to Kpad, e.g. the 3-channel stem): explicit im2col + 1x1 tap-GEMM.
 static int col_kpad(const PPConvDesc& d, const Geo& geo) {
   if (d.algo == PP_ALGO_SIMT) return 0;
-  if (d.C % 64 == 0 || d.O % 64 != 0) return 0;
+  const int kq = is_tf32(d) ? 32 : 64;   // elements per 128-byte operand row
+  if (d.C % kq == 0 || d.O % 64 != 0) return 0;
   const int K = d.C * geo.T;
   if (K > 1024) return 0;
-  return (K + 63) / 64 * 64;
+  return (K + kq - 1) / kq * kq;
 }
 
 // the explicitly im2col'ed matrix col[rows][Kpad] viewed as a 1 x rows image with Kpad channels
 static void plan_col(const PPConvDesc& d, const Geo& geo, int Kpad, TapGemm& g) {
   memset(&g, 0, sizeof(g));
+  g.tf32 = is_tf32(d) ? 1 : 0;
   g.N = 1; g.H = 1; g.W = (int)geo.rows; g.C = Kpad;
   g.P = 1; g.Q = (int)geo.rows;
   g.base_h = 0; g.base_w = 0; g.step_h = 1; g.step_w = 1; g.upper_h = 0; g.upper_w = 0;
@@ -216,7 +228,7 @@ static size_t gn_partial_rows(const PPConvDesc& d, const Geo& geo) {
 
 struct FwdWs {
   float* ca; float* cb; float* partial;
-  __nv_bfloat16* col; __nv_bfloat16* wpad;
+  void* col; void* wpad;   // small-C im2col scratch (element type per d.dtype)
   unsigned int* barrier;   // grid-barrier counter of the single-kernel block
   size_t total;
 };
@@ -231,8 +243,8 @@ static FwdWs carve_fwd(const PPConvDesc& d, const Geo& geo, void* base) {
   if (d.norm == PP_NORM_GN) max_part = gn_partial_rows(d, geo);
   w.partial = reinterpret_cast<float*>(p + off); off += align256(max_part * 2 * d.O * 4);
   const int Kpad = col_kpad(d, geo);
-  w.col = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * (size_t)Kpad * 2);
-  w.wpad = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256((size_t)d.O * Kpad * 2);
+  w.col = p + off; off += align256(geo.rows * (size_t)Kpad * act_esz(d));
+  w.wpad = p + off; off += align256((size_t)d.O * Kpad * act_esz(d));
   w.barrier = reinterpret_cast<unsigned int*>(p + off); off += 256;
   w.total = off;
   return w;
@@ -240,7 +252,7 @@ static FwdWs carve_fwd(const PPConvDesc& d, const Geo& geo, void* base) {
 
 struct BwdWs {
   float* ca; float* cb; float* k1; float* k2; float* k3; float* partial; float* contrib;
-  __nv_bfloat16* dz; __nv_bfloat16* col; float* wpartial;
+  void* dz; void* col; float* wpartial;   // dz / col: element type per d.dtype
   size_t total;
 };
 static BwdWs carve_bwd(const PPConvDesc& d, const Geo& geo, void* base, int wg_splits) {
@@ -257,9 +269,9 @@ static BwdWs carve_bwd(const PPConvDesc& d, const Geo& geo, void* base, int wg_s
   const size_t part_rows = gn ? gn_partial_rows(d, geo) : (size_t)bwd_reduce_max_partials();
   w.partial = reinterpret_cast<float*>(p + off); off += align256(part_rows * 2 * d.O * 4);
   w.contrib = reinterpret_cast<float*>(p + off); off += gn ? align256((size_t)d.N * 2 * d.O * 4) : 0;
-  w.dz = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * d.O * 2);
+  w.dz = p + off; off += align256(geo.rows * d.O * act_esz(d));
   const int Kpad = col_kpad(d, geo);
-  w.col = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(geo.rows * (size_t)Kpad * 2);
+  w.col = p + off; off += align256(geo.rows * (size_t)Kpad * act_esz(d));
   const size_t krow = Kpad ? (size_t)Kpad : (size_t)geo.T * d.C;
   w.wpartial = reinterpret_cast<float*>(p + off);
   off += align256((size_t)wg_splits * d.O * krow * 4);
@@ -287,7 +299,7 @@ static int wgrad_splits_for(const PPConvDesc& d, const Geo& geo, bool* tc) {
 // scratch: col / wpad are only touched on the small-C im2col path (may be NULL otherwise)
 // *stats_rows (optional) receives the number of rows of e.stats_partial the kernel wrote (0: none)
 static int run_fprop(const PPConvDesc& d, const Geo& geo, const void* x, const void* wf, const TapEpilogue& e,
-                     bool* used_tc, __nv_bfloat16* col, __nv_bfloat16* wpad, cudaStream_t s,
+                     bool* used_tc, void* col, void* wpad, cudaStream_t s,
                      int* stats_rows = nullptr) {
   TapGemm g;
   if (stats_rows) *stats_rows = 0;
@@ -298,8 +310,8 @@ static int run_fprop(const PPConvDesc& d, const Geo& geo, const void* x, const v
   }
   const int Kpad = col_kpad(d, geo);
   if (Kpad && col && wpad) {
-    PP_TRY(launch_im2col_small(d, (const __nv_bfloat16*)x, col, geo.rows, geo.P, geo.Q, Kpad, s));
-    PP_TRY(launch_pad_rows((const __nv_bfloat16*)wf, wpad, d.O, geo.T * d.C, Kpad, s));
+    PP_TRY(launch_im2col_small(d, x, col, geo.rows, geo.P, geo.Q, Kpad, s));
+    PP_TRY(launch_pad_rows(wf, wpad, d.O, geo.T * d.C, Kpad, is_tf32(d) ? 1 : 0, s));
     plan_col(d, geo, Kpad, g);
     if (used_tc) *used_tc = true;
     if (stats_rows && e.stats_partial) *stats_rows = tapgemm_tcgen05_grid(g);
@@ -314,6 +326,8 @@ static int run_fprop(const PPConvDesc& d, const Geo& geo, const void* x, const v
     if (stats_rows && e.stats_partial) *stats_rows = tapgemm_tcgen05_grid(g);
     return tapgemm_tcgen05(g, x, wf, e, s);
   }
+  PP_REQUIRE(!is_tf32(d), PP_EUNSUPPORTED, "PP_DTYPE_TF32 conv needs C%%32==0 (or C*kh*kw <= 1024) and O%%64==0 (C=%d O=%d)",
+             d.C, d.O);
   TapEpilogue e2 = e;
   e2.stats_partial = nullptr;
   return tapgemm_simt(g, x, wf, e2, s);
@@ -329,11 +343,14 @@ static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
       if (ph >= d.H || pw >= d.W) continue;
       if (plan_dgrad_phase(d, geo, ph, pw, phases[nph])) ++nph; else any_empty = true;
     }
-  if (any_empty) PP_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)d.N * d.H * d.W * d.C * 2, s));
+  if (any_empty) PP_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)d.N * d.H * d.W * d.C * act_esz(d), s));
   for (int i = 0; i < nph; ++i) {
     TapEpilogue e;
-    e.out = dx; e.out_f32 = 0; e.scale = nullptr; e.shift = nullptr; e.relu = 0; e.stats_partial = nullptr;
+    e.out = dx; e.out_f32 = is_tf32(d) ? 1 : 0; e.scale = nullptr; e.shift = nullptr; e.relu = 0;
+    e.stats_partial = nullptr;
     const bool tc = use_tcgen05(d, tapgemm_tcgen05_supported(phases[i]));
+    PP_REQUIRE(tc || !is_tf32(d), PP_EUNSUPPORTED, "PP_DTYPE_TF32 data gradient needs O%%32==0 and C%%64==0 (C=%d O=%d)",
+               d.C, d.O);
     PP_REQUIRE(tc || d.algo != PP_ALGO_TCGEN05 || d.C % 64 != 0, PP_EUNSUPPORTED,
                "PP_ALGO_TCGEN05 requested but dgrad unsupported");
     if (tc) PP_TRY(tapgemm_tcgen05(phases[i], dz, wd, e, s));
@@ -343,7 +360,7 @@ static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
 }
 
 static int run_wgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const void* x, float* dw, float* wpartial,
-                     __nv_bfloat16* col, int splits, bool tc, cudaStream_t s, int accumulate = 0) {
+                     void* col, int splits, bool tc, cudaStream_t s, int accumulate = 0) {
   TapGemm g;
   if (stem_direct_supported(d)) {
     PP_TRY(stem_wgrad(d, x, dz, wpartial, s));
@@ -351,12 +368,14 @@ static int run_wgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
   }
   const int Kpad = col_kpad(d, geo);
   if (Kpad && col) {
-    PP_TRY(launch_im2col_small(d, (const __nv_bfloat16*)x, col, geo.rows, geo.P, geo.Q, Kpad, s));
+    PP_TRY(launch_im2col_small(d, x, col, geo.rows, geo.P, geo.Q, Kpad, s));
     plan_col(d, geo, Kpad, g);
     PP_TRY(wgrad_tcgen05(g, col, dz, d.O, wpartial, splits, s));
     return launch_wgrad_finalize(d, wpartial, splits, Kpad, dw, s, accumulate);
   }
   plan_fprop(d, geo, g);
+  PP_REQUIRE(tc || !is_tf32(d), PP_EUNSUPPORTED, "PP_DTYPE_TF32 weight gradient needs C%%32==0 and O%%64==0 (C=%d O=%d)",
+             d.C, d.O);
   if (tc) PP_TRY(wgrad_tcgen05(g, x, dz, d.O, wpartial, splits, s));
   else PP_TRY(wgrad_simt(g, x, dz, d.O, wpartial, splits, s));
   return launch_wgrad_finalize(d, wpartial, splits, geo.T * d.C, dw, s, accumulate);
@@ -368,7 +387,7 @@ static int run_wgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
 static int try_fused_block(const PPConvDesc& d, const Geo& geo, const void* x, const void* wf, const FwdWs& ws,
                            FusedArgs a, cudaStream_t s, bool* done) {
   *done = false;
-  if (d.norm != PP_NORM_BN_TRAIN || !a.z || !d.z_f32 || d.algo == PP_ALGO_SIMT) return PP_OK;
+  if (d.norm != PP_NORM_BN_TRAIN || !a.z || !d.z_f32 || d.algo == PP_ALGO_SIMT || is_tf32(d)) return PP_OK;
   if (stem_direct_supported(d) || col_kpad(d, geo)) return PP_OK;
   TapGemm g;
   plan_fprop(d, geo, g);
@@ -423,7 +442,7 @@ int pp_weight_prep(const PPConvDesc* d, const float* w_oihw, void* w_fprop, void
   PP_TRY(geo_of(d, &geo));
   PP_TRY(check_device());
   PP_REQUIRE(w_oihw && w_fprop, PP_EBADARG, "weight pointers are NULL");
-  return launch_weight_prep(*d, w_oihw, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad, (cudaStream_t)stream);
+  return launch_weight_prep(*d, w_oihw, w_fprop, w_dgrad, (cudaStream_t)stream);
 }
 
 int pp_key_pool(const PPConvDesc* d, int Bk, const float* key_nchw, double* S, void* stream) {
@@ -517,6 +536,8 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
              "group / instance norm needs save_mean / save_invstd [N*groups]");
   PP_REQUIRE(d->norm != PP_NORM_BN_EVAL || (running_mean && running_var), PP_EBADARG, "BN eval needs running stats");
   PP_REQUIRE(d->norm != PP_NORM_BN_TRAIN || z, PP_EBADARG, "BN train needs the z buffer");
+  PP_REQUIRE(!is_tf32(*d) || !z || d->z_f32, PP_EBADARG, "PP_DTYPE_TF32 keeps z in fp32 (set z_f32)");
+  const int af32 = is_tf32(*d) ? 1 : 0;
   FwdWs ws = carve_fwd(*d, geo, workspace);
   PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "fwd workspace too small: need %zu, got %zu", ws.total,
              ws_bytes);
@@ -525,7 +546,7 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
     PP_TRY(launch_bn_finalize(*d, (int)geo.rows, nullptr, 0, gamma, beta, running_mean, running_var, save_mean,
                               save_invstd, ws.ca, ws.cb, s));
     TapEpilogue e;
-    e.out = y; e.out_f32 = 0; e.scale = ws.ca; e.shift = ws.cb; e.relu = d->relu; e.stats_partial = nullptr;
+    e.out = y; e.out_f32 = af32; e.scale = ws.ca; e.shift = ws.cb; e.relu = d->relu; e.stats_partial = nullptr;
     return run_fprop(*d, geo, x, w_fprop, e, nullptr, ws.col, ws.wpad, s);
   }
   {
@@ -559,8 +580,8 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
                             save_mean, save_invstd, ws.ca, ws.cb, s));
   // algorithmic bytes of the pass: read z once, write y (bf16) once
   const double zb = d->z_f32 ? 4.0 : 2.0;
-  prof_begin(PROF_AFFINE, (double)geo.rows * d->O * (zb + 2.0), d->C, d->O, geo.T, s);
-  const int rc = launch_affine_apply(z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, (__nv_bfloat16*)y, s);
+  prof_begin(PROF_AFFINE, (double)geo.rows * d->O * (zb + (double)act_esz(*d)), d->C, d->O, geo.T, s);
+  const int rc = launch_affine_apply(z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, y, af32, s);
   prof_end(PROF_AFFINE, s);
   return rc;
 }
@@ -576,6 +597,9 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
   PP_REQUIRE(dy && z && save_mean && save_invstd && dgamma && dbeta, PP_EBADARG, "conv block bwd: NULL pointer");
   PP_REQUIRE(!dx || w_dgrad, PP_EBADARG, "dx requested without w_dgrad");
   PP_REQUIRE(!dw_oihw || x, PP_EBADARG, "dw requested without x");
+  PP_REQUIRE(!is_tf32(*d) || d->z_f32, PP_EBADARG, "PP_DTYPE_TF32 keeps z in fp32 (set z_f32)");
+  const int af32 = is_tf32(*d) ? 1 : 0;
+  const double ab = (double)act_esz(*d);
   bool wg_tc = false;
   const int splits = wgrad_splits_for(*d, geo, &wg_tc);
   BwdWs ws = carve_bwd(*d, geo, workspace, splits);
@@ -586,7 +610,8 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
     PP_TRY(launch_gn_bwd_reduce(*d, HW, (const __nv_bfloat16*)dy, z, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb,
                                 ws.k1, ws.k2, ws.k3, ws.partial, ws.contrib, dgamma, dbeta, s));
     if (!dx && !dw_oihw) return PP_OK;
-    PP_TRY(launch_gn_dz(*d, HW, (const __nv_bfloat16*)dy, z, ws.ca, ws.cb, ws.k1, ws.k2, ws.k3, ws.dz, s));
+    PP_TRY(launch_gn_dz(*d, HW, (const __nv_bfloat16*)dy, z, ws.ca, ws.cb, ws.k1, ws.k2, ws.k3, (__nv_bfloat16*)ws.dz,
+                        s));
     if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));
     if (dw_oihw)
       PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s, d->flags & PP_FLAG_ACC_DW));
@@ -595,17 +620,17 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
   PP_TRY(launch_affine_coef(d->O, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb, s));
   int num_partials = 0;
   const double zb = d->z_f32 ? 4.0 : 2.0;
-  prof_begin(PROF_REDUCE, (double)geo.rows * d->O * (zb + 2.0), d->C, d->O, geo.T, s);   // read dy + z
-  const int rc_red = launch_bwd_reduce((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu,
-                                       ws.partial, &num_partials, s);
+  prof_begin(PROF_REDUCE, (double)geo.rows * d->O * (zb + ab), d->C, d->O, geo.T, s);   // read dy + z
+  const int rc_red = launch_bwd_reduce(dy, af32, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.partial,
+                                       &num_partials, s);
   prof_end(PROF_REDUCE, s);
   PP_TRY(rc_red);
   PP_TRY(launch_bwd_coef(*d, geo.rows, ws.partial, num_partials, gamma, save_mean, save_invstd, dgamma, dbeta, ws.k1,
                          ws.k2, ws.k3, s));
   if (!dx && !dw_oihw) return PP_OK;
-  prof_begin(PROF_DZ, (double)geo.rows * d->O * (zb + 4.0), d->C, d->O, geo.T, s);       // read dy + z, write dz
-  const int rc_dz = launch_bwd_dz((const __nv_bfloat16*)dy, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.k1,
-                                  ws.k2, ws.k3, ws.dz, s);
+  prof_begin(PROF_DZ, (double)geo.rows * d->O * (zb + 2.0 * ab), d->C, d->O, geo.T, s);   // read dy + z, write dz
+  const int rc_dz = launch_bwd_dz(dy, af32, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.k1, ws.k2, ws.k3,
+                                  ws.dz, s);
   prof_end(PROF_DZ, s);
   PP_TRY(rc_dz);
   if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));

@@ -146,7 +146,7 @@ int stem_fprop(const PPConvDesc& d, const void* x, const void* wf, const TapEpil
 int stem_wgrad(const PPConvDesc& d, const void* x, const void* dz, float* partial /*[grid][64][27]*/, cudaStream_t s);
 
 // --- pointwise.cu ---
-int launch_weight_prep(const PPConvDesc& d, const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s);
+int launch_weight_prep(const PPConvDesc& d, const float* w, void* wf, void* wd, cudaStream_t s);  // element type per d.dtype
 int launch_key_pool(const PPConvDesc& d, int Bk, const float* key, double* S, cudaStream_t s);
 int launch_passport_affine_fwd(const PPConvDesc& d, const float* w_oihw, const double* Ss, const double* Sk,
                                const float* b, float alpha, float* gamma, float* beta, float* loss, float* acc,
@@ -169,23 +169,23 @@ int launch_bn_finalize(const PPConvDesc& d, int n_per_channel, const float* stat
 int launch_affine_coef(int O, const float* gamma, const float* beta, const float* mean, const float* invstd,
                        float* ca, float* cb, cudaStream_t s);
 int launch_affine_apply(const void* z, int z_f32, size_t rows, int O, const float* a, const float* b, int relu,
-                        __nv_bfloat16* y, cudaStream_t s);
+                        void* y, int y_f32, cudaStream_t s);
 int launch_col_stats(const void* z, int z_f32, size_t rows, int O, float* partial, int* num_partials,
                      cudaStream_t s);
-int launch_bwd_reduce(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
+int launch_bwd_reduce(const void* dy, int dy_f32, const void* z, int z_f32, size_t rows, int O, const float* a,
                       const float* b, int relu, float* partial, int* num_partials, cudaStream_t s);
 int bwd_reduce_max_partials();
 int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int num_partials, const float* gamma,
                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* k1,
                     float* k2, float* k3, cudaStream_t s);
-int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
-                  const float* b, int relu, const float* k1, const float* k2, const float* k3, __nv_bfloat16* dz,
+int launch_bwd_dz(const void* dy, int act_f32 /*dy and dz*/, const void* z, int z_f32, size_t rows, int O, const float* a,
+                  const float* b, int relu, const float* k1, const float* k2, const float* k3, void* dz,
                   cudaStream_t s);
 int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, int kstride, float* dw_oihw,
                           cudaStream_t s, int accumulate = 0);
-int launch_im2col_small(const PPConvDesc& d, const __nv_bfloat16* x, __nv_bfloat16* col, size_t rows, int P, int Q,
-                        int Kpad, cudaStream_t s);
-int launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int K, int Kpad, cudaStream_t s);
+int launch_im2col_small(const PPConvDesc& d, const void* x, void* col, size_t rows, int P, int Q, int Kpad,
+                        cudaStream_t s);   // element type per d.dtype
+int launch_pad_rows(const void* src, void* dst, int rows, int K, int Kpad, int f32, cudaStream_t s);
 int launch_add_relu_fwd(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, size_t n, cudaStream_t s);
 int launch_add_relu_bwd(const __nv_bfloat16* g, const __nv_bfloat16* y, __nv_bfloat16* gx, size_t n, cudaStream_t s);
 // --- groupnorm.cu (GroupNorm / InstanceNorm: per-(sample, group) statistics, per-(sample, channel) coefficients) ---

@@ -62,14 +62,18 @@ static int resolve_encoders() {
 }
 
 // 2-D row-major matrix [rows, cols] of bf16 (esz 2) or fp32 (esz 4); box = box_rows x 128 bytes, 128B swizzle.
-static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int esz = 2) {
+// `mn32`: SWIZZLE_128B_ATOM_32B instead of SWIZZLE_128B — the only shared-memory layout tcgen05 accepts for MN-major
+// operands of 4-byte types (UMMA layout type 128B_BASE32B: 32-byte chunks XORed with the row index mod 4).
+static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int esz = 2,
+                       bool mn32 = false) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * (uint64_t)esz};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode_tiled(m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                               const_cast<void*>(ptr), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              mn32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u", (int)r,
@@ -80,7 +84,7 @@ static int make_map_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t 
 }
 
 // NHWC activation (bf16, or fp32 when g.tf32) in im2col mode: 128 bytes of channels x `pixels` traversal positions.
-static int make_map_im2col(CUtensorMap* m, const void* ptr, const TapGemm& g, uint32_t pixels) {
+static int make_map_im2col(CUtensorMap* m, const void* ptr, const TapGemm& g, uint32_t pixels, bool mn32 = false) {
   const uint64_t esz = g.tf32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
   cuuint64_t strides[3] = {(cuuint64_t)g.C * esz, (cuuint64_t)g.W * g.C * esz, (cuuint64_t)g.H * g.W * g.C * esz};
@@ -89,7 +93,8 @@ static int make_map_im2col(CUtensorMap* m, const void* ptr, const TapGemm& g, ui
   cuuint32_t estr[4] = {1, (cuuint32_t)g.step_w, (cuuint32_t)g.step_h, 1};
   CUresult r = g_encode_im2col(m, g.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                                const_cast<void*>(ptr), dims, strides, lower, upper, (cuuint32_t)(128 / esz), pixels, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               mn32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeIm2col failed (%d) NHWC=%d,%d,%d,%d lower=%d,%d upper=%d,%d step=%d,%d", (int)r,
@@ -1563,12 +1568,22 @@ int passport_fused_tcgen05(const TapGemm& g, const void* act, const void* B, con
 // ------------------------------------------------------------------------------------------------
 constexpr int kWK = 64;  // pixels per stage
 
-template <int BN>
+// TF32 (fp32 x / dz): MN-major operands of a 4-byte type must use the 128B_BASE32B layout — 128-byte rows (32 channels)
+// whose 32-byte chunks are swizzled with the row index mod 4 (TMA SWIZZLE_128B_ATOM_32B), 4-row k groups 512 B apart.
+// A slab is then 32 channels wide: four x slabs fill the 128 accumulator rows, BN/32 dz slabs the columns, a stage is
+// 32 pixels and one kind::tf32 instruction contracts 8 of them (1024 B further down every slab).
+template <int BN, bool TF32 = false>
 struct WgCfg {
-  static constexpr int kStageA = 2 * kWK * 128;          // 16 KiB: two 64-wide (tap, c) slabs
-  static constexpr int kStageB = (BN / 64) * kWK * 128;  // 8 / 16 / 32 KiB
+  static constexpr int kSlabElems = TF32 ? 32 : 64;      // (tap, c) / o entries per 128-byte row
+  static constexpr int kPix = TF32 ? 32 : kWK;           // pixels per stage
+  static constexpr int kSlabBytes = kPix * 128;
+  static constexpr int kSlabsA = 128 / kSlabElems;
+  static constexpr int kSlabsB = BN / kSlabElems;
+  static constexpr int kStageA = kSlabsA * kSlabBytes;   // 16 KiB
+  static constexpr int kStageB = kSlabsB * kSlabBytes;   // 8 / 16 / 32 KiB
   static constexpr int kStageBytes = kStageA + kStageB;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kPixPerMma = TF32 ? 8 : 16;
   static constexpr int kTmemCols = BN;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
 };
@@ -1584,11 +1599,11 @@ struct WgradDev {
   float* partial;  // [splits][O][Ktot]
 };
 
-template <int BN>
+template <int BN, bool TF32 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDz,
              const __grid_constant__ WgradDev p) {
-  using Cfg = WgCfg<BN>;
+  using Cfg = WgCfg<BN, TF32>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -1629,18 +1644,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
   if (warp == 0) {
     // TMA producer: warp-uniform loop, one elected lane issues the copies
-    // the two A slabs of this tile: rows [k0, k0+64) and [k1, k1+64) of the (tap, c) axis
-    int k0 = m_tile * 128, k1 = k0 + 64;
-    if (k1 >= p.Ktot) k1 = k0;  // odd slab count: load slab 0 twice (its rows are not stored)
-    const int tap0 = k0 / p.C, c0 = k0 - tap0 * p.C;
-    const int tap1 = k1 / p.C, c1 = k1 - tap1 * p.C;
-    const int dw0 = p.tap_dw[tap0], dh0 = p.tap_dh[tap0];
-    const int dw1 = p.tap_dw[tap1], dh1 = p.tap_dh[tap1];
+    // the A slabs of this tile: rows [k_i, k_i + kSlabElems) of the (tap, c) axis, k_i = m_tile*128 + i*kSlabElems
+    int c0[Cfg::kSlabsA], dw[Cfg::kSlabsA], dh[Cfg::kSlabsA];
+#pragma unroll
+    for (int i = 0; i < Cfg::kSlabsA; ++i) {
+      int k = m_tile * 128 + i * Cfg::kSlabElems;
+      if (k >= p.Ktot) k = m_tile * 128;   // past the end: load slab 0 again (its rows are not stored)
+      const int tap = k / p.C;
+      c0[i] = k - tap * p.C;
+      dw[i] = p.tap_dw[tap];
+      dh[i] = p.tap_dh[tap];
+    }
     const int x_tiled = p.x_tiled;
     int stage = 0;
     uint32_t phase = 0;
     for (int ch = chunk_lo; ch < chunk_lo + nchunks; ++ch) {
-      const int m0 = ch * kWK;
+      const int m0 = ch * Cfg::kPix;
       const int img = m0 / p.PQ;
       const int rem = m0 - img * p.PQ;
       const int p0 = rem / p.Q;
@@ -1652,23 +1671,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kStageA;
         mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-        if (x_tiled) {
-          tma_load_4d(&tmX, &full[stage], sa, c0, cw + dw0, chh + dh0, img);
-          tma_load_4d(&tmX, &full[stage], sa + kWK * 128, c1, cw + dw1, chh + dh1, img);
-        } else {
-          tma_load_im2col_4d(&tmX, &full[stage], sa, c0, cw, chh, img, (uint16_t)dw0, (uint16_t)dh0);
-          tma_load_im2col_4d(&tmX, &full[stage], sa + kWK * 128, c1, cw, chh, img, (uint16_t)dw1, (uint16_t)dh1);
+#pragma unroll
+        for (int i = 0; i < Cfg::kSlabsA; ++i) {
+          if (x_tiled) tma_load_4d(&tmX, &full[stage], sa + i * Cfg::kSlabBytes, c0[i], cw + dw[i], chh + dh[i], img);
+          else tma_load_im2col_4d(&tmX, &full[stage], sa + i * Cfg::kSlabBytes, c0[i], cw, chh, img, (uint16_t)dw[i],
+                                  (uint16_t)dh[i]);
         }
 #pragma unroll
-        for (int i = 0; i < BN / 64; ++i)
-          tma_load_2d(&tmDz, &full[stage], sb + i * kWK * 128, n_tile * BN + i * 64, m0);
+        for (int i = 0; i < Cfg::kSlabsB; ++i)
+          tma_load_2d(&tmDz, &full[stage], sb + i * Cfg::kSlabBytes, n_tile * BN + i * Cfg::kSlabElems, m0);
       }
       __syncwarp();
       if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // MMA issuer: warp-uniform loop, one elected lane issues tcgen05.mma / commit
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    constexpr uint32_t idesc = TF32 ? make_idesc_tf32(128, BN, 1, 1) : make_idesc_bf16(128, BN, 1, 1);
     const uint32_t smem0 = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
@@ -1679,11 +1697,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       const uint32_t sb = sa + Cfg::kStageA;
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kWK / 16; ++k) {
-          // 16 pixels (k) per instruction = two 8-row groups of 1024 B; MN slabs are kWK*128 B apart
-          const uint64_t da = make_smem_desc_sw128(sa + k * 2048, kWK * 128, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb + k * 2048, kWK * 128, 1024);
-          tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < Cfg::kPix / Cfg::kPixPerMma; ++k) {
+          if (TF32) {
+            // 8 pixels (k) per instruction = two 4-row groups of 512 B; MN slabs are kSlabBytes apart
+            const uint64_t da = make_smem_desc_mn32(sa + k * 1024, Cfg::kSlabBytes, 512);
+            const uint64_t db = make_smem_desc_mn32(sb + k * 1024, Cfg::kSlabBytes, 512);
+            tc_mma_tf32(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          } else {
+            // 16 pixels (k) per instruction = two 8-row groups of 1024 B; MN slabs are kSlabBytes apart
+            const uint64_t da = make_smem_desc_sw128(sa + k * 2048, Cfg::kSlabBytes, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * 2048, Cfg::kSlabBytes, 1024);
+            tc_mma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
         }
         tc_commit(&empty[stage]);
         if (it == nchunks - 1) tc_commit(tfull);
@@ -1730,7 +1755,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 }
 
 bool wgrad_tcgen05_supported(const TapGemm& g, int O) {
-  if (g.C % 64 != 0 || O % 64 != 0) return false;
+  if (g.C % (g.tf32 ? 32 : 64) != 0 || O % 64 != 0) return false;
   if (g.base_h < -128 || g.base_w < -128 || g.upper_h < -128 || g.upper_w < -128) return false;
   if (g.base_h > 127 || g.base_w > 127 || g.upper_h > 127 || g.upper_w > 127) return false;
   for (int t = 0; t < g.ntaps; ++t)
@@ -1748,7 +1773,8 @@ int wgrad_pick_splits(const TapGemm& g, int O) {
   const int tiles = wgrad_om_paired(g, O) ? 2
                     : wgrad_om_applies(g, O) ? (Ktot / 64 + 3) / 4 : ((Ktot + 127) / 128) * (O / wgrad_bn(O));
   const long long M = (long long)g.N * g.P * g.Q;
-  const int chunks = (int)((M + kWK - 1) / kWK);
+  const int pix = g.tf32 ? 32 : kWK;
+  const int chunks = (int)((M + pix - 1) / pix);
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
   int splits = (2 * sms) / tiles;          // two full waves when the tile count allows it
@@ -1760,32 +1786,32 @@ int wgrad_pick_splits(const TapGemm& g, int O) {
   return splits;
 }
 
-template <int BN>
+template <int BN, bool TF32 = false>
 static int launch_wgrad(const TapGemm& g, const void* x, const void* dz, int O, float* partial, int splits,
                         cudaStream_t s) {
-  using Cfg = WgCfg<BN>;
+  using Cfg = WgCfg<BN, TF32>;
   CUtensorMap tmDz, tmX;
   const long long M = (long long)g.N * g.P * g.Q;
-  PP_TRY(make_map_2d(&tmDz, dz, (uint64_t)M, (uint64_t)O, kWK));
+  PP_TRY(make_map_2d(&tmDz, dz, (uint64_t)M, (uint64_t)O, Cfg::kPix, TF32 ? 4 : 2, TF32));
   int bw = 0, bh = 0, bn = 0;
-  const bool x_tiled = prefer_tiled() && tiled_box_for(g, kWK, &bw, &bh, &bn);
+  const bool x_tiled = !TF32 && prefer_tiled() && tiled_box_for(g, kWK, &bw, &bh, &bn);
   if (x_tiled) PP_TRY(make_map_tiled4d(&tmX, x, g, bw, bh, bn));
-  else PP_TRY(make_map_im2col(&tmX, x, g, kWK));
+  else PP_TRY(make_map_im2col(&tmX, x, g, Cfg::kPix, TF32));
   WgradDev p;
   p.x_tiled = x_tiled ? 1 : 0;
   p.M = (int)M; p.P = g.P; p.Q = g.Q; p.PQ = g.P * g.Q;
   p.base_h = g.base_h; p.base_w = g.base_w; p.step_h = g.step_h; p.step_w = g.step_w;
   p.C = g.C; p.O = O; p.ntaps = g.ntaps; p.Ktot = g.ntaps * g.C;
   p.n_tiles = O / BN;
-  p.chunks_total = (int)((M + kWK - 1) / kWK);
+  p.chunks_total = (int)((M + Cfg::kPix - 1) / Cfg::kPix);
   p.chunks_per_split = (p.chunks_total + splits - 1) / splits;
   for (int t = 0; t < g.ntaps; ++t) { p.tap_dh[t] = g.tap_dh[t]; p.tap_dw[t] = g.tap_dw[t]; }
   p.partial = partial;
-  PP_SET_MAX_SMEM_ONCE((wgrad_kernel<BN>), Cfg::kSmemBytes);
+  PP_SET_MAX_SMEM_ONCE((wgrad_kernel<BN, TF32>), Cfg::kSmemBytes);
   const int m_tiles = (p.Ktot + 127) / 128;
   dim3 grid(m_tiles * p.n_tiles, splits);
   prof_begin(PROF_WGRAD, 2.0 * (double)M * O * g.ntaps * g.C, g.C, O, g.ntaps, s);
-  wgrad_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmX, tmDz, p);
+  wgrad_kernel<BN, TF32><<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmX, tmDz, p);
   prof_end(PROF_WGRAD, s);
   PP_POST_LAUNCH();
   return PP_OK;
@@ -1990,7 +2016,7 @@ wgrad_om_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 static bool wgrad_om_applies(const TapGemm& g, int O) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("PP_NO_WGRAD_OM"); off = (e && e[0] == '1') ? 1 : 0; }
-  return !off && (O == 64 || O == 128) && g.C % 64 == 0;
+  return !off && !g.tf32 && (O == 64 || O == 128) && g.C % 64 == 0;
 }
 
 // tap pairing needs: O == C == 64, canonical 3x3 / stride 1 / pad 1 tap list, and chunks of kWK pixels that are whole
@@ -2047,6 +2073,13 @@ int wgrad_tcgen05(const TapGemm& g, const void* x, const void* dz, int O, float*
   PP_TRY(resolve_encoders());
   PP_REQUIRE(wgrad_tcgen05_supported(g, O), PP_EUNSUPPORTED, "tcgen05 wgrad needs C%%64==0 and O%%64==0 (C=%d O=%d)",
              g.C, O);
+  if (g.tf32) {
+    switch (wgrad_bn(O)) {
+      case 256: return launch_wgrad<256, true>(g, x, dz, O, partial, splits, s);
+      case 128: return launch_wgrad<128, true>(g, x, dz, O, partial, splits, s);
+      default: return launch_wgrad<64, true>(g, x, dz, O, partial, splits, s);
+    }
+  }
   if (wgrad_om_applies(g, O)) return launch_wgrad_om(g, x, dz, O, partial, splits, s);
   switch (wgrad_bn(O)) {
     case 256: return launch_wgrad<256>(g, x, dz, O, partial, splits, s);

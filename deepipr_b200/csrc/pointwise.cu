@@ -57,9 +57,28 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
-int launch_weight_prep(const PPConvDesc& d, const float* w, __nv_bfloat16* wf, __nv_bfloat16* wd, cudaStream_t s) {
+// TF32 mode: the same two layouts in fp32 (the tensor core reads the upper 19 bits of every element)
+__global__ void weight_prep_f32_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd,
+                                       int O, int C, int T) {
+  const size_t total = (size_t)O * C * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int t = (int)((i / C) % T);
+    const int o = (int)(i / ((size_t)C * T));
+    const float v = w[((size_t)o * C + c) * T + t];
+    wf[i] = v;
+    if (wd) wd[((size_t)c * T + t) * O + o] = v;
+  }
+}
+
+int launch_weight_prep(const PPConvDesc& d, const float* w, void* wf, void* wd, cudaStream_t s) {
   const size_t total = (size_t)d.O * d.C * d.kh * d.kw;
-  weight_prep_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(w, wf, wd, d.O, d.C, d.kh * d.kw);
+  if (d.dtype == PP_DTYPE_TF32)
+    weight_prep_f32_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(w, (float*)wf, (float*)wd, d.O, d.C,
+                                                                          d.kh * d.kw);
+  else
+    weight_prep_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, d.O,
+                                                                      d.C, d.kh * d.kw);
   PP_POST_LAUNCH();
   return PP_OK;
 }
@@ -465,9 +484,10 @@ int launch_affine_coef(int O, const float* gamma, const float* beta, const float
 // ---------------------------------------------------------------------------------------------
 // affine + ReLU pass: y[r, o] = relu(a[o]*z[r,o] + b[o]); 8 channels (one 128-bit bf16 vector) per thread
 // ---------------------------------------------------------------------------------------------
+template <bool AF32>
 __global__ void affine_apply_kernel(const void* __restrict__ z, int z_f32, size_t nvec, int O,
                                     const float* __restrict__ a, const float* __restrict__ b, int relu,
-                                    __nv_bfloat16* __restrict__ y) {
+                                    void* __restrict__ y) {
   const int vec_per_row = O >> 3;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -489,8 +509,8 @@ __global__ void affine_apply_kernel(const void* __restrict__ z, int z_f32, size_
         v1[k] = fmaf(v1[k], ca[k], cb[k]);
         if (relu) { v0[k] = fmaxf(v0[k], 0.0f); v1[k] = fmaxf(v1[k], 0.0f); }
       }
-      store8_bf16(y, i, v0);
-      store8_bf16(y, i + stride, v1);
+      store8(y, AF32, i, v0);
+      store8(y, AF32, i + stride, v1);
     }
     if (i < nvec) {
       float v[8];
@@ -500,7 +520,7 @@ __global__ void affine_apply_kernel(const void* __restrict__ z, int z_f32, size_
         v[k] = fmaf(v[k], ca[k], cb[k]);
         if (relu) v[k] = fmaxf(v[k], 0.0f);
       }
-      store8_bf16(y, i, v);
+      store8(y, AF32, i, v);
     }
     return;
   }
@@ -515,17 +535,21 @@ __global__ void affine_apply_kernel(const void* __restrict__ z, int z_f32, size_
       v[k] = fmaf(v[k], ca[k], cb[k]);
       if (relu) v[k] = fmaxf(v[k], 0.0f);
     }
-    store8_bf16(y, i, v);
+    store8(y, AF32, i, v);
   }
 }
 
 int launch_affine_apply(const void* z, int z_f32, size_t rows, int O, const float* a, const float* b, int relu,
-                        __nv_bfloat16* y, cudaStream_t s) {
+                        void* y, int y_f32, cudaStream_t s) {
   PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "affine pass needs O%%8==0 (O=%d)", O);
   const size_t nvec = rows * (size_t)(O / 8);
-  static int occ = 0;
-  affine_apply_kernel<<<streaming_grid(affine_apply_kernel, &occ, nvec, 256, O / 8), 256, 0, s>>>(z, z_f32, nvec, O, a,
-                                                                                                 b, relu, y);
+  static int occ[2] = {0, 0};
+  if (y_f32)
+    affine_apply_kernel<true><<<streaming_grid(affine_apply_kernel<true>, &occ[1], nvec, 256, O / 8), 256, 0, s>>>(
+        z, z_f32, nvec, O, a, b, relu, y);
+  else
+    affine_apply_kernel<false><<<streaming_grid(affine_apply_kernel<false>, &occ[0], nvec, 256, O / 8), 256, 0, s>>>(
+        z, z_f32, nvec, O, a, b, relu, y);
   PP_POST_LAUNCH();
   return PP_OK;
 }
@@ -541,8 +565,8 @@ int bwd_reduce_max_partials() { return kRedMaxBlocks; }
 // Shared skeleton of the per-channel column reductions: each thread owns one 8-channel vector column
 // and a row lane; rows are strided over (row lanes x blocks); row lanes are combined through shared
 // memory in a fixed order.  MODE 0: (sum z, sum z^2).  MODE 1: (sum dy_m, sum dy_m*z).
-template <int MODE>
-__global__ void column_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ z, int z_f32,
+template <int MODE, bool AF32>
+__global__ void column_reduce_kernel(const void* __restrict__ dy, const void* __restrict__ z, int z_f32,
                                      size_t rows, int O, const float* __restrict__ a, const float* __restrict__ b,
                                      int relu, float* __restrict__ partial) {
   extern __shared__ float s_part[];  // [row_lanes][2][O]
@@ -581,8 +605,8 @@ __global__ void column_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
         }
       } else {
         float g0[8], g1[8];
-        load8_bf16(dy, v0, g0);
-        load8_bf16(dy, v1, g1);
+        load8(dy, AF32, v0, g0);
+        load8(dy, AF32, v1, g1);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float gm = g0[k];
@@ -611,7 +635,7 @@ __global__ void column_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
         }
       } else {
         float g[8];
-        load8_bf16(dy, vi, g);
+        load8(dy, AF32, vi, g);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float gm = g[k];
@@ -635,37 +659,29 @@ __global__ void column_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
   }
 }
 
-static int column_reduce_launch(int mode, const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O,
-                                const float* a, const float* b, int relu, float* partial, int* num_partials,
-                                cudaStream_t s) {
-  PP_REQUIRE(O % 8 == 0 && O / 8 <= kRedThreads, PP_EBADSHAPE, "column reduce needs O%%8==0 and O<=2048 (O=%d)", O);
+template <int MODE, bool AF32>
+static int column_reduce_launch_t(const void* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
+                                  const float* b, int relu, float* partial, int* num_partials, cudaStream_t s) {
   const int vec_per_row = O / 8;
   const int row_lanes = kRedThreads / vec_per_row;
   const size_t smem = (size_t)row_lanes * 2 * O * sizeof(float);
   // one wave: every block gets the same share of rows, so a partial second wave would cost a full one
-  static int occ[2] = {0, 0};
-  if (occ[mode] <= 0) {
+  static int occ = 0;
+  if (occ <= 0) {
     int o = 0;
-    cudaError_t e = mode == 0
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, column_reduce_kernel<0>, kRedThreads, smem)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, column_reduce_kernel<1>, kRedThreads, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, column_reduce_kernel<MODE, AF32>, kRedThreads, smem);
     if (e != cudaSuccess || o < 1) { cudaGetLastError(); o = 2; }
-    occ[mode] = o;
+    occ = o;
   }
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  size_t max_blocks = (size_t)sms * occ[mode];
+  size_t max_blocks = (size_t)sms * occ;
   if (max_blocks > (size_t)kRedMaxBlocks) max_blocks = kRedMaxBlocks;
   size_t blocks = (rows + row_lanes - 1) / row_lanes;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
-  if (mode == 0) {
-    PP_SET_MAX_SMEM_ONCE((column_reduce_kernel<0>), 64 * 1024);
-    column_reduce_kernel<0><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, relu, partial);
-  } else {
-    PP_SET_MAX_SMEM_ONCE((column_reduce_kernel<1>), 64 * 1024);
-    column_reduce_kernel<1><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, relu, partial);
-  }
+  PP_SET_MAX_SMEM_ONCE((column_reduce_kernel<MODE, AF32>), 64 * 1024);
+  column_reduce_kernel<MODE, AF32><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, relu, partial);
   PP_POST_LAUNCH();
   *num_partials = (int)blocks;
   return PP_OK;
@@ -673,12 +689,15 @@ static int column_reduce_launch(int mode, const __nv_bfloat16* dy, const void* z
 
 int launch_col_stats(const void* z, int z_f32, size_t rows, int O, float* partial, int* num_partials,
                      cudaStream_t s) {
-  return column_reduce_launch(0, nullptr, z, z_f32, rows, O, nullptr, nullptr, 0, partial, num_partials, s);
+  PP_REQUIRE(O % 8 == 0 && O / 8 <= kRedThreads, PP_EBADSHAPE, "column reduce needs O%%8==0 and O<=2048 (O=%d)", O);
+  return column_reduce_launch_t<0, false>(nullptr, z, z_f32, rows, O, nullptr, nullptr, 0, partial, num_partials, s);
 }
 
-int launch_bwd_reduce(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
+int launch_bwd_reduce(const void* dy, int dy_f32, const void* z, int z_f32, size_t rows, int O, const float* a,
                       const float* b, int relu, float* partial, int* num_partials, cudaStream_t s) {
-  return column_reduce_launch(1, dy, z, z_f32, rows, O, a, b, relu, partial, num_partials, s);
+  PP_REQUIRE(O % 8 == 0 && O / 8 <= kRedThreads, PP_EBADSHAPE, "column reduce needs O%%8==0 and O<=2048 (O=%d)", O);
+  if (dy_f32) return column_reduce_launch_t<1, true>(dy, z, z_f32, rows, O, a, b, relu, partial, num_partials, s);
+  return column_reduce_launch_t<1, false>(dy, z, z_f32, rows, O, a, b, relu, partial, num_partials, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -723,10 +742,11 @@ int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int 
   return PP_OK;
 }
 
-__global__ void bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const void* __restrict__ z, int z_f32,
+template <bool AF32>
+__global__ void bwd_dz_kernel(const void* __restrict__ dy, const void* __restrict__ z, int z_f32,
                               size_t nvec, int O, const float* __restrict__ a, const float* __restrict__ b, int relu,
                               const float* __restrict__ k1, const float* __restrict__ k2,
-                              const float* __restrict__ k3, __nv_bfloat16* __restrict__ dz) {
+                              const float* __restrict__ k3, void* __restrict__ dz) {
   const int vec_per_row = O >> 3;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -744,8 +764,8 @@ __global__ void bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const void* 
       float z0[8], z1[8], g0[8], g1[8], o0[8], o1[8];
       load8(z, z_f32, i, z0);
       load8(z, z_f32, i + stride, z1);
-      load8_bf16(dy, i, g0);
-      load8_bf16(dy, i + stride, g1);
+      load8(dy, AF32, i, g0);
+      load8(dy, AF32, i + stride, g1);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float gm0 = g0[k], gm1 = g1[k];
@@ -754,20 +774,20 @@ __global__ void bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const void* 
         o0[k] = fmaf(c1[k], gm0, fmaf(c2[k], z0[k], c3[k]));
         o1[k] = fmaf(c1[k], gm1, fmaf(c2[k], z1[k], c3[k]));
       }
-      store8_bf16(dz, i, o0);
-      store8_bf16(dz, i + stride, o1);
+      store8(dz, AF32, i, o0);
+      store8(dz, AF32, i + stride, o1);
     }
     if (i < nvec) {
       float zv[8], g[8], out[8];
       load8(z, z_f32, i, zv);
-      load8_bf16(dy, i, g);
+      load8(dy, AF32, i, g);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float gm = g[k];
         if (relu && !(fmaf(zv[k], ca[k], cb[k]) > 0.0f)) gm = 0.0f;
         out[k] = fmaf(c1[k], gm, fmaf(c2[k], zv[k], c3[k]));
       }
-      store8_bf16(dz, i, out);
+      store8(dz, AF32, i, out);
     }
     return;
   }
@@ -775,7 +795,7 @@ __global__ void bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const void* 
     const int ch = (int)(i % vec_per_row) << 3;
     float zv[8], g[8], ca[8], cb[8], c1[8], c2[8], c3[8], out[8];
     load8(z, z_f32, i, zv);
-    load8_bf16(dy, i, g);
+    load8(dy, AF32, i, g);
     load8_coef(a, ch, ca);
     load8_coef(b, ch, cb);
     load8_coef(k1, ch, c1);
@@ -787,18 +807,22 @@ __global__ void bwd_dz_kernel(const __nv_bfloat16* __restrict__ dy, const void* 
       if (relu && !(fmaf(zv[k], ca[k], cb[k]) > 0.0f)) gm = 0.0f;
       out[k] = fmaf(c1[k], gm, fmaf(c2[k], zv[k], c3[k]));
     }
-    store8_bf16(dz, i, out);
+    store8(dz, AF32, i, out);
   }
 }
 
-int launch_bwd_dz(const __nv_bfloat16* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
-                  const float* b, int relu, const float* k1, const float* k2, const float* k3, __nv_bfloat16* dz,
+int launch_bwd_dz(const void* dy, int act_f32, const void* z, int z_f32, size_t rows, int O, const float* a,
+                  const float* b, int relu, const float* k1, const float* k2, const float* k3, void* dz,
                   cudaStream_t s) {
   PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "dz pass needs O%%8==0 (O=%d)", O);
   const size_t nvec = rows * (size_t)(O / 8);
-  static int occ = 0;
-  bwd_dz_kernel<<<streaming_grid(bwd_dz_kernel, &occ, nvec, 256, O / 8), 256, 0, s>>>(dy, z, z_f32, nvec, O, a, b, relu,
-                                                                                     k1, k2, k3, dz);
+  static int occ[2] = {0, 0};
+  if (act_f32)
+    bwd_dz_kernel<true><<<streaming_grid(bwd_dz_kernel<true>, &occ[1], nvec, 256, O / 8), 256, 0, s>>>(
+        dy, z, z_f32, nvec, O, a, b, relu, k1, k2, k3, dz);
+  else
+    bwd_dz_kernel<false><<<streaming_grid(bwd_dz_kernel<false>, &occ[0], nvec, 256, O / 8), 256, 0, s>>>(
+        dy, z, z_f32, nvec, O, a, b, relu, k1, k2, k3, dz);
   PP_POST_LAUNCH();
   return PP_OK;
 }
@@ -1017,26 +1041,76 @@ __global__ void im2col_small_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
   }
 }
 
-int launch_im2col_small(const PPConvDesc& d, const __nv_bfloat16* x, __nv_bfloat16* col, size_t rows, int P, int Q,
-                        int Kpad, cudaStream_t s) {
-  const size_t total = rows * (size_t)(Kpad / 8);
-  im2col_small_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(x, col, rows, d.H, d.W, d.C, d.kh, d.kw, d.stride,
-                                                                    d.pad, P, Q, Kpad);
+// fp32 variant (TF32 mode): 4 columns (one 128-bit vector) per thread
+__global__ void im2col_small_f32_kernel(const float* __restrict__ x, float* __restrict__ col, size_t rows, int H, int W,
+                                        int C, int kh, int kw, int stride, int pad, int P, int Q, int Kpad) {
+  __shared__ int s_off[1024];
+  const int K = kh * kw * C;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int v = -1;
+    if (k < K) {
+      const int t = k / C, c = k - t * C;
+      v = ((t / kw) << 20) | ((t % kw) << 12) | c;
+    }
+    s_off[k] = v;
+  }
+  __syncthreads();
+  const int groups = Kpad >> 2;
+  const size_t total = rows * groups;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int kg = (int)(i % groups);
+    const size_t m = i / groups;
+    float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (s_off[kg * 4] >= 0) {
+      const int q = (int)(m % Q);
+      const int p = (int)((m / Q) % P);
+      const size_t img = m / ((size_t)P * Q);
+      const int h0 = p * stride - pad, w0 = q * stride - pad;
+      const float* xi = x + img * (size_t)H * W * C;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = s_off[kg * 4 + j];
+        if (e >= 0) {
+          const int h = h0 + (e >> 20), w = w0 + ((e >> 12) & 0xff), c = e & 0xfff;
+          if (h >= 0 && h < H && w >= 0 && w < W) v[j] = __ldg(xi + ((size_t)h * W + w) * C + c);
+        }
+      }
+    }
+    reinterpret_cast<float4*>(col)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+int launch_im2col_small(const PPConvDesc& d, const void* x, void* col, size_t rows, int P, int Q, int Kpad,
+                        cudaStream_t s) {
+  if (d.dtype == PP_DTYPE_TF32) {
+    const size_t total = rows * (size_t)(Kpad / 4);
+    im2col_small_f32_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(
+        (const float*)x, (float*)col, rows, d.H, d.W, d.C, d.kh, d.kw, d.stride, d.pad, P, Q, Kpad);
+  } else {
+    const size_t total = rows * (size_t)(Kpad / 8);
+    im2col_small_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)col, rows, d.H, d.W, d.C, d.kh, d.kw, d.stride, d.pad, P, Q, Kpad);
+  }
   PP_POST_LAUNCH();
   return PP_OK;
 }
 
-__global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
-                                int K, int Kpad) {
+template <typename T>
+__global__ void pad_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, int K, int Kpad) {
   const int total = rows * Kpad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / Kpad, k = i - r * Kpad;
-    dst[i] = k < K ? src[(size_t)r * K + k] : __float2bfloat16_rn(0.0f);
+    dst[i] = k < K ? src[(size_t)r * K + k] : T(0.0f);
   }
 }
 
-int launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, int rows, int K, int Kpad, cudaStream_t s) {
-  pad_rows_kernel<<<grid_for((size_t)rows * Kpad, 256, 1024), 256, 0, s>>>(src, dst, rows, K, Kpad);
+int launch_pad_rows(const void* src, void* dst, int rows, int K, int Kpad, int f32, cudaStream_t s) {
+  if (f32)
+    pad_rows_kernel<float><<<grid_for((size_t)rows * Kpad, 256, 1024), 256, 0, s>>>((const float*)src, (float*)dst, rows,
+                                                                                   K, Kpad);
+  else
+    pad_rows_kernel<__nv_bfloat16><<<grid_for((size_t)rows * Kpad, 256, 1024), 256, 0, s>>>(
+        (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, rows, K, Kpad);
   PP_POST_LAUNCH();
   return PP_OK;
 }

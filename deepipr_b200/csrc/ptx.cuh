@@ -180,6 +180,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   return d;
 }
 
+// MN-major operand of a 4-byte type (TF32): layout 128B_BASE32B — rows (one per k) of 128 B = 32 MN elements whose
+// 32-byte chunks are XORed with (row & 3) (TMA SWIZZLE_128B_ATOM_32B), 4-row k groups SBO apart, 32-element MN slabs
+// LBO apart.
+__device__ __forceinline__ uint64_t make_smem_desc_mn32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;                            // descriptor version = 1 (sm_100)
+  d |= static_cast<uint64_t>(1) << 61;                            // layout = SWIZZLE_128B_BASE32B
+  return d;
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                                   // [4,6)   D format  = F32

@@ -44,7 +44,7 @@ bool stem_direct_supported(const PPConvDesc& d) {
     const char* e = getenv("PP_STEM_DIRECT");   // =0 restores the im2col + tensor-core path (A/B comparison)
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  return enabled && d.algo != PP_ALGO_SIMT && d.C == 3 && d.O == kStemO && d.kh == 3 && d.kw == 3 && d.stride == 1 &&
+  return enabled && d.algo != PP_ALGO_SIMT && d.dtype == PP_DTYPE_BF16 && d.C == 3 && d.O == kStemO && d.kh == 3 && d.kw == 3 && d.stride == 1 &&
          d.pad == 1;
 }
 

@@ -33,6 +33,16 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, size_t vec_idx, co
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
   reinterpret_cast<uint4*>(p)[vec_idx] = u;
 }
+// activation-typed store: fp32 (two 128-bit stores) when f32 != 0, else one bf16 vector
+__device__ __forceinline__ void store8(void* p, int f32, size_t vec_idx, const float (&v)[8]) {
+  if (f32) {
+    float4* q = reinterpret_cast<float4*>(p) + vec_idx * 2;
+    q[0] = make_float4(v[0], v[1], v[2], v[3]);
+    q[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    store8_bf16(reinterpret_cast<__nv_bfloat16*>(p), vec_idx, v);
+  }
+}
 __device__ __forceinline__ void load8_coef(const float* c, int ch, float (&v)[8]) {
   const float4 x0 = __ldg(reinterpret_cast<const float4*>(c + ch));
   const float4 x1 = __ldg(reinterpret_cast<const float4*>(c + ch + 4));

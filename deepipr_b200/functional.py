@@ -66,14 +66,14 @@ def weight_epoch():
 
 
 def make_desc(spec: ConvSpec, N, H, W, norm=L.PP_NORM_NONE, relu=0, z_f32=0, eps=1e-5, momentum=0.1, algo=None,
-              groups=0, flags=0):
+              groups=0, flags=0, dtype=L.PP_DTYPE_BF16):
     algo = ALGO if algo is None else algo
-    key = (spec, N, H, W, norm, relu, z_f32, eps, momentum, algo, groups, flags)
+    key = (spec, N, H, W, norm, relu, z_f32, eps, momentum, algo, groups, flags, dtype)
     d = _desc_cache.get(key)
     if d is None:
         d = L.PPConvDesc(N=N, C=spec.C, H=H, W=W, O=spec.O, kh=spec.kh, kw=spec.kw, stride=spec.stride, pad=spec.pad,
                          norm=norm, relu=int(relu), z_f32=int(z_f32), eps=eps, momentum=momentum, algo=algo,
-                         groups=int(groups), flags=int(flags))
+                         groups=int(groups), flags=int(flags), dtype=int(dtype))
         _desc_cache[key] = d
         if len(_desc_cache) > 4096:
             _desc_cache.clear()
@@ -103,26 +103,41 @@ def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     return x.contiguous(memory_format=torch.channels_last)
 
 
+def act_dtype(dtype: int) -> torch.dtype:
+    """Element type of x / y / dy / dx for a PP_DTYPE_* arithmetic type."""
+    return torch.float32 if dtype == L.PP_DTYPE_TF32 else torch.bfloat16
+
+
+def to_nhwc(x: torch.Tensor, dtype: int) -> torch.Tensor:
+    """Dense NHWC memory in the activation type of `dtype` (bf16, or fp32 for PP_DTYPE_TF32); no copy if it already is."""
+    t = act_dtype(dtype)
+    if x.dtype != t:
+        x = x.to(t)
+    return x.contiguous(memory_format=torch.channels_last)
+
+
 @dataclass
 class PreparedWeight:
-    wf: torch.Tensor                 # bf16 [O, kh, kw, C]
-    wd: Optional[torch.Tensor]       # bf16 [C, kh, kw, O] or None
+    wf: torch.Tensor                 # [O, kh, kw, C], bf16 (fp32 for PP_DTYPE_TF32)
+    wd: Optional[torch.Tensor]       # [C, kh, kw, O] or None
     version: int = -1
     data_ptr: int = 0
     epoch: int = -1
+    dtype: int = L.PP_DTYPE_BF16
 
 
-def prepare_weight(weight: torch.Tensor, spec: ConvSpec, need_dgrad: bool) -> PreparedWeight:
-    """fp32 OIHW master weight -> bf16 operand copies (pp_weight_prep)."""
+def prepare_weight(weight: torch.Tensor, spec: ConvSpec, need_dgrad: bool, dtype: int = L.PP_DTYPE_BF16) -> PreparedWeight:
+    """fp32 OIHW master weight -> operand copies in the two layouts the tensor-core kernels read (pp_weight_prep)."""
     require_cuda(weight, "conv weight")
     w = weight.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
-    wf = torch.empty((spec.O, spec.kh, spec.kw, spec.C), dtype=torch.bfloat16, device=w.device)
-    wd = torch.empty((spec.C, spec.kh, spec.kw, spec.O), dtype=torch.bfloat16, device=w.device) if need_dgrad else None
-    d, _ = make_desc(spec, 1, max(spec.kh, 1), max(spec.kw, 1))
+    t = act_dtype(dtype)
+    wf = torch.empty((spec.O, spec.kh, spec.kw, spec.C), dtype=t, device=w.device)
+    wd = torch.empty((spec.C, spec.kh, spec.kw, spec.O), dtype=t, device=w.device) if need_dgrad else None
+    d, _ = make_desc(spec, 1, max(spec.kh, 1), max(spec.kw, 1), dtype=dtype)
     L.check(L.load().pp_weight_prep(C.byref(d), L.ptr(w), L.ptr(wf), L.ptr(wd), _stream()), "pp_weight_prep")
-    return PreparedWeight(wf, wd, weight._version, weight.data_ptr(), _weight_epoch)
+    return PreparedWeight(wf, wd, weight._version, weight.data_ptr(), _weight_epoch, dtype)
 
 
 def master_weight(weight: torch.Tensor) -> torch.Tensor:
@@ -346,6 +361,7 @@ class BlockOpts:
     out_dtype: Optional[torch.dtype] = None
     algo: Optional[int] = None
     groups: int = 0           # PP_NORM_GN: number of groups (== O for InstanceNorm)
+    dtype: int = L.PP_DTYPE_BF16   # PP_DTYPE_*: bf16 tensors / kind::f16, or fp32 tensors / kind::tf32
     #: the block's weight / gamma / beta are Parameters that receive gradients from this operator ONLY (ConvBlock):
     #: when they live in a parallel.FlatParams their gradients are accumulated straight into the flat buffer by
     #: the producing kernels (PP_FLAG_ACC_*), and autograd sees no gradient for them
@@ -379,11 +395,14 @@ class _ConvBlockFn(torch.autograd.Function):
             raise RuntimeError(f"input has {Cx} channels, block expects {spec.C}")
         P, Q = spec.out_hw(H, W)
         dev = x.device
-        xc = to_nhwc_bf16(x.detach())
+        if prepared.dtype != o.dtype:
+            raise RuntimeError("deepipr_b200: weight operands were prepared for another arithmetic type")
+        adt = act_dtype(o.dtype)
+        xc = to_nhwc(x.detach(), o.dtype)
         need_grad = any(ctx.needs_input_grad[:4])
         keep_z = need_grad or o.norm in (L.PP_NORM_BN_TRAIN, L.PP_NORM_GN)
-        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups)
-        y = torch.empty((N, spec.O, P, Q), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, dtype=o.dtype)
+        y = torch.empty((N, spec.O, P, Q), dtype=adt, device=dev, memory_format=torch.channels_last)
         z = torch.empty((N, P, Q, spec.O), dtype=torch.float32 if o.z_f32 else torch.bfloat16, device=dev) \
             if keep_z else None
         nstat = N * o.groups if o.norm == L.PP_NORM_GN else spec.O   # GN/IN: one (mean, invstd) per sample and group
@@ -417,7 +436,7 @@ class _ConvBlockFn(torch.autograd.Function):
             ctx.gdtype = None if gamma is None else gamma.dtype
             ctx.bdtype = None if beta is None else beta.dtype
         out_dtype = o.out_dtype or x.dtype
-        if out_dtype != torch.bfloat16:
+        if out_dtype != adt:
             y = y.to(out_dtype)
         # The output keeps the memory format of the input: channels_last in -> channels_last out (no copy; what the
         # nets of this package and autocast pipelines use), NCHW-contiguous in -> NCHW-contiguous out, because the
@@ -433,12 +452,13 @@ class _ConvBlockFn(torch.autograd.Function):
         o, spec = ctx.o, ctx.o.spec
         N, Cx, H, W = ctx.xshape
         dev = gy.device
-        gyc = to_nhwc_bf16(gy)
+        adt = act_dtype(o.dtype)
+        gyc = to_nhwc(gy, o.dtype)
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         sw, sg, sb = ctx.slots
         flags = (L.PP_FLAG_ACC_DW if sw else 0) | (L.PP_FLAG_ACC_DGAMMA if sg else 0) | (L.PP_FLAG_ACC_DBETA if sb else 0)
-        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, flags)
-        dx = torch.empty((N, Cx, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last) \
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, flags, o.dtype)
+        dx = torch.empty((N, Cx, H, W), dtype=adt, device=dev, memory_format=torch.channels_last) \
             if need_dx else None
         if sw:
             dw = sw[0].grad_view(sw[1])
@@ -453,7 +473,7 @@ class _ConvBlockFn(torch.autograd.Function):
             C.byref(d), L.ptr(gyc), L.ptr(xc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(g), L.ptr(b), L.ptr(save_mean),
             L.ptr(save_invstd), L.ptr(dx), L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), C.c_size_t(nbytes),
             _stream()), "pp_conv_block_bwd")
-        if dx is not None and ctx.x_dtype != torch.bfloat16:
+        if dx is not None and ctx.x_dtype != adt:
             dx = dx.to(ctx.x_dtype)
         gg = dgamma.reshape(ctx.gshape).to(ctx.gdtype) if (ctx.gshape is not None and ctx.needs_input_grad[2]) else None
         gb = dbeta.reshape(ctx.bshape).to(ctx.bdtype) if (ctx.bshape is not None and ctx.needs_input_grad[3]) else None
@@ -487,12 +507,15 @@ class _PassportConvFn(torch.autograd.Function):
             raise RuntimeError(f"input has {Cx} channels, block expects {spec.C}")
         P, Q = spec.out_hw(H, W)
         dev = x.device
-        xc = to_nhwc_bf16(x.detach())
+        if prepared.dtype != o.dtype:
+            raise RuntimeError("deepipr_b200: weight operands were prepared for another arithmetic type")
+        adt = act_dtype(o.dtype)
+        xc = to_nhwc(x.detach(), o.dtype)
         w = master_weight(weight)
         need_grad = any(ctx.needs_input_grad[:2])
         keep_z = need_grad or o.norm in (L.PP_NORM_BN_TRAIN, L.PP_NORM_GN)
-        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups)
-        y = torch.empty((N, spec.O, P, Q), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, dtype=o.dtype)
+        y = torch.empty((N, spec.O, P, Q), dtype=adt, device=dev, memory_format=torch.channels_last)
         z = torch.empty((N, P, Q, spec.O), dtype=torch.float32 if o.z_f32 else torch.bfloat16, device=dev) \
             if keep_z else None
         nstat = N * o.groups if o.norm == L.PP_NORM_GN else spec.O
@@ -517,7 +540,7 @@ class _PassportConvFn(torch.autograd.Function):
             ctx.xshape = (N, Cx, H, W)
             ctx.wshape = weight.shape
         out_dtype = o.out_dtype or x.dtype
-        if out_dtype != torch.bfloat16:
+        if out_dtype != adt:
             y = y.to(out_dtype)
         if not x.is_contiguous(memory_format=torch.channels_last):
             y = y.contiguous()          # keep the input's memory format (see _ConvBlockFn.forward)
@@ -535,11 +558,12 @@ class _PassportConvFn(torch.autograd.Function):
         N, Cx, H, W = ctx.xshape
         dev = xc.device
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        adt = act_dtype(o.dtype)
         if gy is None:          # only the sign loss was used downstream
-            gy = torch.zeros((N, spec.O) + spec.out_hw(H, W), dtype=torch.bfloat16, device=dev)
-        gyc = to_nhwc_bf16(gy)
-        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, 0)
-        dx = torch.empty((N, Cx, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last) \
+            gy = torch.zeros((N, spec.O) + spec.out_hw(H, W), dtype=adt, device=dev)
+        gyc = to_nhwc(gy, o.dtype)
+        d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, 0, o.dtype)
+        dx = torch.empty((N, Cx, H, W), dtype=adt, device=dev, memory_format=torch.channels_last) \
             if need_dx else None
         dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dev) if need_dw else None
         dgamma = torch.empty(spec.O, dtype=torch.float32, device=dev)
@@ -559,7 +583,7 @@ class _PassportConvFn(torch.autograd.Function):
                 C.byref(d), L.ptr(gyc), L.ptr(xc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(gamma), L.ptr(beta),
                 L.ptr(save_mean), L.ptr(save_invstd), L.ptr(dx), None, L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws),
                 C.c_size_t(nbytes), _stream()), "pp_conv_block_bwd")
-        if dx is not None and ctx.x_dtype != torch.bfloat16:
+        if dx is not None and ctx.x_dtype != adt:
             dx = dx.to(ctx.x_dtype)
         return dx, dw, None, None, None
 
@@ -619,29 +643,32 @@ def conv_fwd_raw(x, prepared: PreparedWeight, spec: ConvSpec, z_f32=False, algo=
     require_cuda(x, "input")
     N, _, H, W = x.shape
     P, Q = spec.out_hw(H, W)
-    xc = to_nhwc_bf16(x)
-    d, key = make_desc(spec, N, H, W, z_f32=int(z_f32), algo=algo)
+    tf32 = prepared.dtype == L.PP_DTYPE_TF32
+    z_f32 = bool(z_f32) or tf32
+    xc = to_nhwc(x, prepared.dtype)
+    d, key = make_desc(spec, N, H, W, z_f32=int(z_f32), algo=algo, dtype=prepared.dtype)
     z = torch.empty((N, P, Q, spec.O), dtype=torch.float32 if z_f32 else torch.bfloat16, device=x.device)
-    L.check(L.load().pp_conv_fwd_raw(C.byref(d), L.ptr(xc), L.ptr(prepared.wf), L.ptr(z), None, C.c_size_t(0),
+    ws, nbytes = workspace(d, key, L.PP_WS_FWD, x.device)
+    L.check(L.load().pp_conv_fwd_raw(C.byref(d), L.ptr(xc), L.ptr(prepared.wf), L.ptr(z), L.ptr(ws), C.c_size_t(nbytes),
                                      _stream()), "pp_conv_fwd_raw")
     return z  # NHWC
 
 
 def conv_dgrad(dz_nhwc, prepared: PreparedWeight, spec: ConvSpec, N, H, W, algo=None):
     require_cuda(dz_nhwc, "dz")
-    d, key = make_desc(spec, N, H, W, algo=algo)
-    dz = dz_nhwc.to(torch.bfloat16).contiguous()
-    dx = torch.empty((N, H, W, spec.C), dtype=torch.bfloat16, device=dz.device)
+    d, key = make_desc(spec, N, H, W, algo=algo, dtype=prepared.dtype)
+    dz = dz_nhwc.to(act_dtype(prepared.dtype)).contiguous()
+    dx = torch.empty((N, H, W, spec.C), dtype=act_dtype(prepared.dtype), device=dz.device)
     L.check(L.load().pp_conv_dgrad(C.byref(d), L.ptr(dz), L.ptr(prepared.wd), L.ptr(dx), _stream()), "pp_conv_dgrad")
     return dx  # NHWC
 
 
-def conv_wgrad(dz_nhwc, x, spec: ConvSpec, algo=None):
+def conv_wgrad(dz_nhwc, x, spec: ConvSpec, algo=None, dtype=L.PP_DTYPE_BF16):
     require_cuda(dz_nhwc, "dz")
     N, _, H, W = x.shape
-    xc = to_nhwc_bf16(x)
-    d, key = make_desc(spec, N, H, W, algo=algo)
-    dz = dz_nhwc.to(torch.bfloat16).contiguous()
+    xc = to_nhwc(x, dtype)
+    d, key = make_desc(spec, N, H, W, algo=algo, dtype=dtype)
+    dz = dz_nhwc.to(act_dtype(dtype)).contiguous()
     dw = torch.empty((spec.O, spec.C, spec.kh, spec.kw), dtype=torch.float32, device=dz.device)
     ws, nbytes = workspace(d, key, L.PP_WS_BWD, dz.device)
     L.check(L.load().pp_conv_wgrad(C.byref(d), L.ptr(dz), L.ptr(xc), L.ptr(dw), L.ptr(ws), C.c_size_t(nbytes),

@@ -94,8 +94,43 @@ def _norm_groups(bn_module):
     return 0
 
 
+#: package-wide default arithmetic of the contractions; a block's own ``precision`` attribute overrides it
+_DEFAULT_PRECISION = 'bf16'
+
+
+def set_precision(precision):
+    """Arithmetic of every block that does not set its own ``precision``:
+
+    ``'bf16'``  bf16 activations, tcgen05 kind::f16 — BASELINE configs 3-5 (the model runs under autocast(bf16) or is
+                fed bf16); fp32 inputs are converted on entry and the output returns in the input's dtype.
+    ``'tf32'``  fp32 activations end to end, tcgen05 kind::tf32 — BASELINE config 2 (train_v1.py:13-29 runs the
+                reference in fp32, where torch's cuDNN convolutions use TF32 by default).  Applies to fp32 inputs
+                outside autocast; bf16 inputs, autocast regions and group / instance norm blocks keep the bf16 path.
+    Returns the previous setting."""
+    global _DEFAULT_PRECISION
+    if precision not in ('bf16', 'tf32'):
+        raise ValueError(f"precision must be 'bf16' or 'tf32', got {precision!r}")
+    prev, _DEFAULT_PRECISION = _DEFAULT_PRECISION, precision
+    return prev
+
+
+def get_precision():
+    return _DEFAULT_PRECISION
+
+
 class _FusedConvMixin:
     """Weight-operand cache + dispatch shared by the three block types."""
+
+    #: 'bf16' | 'tf32' | None (package default, see set_precision)
+    precision = None
+
+    def _dtype(self, x, norm):
+        """PP_DTYPE_* of this call (see set_precision)."""
+        p = self.precision or _DEFAULT_PRECISION
+        if (p == 'tf32' and x.dtype == torch.float32 and not torch.is_autocast_enabled()
+                and norm != L.PP_NORM_GN):
+            return L.PP_DTYPE_TF32
+        return L.PP_DTYPE_BF16
 
     #: keep the conv output z (saved for backward, re-read by the affine pass) in fp32.  bf16 halves that
     #: traffic but adds a second rounding in front of the bf16 output (DESIGN.md "Precision").
@@ -117,8 +152,8 @@ class _FusedConvMixin:
         self.__dict__.pop('_pp_prepared', None)
         self.__dict__.pop('_pp_keypool', None)
 
-    def _prepared(self):
-        """bf16 operand copies of the conv weight (pp_weight_prep).
+    def _prepared(self, dtype=L.PP_DTYPE_BF16):
+        """Operand copies of the conv weight (pp_weight_prep): bf16, or fp32 re-layouts for PP_DTYPE_TF32.
 
         Tensor._version does not see edits made through ``.data`` (the idiom of the reference's pruning / flip attack
         scripts: ``p.data.mul_(mask)``, ``w.data.copy_(...)``), so the cached copies are trusted only where every
@@ -130,13 +165,13 @@ class _FusedConvMixin:
         if (cached is not None and torch.is_grad_enabled() and self.training
                 and getattr(w, '_pp_flat_slot', None) is not None
                 and cached.version == w._version and cached.data_ptr == w.data_ptr()
-                and cached.epoch == F_.weight_epoch() and cached.wf.device == w.device):
+                and cached.epoch == F_.weight_epoch() and cached.wf.device == w.device and cached.dtype == dtype):
             return cached
-        prepared = F_.prepare_weight(w, self._spec(), need_dgrad=True)
+        prepared = F_.prepare_weight(w, self._spec(), need_dgrad=True, dtype=dtype)
         self.__dict__['_pp_prepared'] = prepared
         return prepared
 
-    def _bn_opts(self, norm, relu, z_f32, x):
+    def _bn_opts(self, norm, relu, z_f32, x, dtype=L.PP_DTYPE_BF16):
         bn = getattr(self, 'bn', None)
         rm = rv = None
         eps, momentum = 1e-5, 0.1
@@ -160,9 +195,10 @@ class _FusedConvMixin:
                     raise ValueError(f"Expected more than 1 spatial element when training, got input size "
                                      f"{torch.Size((x.shape[0], spec.O, P, Q))}")
         out_dtype = torch.bfloat16 if (torch.is_autocast_enabled() or x.dtype == torch.bfloat16) else x.dtype
-        return F_.BlockOpts(spec=self._spec(), norm=norm, relu=bool(relu), z_f32=bool(z_f32), eps=float(eps),
+        return F_.BlockOpts(spec=self._spec(), norm=norm, relu=bool(relu),
+                            z_f32=bool(z_f32) or dtype == L.PP_DTYPE_TF32, eps=float(eps),
                             momentum=float(momentum), running_mean=rm, running_var=rv, out_dtype=out_dtype,
-                            groups=int(groups))
+                            groups=int(groups), dtype=dtype)
 
 
 class ConvBlock(nn.Module, _FusedConvMixin):
@@ -190,11 +226,12 @@ class ConvBlock(nn.Module, _FusedConvMixin):
         F_.require_cuda(x, "ConvBlock input")
         self._check_conv()
         norm = _norm_mode(self.bn)
-        prepared = self._prepared()
+        dtype = self._dtype(x, norm)
+        prepared = self._prepared(dtype)
         if norm is None:
             # a norm module this library has no kernel for (e.g. InstanceNorm with running statistics):
             # fused conv, then the module itself
-            o = self._bn_opts(L.PP_NORM_NONE, False, False, x)
+            o = self._bn_opts(L.PP_NORM_NONE, False, False, x, dtype)
             y = F_.conv_block(x, self.conv.weight, None, self.conv.bias, prepared, o)
             y = self.bn(y)
             return self.relu(y) if self.relu is not None else y
@@ -203,7 +240,7 @@ class ConvBlock(nn.Module, _FusedConvMixin):
         else:
             # BatchNorm2d / GroupNorm carry an affine; InstanceNorm2d(o) does not (weight, bias are None)
             gamma, beta = self.bn.weight, self.bn.bias
-        o = self._bn_opts(norm, self.relu is not None, self.z_f32, x)
+        o = self._bn_opts(norm, self.relu is not None, self.z_f32, x, dtype)
         o.direct_grad_ok = True      # conv.weight / bn.weight / bn.bias (or conv.bias) feed this operator only
         return F_.conv_block(x, self.conv.weight, gamma, beta, prepared, o)
 
@@ -378,8 +415,9 @@ class _PassportBase(nn.Module, _FusedConvMixin):
         b = loss_module.b if loss_module is not None else None
         pc = F_.PassportCtx(S_skey, S_key, None if b is None else b.detach().reshape(-1).float().contiguous(),
                             float(loss_module.alpha) if loss_module is not None else 0.0)
-        o = self._bn_opts(norm, relu, self.z_f32, x)
-        y, gamma, beta, loss, acc = F_.passport_conv(x, self.weight, self._prepared(), o, pc)
+        dtype = self._dtype(x, norm)
+        o = self._bn_opts(norm, relu, self.z_f32, x, dtype)
+        y, gamma, beta, loss, acc = F_.passport_conv(x, self.weight, self._prepared(dtype), o, pc)
         if loss_module is not None:
             loss_module.reset()
             loss_module._add_fused(gamma.view(1, -1, 1, 1), loss, acc)
@@ -390,14 +428,15 @@ class _PassportBase(nn.Module, _FusedConvMixin):
         F_.require_cuda(x, "passport block input")
         self._check_conv()
         norm = _norm_mode(self.bn)
-        prepared = self._prepared()
+        dtype = self._dtype(x, norm)
+        prepared = self._prepared(dtype)
         if norm is None:   # norm module without a kernel here: fused conv, then the module and the affine in torch
-            o = self._bn_opts(L.PP_NORM_NONE, False, False, x)
+            o = self._bn_opts(L.PP_NORM_NONE, False, False, x, dtype)
             y = F_.conv_block(x, self.weight, None, None, prepared, o)
             y = self.bn(y)
             y = gamma.view(1, -1, 1, 1).to(y.dtype) * y + beta.view(1, -1, 1, 1).to(y.dtype)
             return torch.relu_(y) if relu else y
-        o = self._bn_opts(norm, relu, self.z_f32, x)
+        o = self._bn_opts(norm, relu, self.z_f32, x, dtype)
         return F_.conv_block(x, self.weight, gamma, beta, prepared, o)
 
     def _load_placeholders(self, state_dict, prefix):

@@ -53,6 +53,14 @@ enum { PP_ALGO_AUTO = 0, PP_ALGO_TCGEN05 = 1, PP_ALGO_SIMT = 2 };
  * no extra launches). */
 enum { PP_FLAG_ACC_DW = 1, PP_FLAG_ACC_DGAMMA = 2, PP_FLAG_ACC_DBETA = 4 };
 enum { PP_WS_FWD = 0, PP_WS_BWD = 1 };
+/* PPConvDesc.dtype — the arithmetic type of the contractions and the element type of every activation-shaped tensor
+ * that crosses this boundary (x, y, dy, dx; the weight operand copies of pp_weight_prep):
+ *   PP_DTYPE_BF16  bf16 tensors, tcgen05 kind::f16 (bf16 x bf16 -> fp32)               BASELINE configs 3-5
+ *   PP_DTYPE_TF32  fp32 tensors read by the tensor cores as TF32, tcgen05 kind::tf32   BASELINE config 2
+ *                  (what the reference's fp32 modules do on a GPU: torch leaves cudnn.allow_tf32 on; train_v1.py:13-29)
+ * z (conv output saved for backward) is fp32 in TF32 mode; group / instance norm and the single-kernel passport block
+ * are bf16-only (PP_EUNSUPPORTED / kernel sequence otherwise). */
+enum { PP_DTYPE_BF16 = 0, PP_DTYPE_TF32 = 1 };
 
 /* Geometry + mode of one conv block.  Mirrors the constructor arguments of the
  * reference blocks: PassportBlock(i, o, ks, s, pd, ...) models/layers/passportconv2d.py:12-18,
@@ -71,6 +79,7 @@ typedef struct PPConvDesc {
   int32_t algo;       /* PP_ALGO_*; AUTO picks tcgen05 when C%64==0 && O%64==0   */
   int32_t groups;     /* PP_NORM_GN only: number of groups (O for InstanceNorm); else 0  */
   int32_t flags;      /* PP_FLAG_* (backward only); 0 = overwrite dw / dgamma / dbeta    */
+  int32_t dtype;      /* PP_DTYPE_*: element type of x / y / dy / dx and of the weight operand copies */
 } PPConvDesc;
 
 int pp_version(void);

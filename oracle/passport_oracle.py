@@ -28,6 +28,12 @@ is NOT rounded: the CUDA path evaluates it from the fp32 master weight and the f
 the signature and has to match the reference's fp32 get_scale() bit for bit.  Block outputs and residual joins ARE
 rounded in this mode — activations are bf16 tensors on the CUDA path ("bf16 activations", BASELINE.json north_star),
 each produced by one rounding of an fp32 result — so that whole-network logits can be held to 1e-3.
+
+`round_bf16='tf32'` is the model of BASELINE config 2 (AlexNet V1 in fp32, train_v1.py:13-29): the reference's fp32
+modules on a GPU run their cuDNN convolutions in TF32 (torch.backends.cudnn.allow_tf32 defaults to True), i.e. every
+operand of the three contractions of a convolution — (x, W) forward, (dz, W) data gradient, (x, dz) weight gradient —
+is cut to 10 explicit mantissa bits and accumulated in fp32; everything else (normalisation, affine, losses, the
+passport affine) stays fp32.  Nothing is rounded to bf16 in this mode.
 """
 import copy
 
@@ -42,6 +48,42 @@ def bf16_round(t, enabled=True):
         return t
     r = t.detach().to(torch.bfloat16).to(t.dtype)
     return t + (r - t.detach()) if t.requires_grad else r
+
+
+def tf32_cut(t):
+    """The value a TF32 tensor-core instruction reads from an fp32 operand: the low 13 mantissa bits are dropped."""
+    return (t.detach().contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+class _ConvTF32(torch.autograd.Function):
+    """nn.Conv2d forward / backward with TF32 operands and fp32 accumulation (what cuDNN runs for the reference's fp32
+    nn.Conv2d on Ampere-and-later GPUs; passportconv2d.py:18,218)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, pad):
+        ctx.save_for_backward(x, w)
+        ctx.sp = (stride, pad)
+        ctx.has_bias = bias is not None
+        return F.conv2d(tf32_cut(x), tf32_cut(w), None if bias is None else bias.detach(), stride, pad)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        stride, pad = ctx.sp
+        gc = tf32_cut(g)
+        dx = torch.nn.grad.conv2d_input(x.shape, tf32_cut(w), gc, stride, pad) if ctx.needs_input_grad[0] else None
+        dw = torch.nn.grad.conv2d_weight(tf32_cut(x), w.shape, gc, stride, pad) if ctx.needs_input_grad[1] else None
+        db = g.sum((0, 2, 3)) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None
+
+
+def batch_conv(x, weight, bias, stride, pad, mode=False):
+    """The block's convolution over the minibatch under an operand model: False = plain fp32, True = operands rounded
+    to bf16, 'tf32' = TF32 operands in all three contractions."""
+    if mode == 'tf32':
+        return _ConvTF32.apply(x, weight, bias, stride, pad)
+    rb = mode is True
+    return F.conv2d(bf16_round(x, rb), bf16_round(weight, rb), bias, stride, pad)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -75,9 +117,9 @@ def normalise(z, kind, running_mean=None, running_var=None, training=True, momen
     return z
 
 
-def passport_forward(x, weight, gamma, beta, stride, pad, norm_kind, relu, **norm_args):
+def passport_forward(x, weight, gamma, beta, stride, pad, norm_kind, relu, mode=False, **norm_args):
     """y = relu(gamma * norm(conv(x, W)) + beta)   (passportconv2d.py:218-222)."""
-    z = F.conv2d(x, weight, None, stride, pad)
+    z = batch_conv(x, weight, None, stride, pad, mode)
     zn = normalise(z, norm_kind, **norm_args)
     y = gamma.view(1, -1, 1, 1) * zn + beta.view(1, -1, 1, 1)
     return F.relu(y) if relu else y
@@ -152,16 +194,14 @@ class OracleConvBlock(_OracleBlockBase):
 
     def forward(self, x):
         stride, pad = self._conv_args()
-        xr = bf16_round(x, self.round_bf16)
-        wr = bf16_round(self.conv.weight, self.round_bf16)
-        z = F.conv2d(xr, wr, self.conv.bias, stride, pad)
+        z = batch_conv(x, self.conv.weight, self.conv.bias, stride, pad, self.round_bf16)
         kind = self._norm_kind()
         if kind != 'none':
             zn = normalise(z, kind, **self._norm_args())
             if self.bn.weight is not None:
                 zn = zn * self.bn.weight.view(1, -1, 1, 1) + self.bn.bias.view(1, -1, 1, 1)
             z = zn
-        return bf16_round(F.relu(z) if self.has_relu else z, self.round_bf16)
+        return bf16_round(F.relu(z) if self.has_relu else z, self.round_bf16 is True)
 
 
 class OraclePassportBlock(_OracleBlockBase):
@@ -189,9 +229,6 @@ class OraclePassportBlock(_OracleBlockBase):
         self.round_bf16 = round_bf16
         return self
 
-    def _w(self):
-        return bf16_round(self.weight, self.round_bf16)
-
     def get_scale(self, force_passport=False, ind=0):
         use_public = self.scale is not None and not force_passport and (ind == 0 or not self.private)
         if use_public:
@@ -214,9 +251,9 @@ class OraclePassportBlock(_OracleBlockBase):
         stride, pad = self._conv_args()
         gamma = self.get_scale(force_passport, ind)
         beta = self.get_bias(force_passport, ind)
-        y = passport_forward(bf16_round(x, self.round_bf16), self._w(), gamma.reshape(-1), beta.reshape(-1), stride,
-                             pad, self._norm_kind(), self.has_relu, **self._norm_args())
-        return bf16_round(y, self.round_bf16)
+        y = passport_forward(x, self.weight, gamma.reshape(-1), beta.reshape(-1), stride, pad, self._norm_kind(),
+                             self.has_relu, mode=self.round_bf16, **self._norm_args())
+        return bf16_round(y, self.round_bf16 is True)
 
 
 def _call_block(block, x, force_passport, ind):
@@ -250,7 +287,7 @@ class OracleBasicUnit(nn.Module):
                 sc = m(sc)
         else:
             sc = _call_block(self.shortcut, x, force_passport, ind)
-        return bf16_round(F.relu(out + sc), self.round_bf16)
+        return bf16_round(F.relu(out + sc), self.round_bf16 is True)
 
 
 def mirror(model, round_bf16=False):

@@ -125,3 +125,27 @@ def test_strided_data_gradient_phase_decomposition():
                             if 0 <= f < P:
                                 dx[:, :, h, ww] += dz[:, :, e, f] @ w[:, :, r, c]
     assert torch.allclose(dx, x.grad, atol=1e-12)
+
+
+def test_tf32_operand_model_of_the_oracle():
+    """oracle.batch_conv(mode='tf32') — the model of BASELINE config 2 — cuts the operands of all three contractions of
+    a convolution to TF32 and accumulates exactly as the fp32 operators do on those operands."""
+    import torch.nn.functional as F
+    from oracle import passport_oracle as po
+    torch.manual_seed(0)
+    x = torch.randn(3, 32, 6, 6, requires_grad=True)
+    w = torch.randn(64, 32, 3, 3, requires_grad=True)
+    b = torch.randn(64, requires_grad=True)
+    g = torch.randn(3, 64, 6, 6)
+    z = po.batch_conv(x, w, b, 1, 1, 'tf32')
+    z.backward(g)
+    xc, wc, gc = po.tf32_cut(x), po.tf32_cut(w), po.tf32_cut(g)
+    # cut values are representable with 10 explicit mantissa bits and never larger in magnitude than the input
+    assert torch.equal(po.tf32_cut(xc), xc) and bool((xc.abs() <= x.detach().abs()).all())
+    assert float(((xc - x.detach()).abs() / x.detach().abs().clamp_min(1e-30)).max()) < 2.0 ** -10
+    assert torch.equal(z.detach(), F.conv2d(xc, wc, b.detach(), 1, 1))
+    assert torch.equal(x.grad, torch.nn.grad.conv2d_input(x.shape, wc, gc, 1, 1))
+    assert torch.equal(w.grad, torch.nn.grad.conv2d_weight(xc, w.shape, gc, 1, 1))
+    assert torch.allclose(b.grad, g.sum((0, 2, 3)))
+    # and the whole thing stays within TF32 distance of the exact fp32 operator
+    assert float((z.detach() - F.conv2d(x.detach(), w.detach(), b.detach(), 1, 1)).norm() / z.detach().norm()) < 2e-3
