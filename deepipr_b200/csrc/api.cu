@@ -523,6 +523,14 @@ int pp_sign_loss_bwd(int O, const float* gamma, const float* b_sign, float alpha
 int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, void* z, void* y, float* save_mean,
                       float* save_invstd, void* workspace, size_t ws_bytes, void* stream) {
+  return pp_conv_block_fwd_res(d, x, w_fprop, gamma, beta, running_mean, running_var, z, y, save_mean, save_invstd,
+                               nullptr, workspace, ws_bytes, stream);
+}
+
+int pp_conv_block_fwd_res(const PPConvDesc* d, const void* x, const void* w_fprop, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, void* z, void* y,
+                          float* save_mean, float* save_invstd, const void* residual, void* workspace, size_t ws_bytes,
+                          void* stream) {
   Geo geo;
   PP_TRY(geo_of(d, &geo));
   PP_TRY(check_device());
@@ -537,6 +545,8 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
   PP_REQUIRE(d->norm != PP_NORM_BN_EVAL || (running_mean && running_var), PP_EBADARG, "BN eval needs running stats");
   PP_REQUIRE(d->norm != PP_NORM_BN_TRAIN || z, PP_EBADARG, "BN train needs the z buffer");
   PP_REQUIRE(!is_tf32(*d) || !z || d->z_f32, PP_EBADARG, "PP_DTYPE_TF32 keeps z in fp32 (set z_f32)");
+  PP_REQUIRE(!residual || (z && !is_tf32(*d) && d->norm != PP_NORM_GN), PP_EUNSUPPORTED,
+             "the fused residual join needs the z buffer, bf16 tensors and a batch-norm / plain block");
   const int af32 = is_tf32(*d) ? 1 : 0;
   FwdWs ws = carve_fwd(*d, geo, workspace);
   PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "fwd workspace too small: need %zu, got %zu", ws.total,
@@ -555,7 +565,7 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
     fa.y = y; fa.z = d->z_f32 ? (float*)z : nullptr; fa.gamma_in = gamma; fa.beta_in = beta;
     fa.rmean = running_mean; fa.rvar = running_var; fa.save_mean = save_mean; fa.save_invstd = save_invstd;
     bool done = false;
-    PP_TRY(try_fused_block(*d, geo, x, w_fprop, ws, fa, s, &done));
+    if (!residual) PP_TRY(try_fused_block(*d, geo, x, w_fprop, ws, fa, s, &done));
     if (done) return PP_OK;
   }
   TapEpilogue e;
@@ -580,8 +590,9 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
                             save_mean, save_invstd, ws.ca, ws.cb, s));
   // algorithmic bytes of the pass: read z once, write y (bf16) once
   const double zb = d->z_f32 ? 4.0 : 2.0;
-  prof_begin(PROF_AFFINE, (double)geo.rows * d->O * (zb + (double)act_esz(*d)), d->C, d->O, geo.T, s);
-  const int rc = launch_affine_apply(z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, y, af32, s);
+  prof_begin(PROF_AFFINE, (double)geo.rows * d->O * (zb + (double)act_esz(*d) + (residual ? 2.0 : 0.0)), d->C, d->O,
+             geo.T, s);
+  const int rc = launch_affine_apply(z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, y, af32, residual, s);
   prof_end(PROF_AFFINE, s);
   return rc;
 }
@@ -617,16 +628,15 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
       PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s, d->flags & PP_FLAG_ACC_DW));
     return PP_OK;
   }
-  PP_TRY(launch_affine_coef(d->O, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb, s));
   int num_partials = 0;
   const double zb = d->z_f32 ? 4.0 : 2.0;
   prof_begin(PROF_REDUCE, (double)geo.rows * d->O * (zb + ab), d->C, d->O, geo.T, s);   // read dy + z
-  const int rc_red = launch_bwd_reduce(dy, af32, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.partial,
-                                       &num_partials, s);
+  const int rc_red = launch_bwd_reduce(dy, af32, z, d->z_f32, geo.rows, d->O, gamma, beta, save_mean, save_invstd,
+                                       d->relu, ws.partial, &num_partials, s);
   prof_end(PROF_REDUCE, s);
   PP_TRY(rc_red);
-  PP_TRY(launch_bwd_coef(*d, geo.rows, ws.partial, num_partials, gamma, save_mean, save_invstd, dgamma, dbeta, ws.k1,
-                         ws.k2, ws.k3, s));
+  PP_TRY(launch_bwd_coef(*d, geo.rows, ws.partial, num_partials, gamma, beta, save_mean, save_invstd, dgamma, dbeta,
+                         ws.k1, ws.k2, ws.k3, ws.ca, ws.cb, s));
   if (!dx && !dw_oihw) return PP_OK;
   prof_begin(PROF_DZ, (double)geo.rows * d->O * (zb + 2.0 * ab), d->C, d->O, geo.T, s);   // read dy + z, write dz
   const int rc_dz = launch_bwd_dz(dy, af32, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.k1, ws.k2, ws.k3,
@@ -771,6 +781,26 @@ int pp_add_relu_bwd(size_t n, const void* gy, const void* y, void* gx, void* str
   if (n == 0) return PP_OK;
   return launch_add_relu_bwd((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y, (__nv_bfloat16*)gx, n,
                              (cudaStream_t)stream);
+}
+
+int pp_maxpool_fwd(int N, int H, int W, int C, int k, int stride, int pad, const void* x, int f32, void* y,
+                   uint8_t* argmax, void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, PP_EBADSHAPE, "maxpool: N=%d H=%d W=%d C=%d (C%%8)", N, H, W, C);
+  PP_REQUIRE(k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && 2 * pad <= k && H + 2 * pad >= k && W + 2 * pad >= k,
+             PP_EBADSHAPE, "maxpool: k=%d stride=%d pad=%d", k, stride, pad);
+  PP_REQUIRE(x && y && argmax, PP_EBADARG, "maxpool: NULL pointer");
+  return launch_maxpool_fwd(N, H, W, C, k, stride, pad, x, f32, y, argmax, (cudaStream_t)stream);
+}
+
+int pp_maxpool_bwd(int N, int H, int W, int C, int k, int stride, int pad, const void* dy, const uint8_t* argmax,
+                   int f32, void* dx, void* stream) {
+  PP_TRY(check_device());
+  PP_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, PP_EBADSHAPE, "maxpool: N=%d H=%d W=%d C=%d (C%%8)", N, H, W, C);
+  PP_REQUIRE(k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && 2 * pad <= k && H + 2 * pad >= k && W + 2 * pad >= k,
+             PP_EBADSHAPE, "maxpool: k=%d stride=%d pad=%d", k, stride, pad);
+  PP_REQUIRE(dy && dx && argmax, PP_EBADARG, "maxpool bwd: NULL pointer");
+  return launch_maxpool_bwd(N, H, W, C, k, stride, pad, dy, argmax, f32, dx, (cudaStream_t)stream);
 }
 
 int pp_debug_last_timeout(void) { return debug_last_timeout(); }

@@ -169,15 +169,18 @@ int launch_bn_finalize(const PPConvDesc& d, int n_per_channel, const float* stat
 int launch_affine_coef(int O, const float* gamma, const float* beta, const float* mean, const float* invstd,
                        float* ca, float* cb, cudaStream_t s);
 int launch_affine_apply(const void* z, int z_f32, size_t rows, int O, const float* a, const float* b, int relu,
-                        void* y, int y_f32, cudaStream_t s);
+                        void* y, int y_f32, const void* res /*bf16 residual added after the ReLU, or NULL*/,
+                        cudaStream_t s);
 int launch_col_stats(const void* z, int z_f32, size_t rows, int O, float* partial, int* num_partials,
                      cudaStream_t s);
-int launch_bwd_reduce(const void* dy, int dy_f32, const void* z, int z_f32, size_t rows, int O, const float* a,
-                      const float* b, int relu, float* partial, int* num_partials, cudaStream_t s);
+int launch_bwd_reduce(const void* dy, int dy_f32, const void* z, int z_f32, size_t rows, int O, const float* gamma,
+                      const float* beta, const float* mean, const float* invstd, int relu, float* partial,
+                      int* num_partials, cudaStream_t s);   // the mask coefficients are derived in the kernel
 int bwd_reduce_max_partials();
 int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int num_partials, const float* gamma,
-                    const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* k1,
-                    float* k2, float* k3, cudaStream_t s);
+                    const float* beta, const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                    float* k1, float* k2, float* k3, float* ca, float* cb /*mask coefficients for the dz pass*/,
+                    cudaStream_t s);
 int launch_bwd_dz(const void* dy, int act_f32 /*dy and dz*/, const void* z, int z_f32, size_t rows, int O, const float* a,
                   const float* b, int relu, const float* k1, const float* k2, const float* k3, void* dz,
                   cudaStream_t s);
@@ -186,6 +189,10 @@ int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits,
 int launch_im2col_small(const PPConvDesc& d, const void* x, void* col, size_t rows, int P, int Q, int Kpad,
                         cudaStream_t s);   // element type per d.dtype
 int launch_pad_rows(const void* src, void* dst, int rows, int K, int Kpad, int f32, cudaStream_t s);
+int launch_maxpool_fwd(int N, int H, int W, int C, int k, int s, int p, const void* x, int f32, void* y, uint8_t* idx,
+                       cudaStream_t st);
+int launch_maxpool_bwd(int N, int H, int W, int C, int k, int s, int p, const void* dy, const uint8_t* idx, int f32,
+                       void* dx, cudaStream_t st);
 int launch_add_relu_fwd(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, size_t n, cudaStream_t s);
 int launch_add_relu_bwd(const __nv_bfloat16* g, const __nv_bfloat16* y, __nv_bfloat16* gx, size_t n, cudaStream_t s);
 // --- groupnorm.cu (GroupNorm / InstanceNorm: per-(sample, group) statistics, per-(sample, channel) coefficients) ---

@@ -910,8 +910,9 @@ static PxnPlan plan_pxn(const TapGemm& g) {
   if (R > g.P) R = g.P;
   while (R > 1 && (g.P % R != 0 || (R * g.Q) % 32 != 0)) --R;
   const int npx = R * g.Q;
-  if (g.P % R != 0 || npx != 256 || R < 2) return pl;   // full-width N = 256 tiles of >= 2 image rows only
-                                                          // (32x32 and 16x16 feature maps)
+  // N = R image rows x Q pixels: 256 on the 32x32 / 16x16 CIFAR maps, 224 (4 rows) on the 56x56 ImageNet maps — a
+  // multiple of 32 (epilogue chunk) that keeps the instruction near full width
+  if (g.P % R != 0 || npx % 32 != 0 || npx < 192 || R < 2) return pl;
   if (g.Q * 128 % 1024 != 0) return pl;   // tap windows must start on a swizzle-atom boundary: Q % 8 == 0
   PxnDev& d = pl.dev;
   memset(&d, 0, sizeof(d));
@@ -1048,11 +1049,13 @@ int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapE
 //
 //   warp 0      TMA producer (as tapgemm_kernel)
 //   warp 1      MMA issuer; local tile s accumulates into TMEM columns [256 s, 256 s + 256)
-//   warps 2..5  (a) gamma / beta rows of this CTA while the first tile is being computed,
-//               (b) pass 1 per tile: z (fp32, saved for backward) out, column sums of z and z^2,
+//   warps 2..9  (a) gamma / beta rows of this CTA while the first tile is being computed,
+//               (b) pass 1 per tile: z (fp32, saved for backward) out, column sums of z and z^2
+//                   (warps 2..5 for a tile whose successor's main loop hides it; all eight — two per TMEM lane
+//                   quarter, four 32-column chunks each — for the last tile, which nothing hides),
 //               ---- grid barrier ----
 //               (c) all warps: fixed-order reduction of the partials -> a = gamma * invstd, b = beta - a * mean,
-//               (d) pass 2 per tile: y = relu(a z + b) from TMEM.
+//               (d) pass 2 per tile: y = relu(a z + b) from TMEM, eight warps.
 // The z write of the first tile overlaps the second tile's main loop; after the barrier only y (2 bytes / element) is
 // written.  Against the multi-kernel path this removes the re-read of z (4 bytes / element), two launches
 // (bn_finalize, affine_apply) and, on the passport path, two more (gemv, sign loss).
@@ -1083,6 +1086,7 @@ struct FusedDev {
 };
 
 constexpr int kFusedBN = 256;
+constexpr int kFusedThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int kFusedStages = 4;
 constexpr int kFusedStageBytes = kBM * kBK * 2 + kFusedBN * kBK * 2;   // 48 KiB
 constexpr int kFusedSmemBytes = 1024 + kFusedStages * kFusedStageBytes + 2 * kFusedBN * 4 /*a, b*/ +
@@ -1114,7 +1118,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFusedThreads, 1)
 passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ FusedDev p) {
   constexpr int BN = kFusedBN;
@@ -1226,16 +1230,20 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else {
     // ===================== epilogue warps, part 1 =====================
-    const int ew = warp - 2;
+    const int ew = warp - 2;              // 0..7
+    const int half = ew >> 2;             // 0: warps 2..5, 1: warps 6..9 (join for the last tile and for pass 2)
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int tid_e = ew * 32 + lane;
-    // (a) passport-derived gamma / beta for the channels this CTA owns (4 warps x 1 channel, strided over the grid);
+    const int tid_e = ew * 32 + lane;     // 0..255
+    // per-warp store staging: warps 2..5 own s_stage; warps 6..9 only work once the main loop is over and borrow
+    // idle pipeline-stage memory (past the 20 KiB the fp64 scratch of step (c) uses)
+    uint8_t* my_stage = half == 0 ? s_stage + (ew & 3) * 4096 : stage_base + 32768 + (ew & 3) * 4096;
+    // (a) passport-derived gamma / beta for the channels this CTA owns (8 warps x 1 channel, strided over the grid);
     //     hidden behind the first tile's main loop
     if (p.w_oihw != nullptr) {
       const int K = p.Cin * p.T;                    // one OIHW row; the pooled patches use the same element order
       const int n4 = K >> 2;                        // K % 4 == 0 (C % 64 == 0 on this path)
-      for (int c = (int)blockIdx.x * 4 + ew; c < g.Nout; c += 4 * grid) {
+      for (int c = (int)blockIdx.x * 8 + ew; c < g.Nout; c += 8 * grid) {
         const float4* r4 = reinterpret_cast<const float4*>(p.w_oihw + (size_t)c * K);
         double g4[4] = {0.0, 0.0, 0.0, 0.0}, b4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
@@ -1267,21 +1275,27 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
     }
-    for (int i = tid_e; i < 2 * BN; i += 128) s_acc[i] = 0.0f;
+    if (half == 0)
+      for (int i = tid_e; i < 2 * BN; i += 128) s_acc[i] = 0.0f;
     // (b) pass 1: z out (fp32), column sums
     for (int s = 0; s < nlocal; ++s) {
+      const bool all8 = (s == nlocal - 1);     // nothing hides the last tile's pass: every epilogue warp takes part
+      if (!all8 && half == 1) continue;
+      const int jbeg = all8 ? half * 4 : 0;
+      const int jend = all8 ? jbeg + 4 : BN / 32;
       const int tile = (int)blockIdx.x + s * grid;
       const int m_tile = tile / g.num_n_tiles;
       const int m = m_tile * kBM + row;
       const bool valid = m < g.M;
       const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
       const long long out_row = (long long)m;
-      named_bar_sync(1, 128);   // s_acc zeroed / previous tile's s_red consumed
+      // s_acc zeroed / previous tile's s_red consumed
+      if (all8) named_bar_sync(2, 256); else named_bar_sync(1, 128);
       mbar_wait(&tfull[s], 0, 1800 + s);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + s * BN;
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int j = jbeg; j < jend; ++j) {
         uint32_t raw[32];
         tmem_ld_32x32(taddr + j * 32, raw);
         tmem_ld_wait();
@@ -1297,11 +1311,11 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
           const float s1 = warp_column_sum(t1, lane);
           const float s2 = warp_column_sum(t2, lane);
-          s_red[(ew * 2 + 0) * BN + j * 32 + lane] = s1;
-          s_red[(ew * 2 + 1) * BN + j * 32 + lane] = s2;
+          s_red[(quarter * 2 + 0) * BN + j * 32 + lane] = s1;     // one slot per lane quarter: the two warps of a
+          s_red[(quarter * 2 + 1) * BN + j * 32 + lane] = s2;     // quarter own disjoint column chunks
         }
         if (p.z != nullptr) {
-          float4* st = reinterpret_cast<float4*>(s_stage + ew * 4096);
+          float4* st = reinterpret_cast<float4*>(my_stage);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             st[lane * 8 + (i ^ (lane & 7))] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -1317,19 +1331,23 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           __syncwarp();
         }
       }
-      named_bar_sync(1, 128);
-      for (int i = tid_e; i < BN; i += 128) {
-        const float a1 = s_red[(0 * 2 + 0) * BN + i] + s_red[(1 * 2 + 0) * BN + i] + s_red[(2 * 2 + 0) * BN + i] +
-                         s_red[(3 * 2 + 0) * BN + i];
-        const float a2 = s_red[(0 * 2 + 1) * BN + i] + s_red[(1 * 2 + 1) * BN + i] + s_red[(2 * 2 + 1) * BN + i] +
-                         s_red[(3 * 2 + 1) * BN + i];
-        s_acc[i] += a1;            // column i is only ever touched by this thread
-        s_acc[BN + i] += a2;
+      if (all8) named_bar_sync(2, 256); else named_bar_sync(1, 128);
+      if (half == 0) {
+        for (int i = tid_e; i < BN; i += 128) {
+          const float a1 = s_red[(0 * 2 + 0) * BN + i] + s_red[(1 * 2 + 0) * BN + i] + s_red[(2 * 2 + 0) * BN + i] +
+                           s_red[(3 * 2 + 0) * BN + i];
+          const float a2 = s_red[(0 * 2 + 1) * BN + i] + s_red[(1 * 2 + 1) * BN + i] + s_red[(2 * 2 + 1) * BN + i] +
+                           s_red[(3 * 2 + 1) * BN + i];
+          s_acc[i] += a1;            // column i is only ever touched by this thread
+          s_acc[BN + i] += a2;
+        }
       }
     }
-    named_bar_sync(1, 128);
-    float* dst = p.partial + (size_t)blockIdx.x * 2 * BN;
-    for (int i = tid_e; i < 2 * BN; i += 128) dst[i] = s_acc[i];
+    if (half == 0) {
+      named_bar_sync(1, 128);
+      float* dst = p.partial + (size_t)blockIdx.x * 2 * BN;
+      for (int i = tid_e; i < 2 * BN; i += 128) dst[i] = s_acc[i];
+    }
   }
 
   // ===================== grid-wide: every tile's statistics are in global memory =====================
@@ -1340,12 +1358,15 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   // (c) all 192 threads: fixed-order reduction of the partial rows of the CTAs that share this CTA's 256 columns.
   //     The pipeline stages are idle now: their memory holds the fp64 scratch.
   {
-    double* sh = reinterpret_cast<double*>(stage_base);     // [3 groups][2 * BN]
-    const int grp = threadIdx.x / 64;                       // rows k == grp (mod 3)
+    constexpr int kGroups = kFusedThreads / 64;             // 5
+    double* sh = reinterpret_cast<double*>(stage_base);     // [kGroups][2 * BN] = 20 KiB
+    const int grp = threadIdx.x / 64;                       // rows k == grp (mod kGroups)
     const int l64 = threadIdx.x % 64;                       // float4 #l64 of sum z, float4 #l64 of sum z^2
     const int nrows = grid / g.num_n_tiles;
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = grp; k < nrows; k += 3) {
+    // the loads of different rows are independent (only the fp64 adds are ordered): keep eight rows in flight
+#pragma unroll 8
+    for (int k = grp; k < nrows; k += kGroups) {
       const float4* rowp = reinterpret_cast<const float4*>(p.partial + (size_t)(my_n_tile + k * g.num_n_tiles) * 2 * BN);
       const float4 u = __ldcg(rowp + l64);
       const float4 w = __ldcg(rowp + 64 + l64);
@@ -1359,9 +1380,13 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     __syncthreads();
     const double n = (double)g.M;
-    for (int col = threadIdx.x; col < BN; col += kThreads) {
-      const double s1 = sh[col] + sh[2 * BN + col] + sh[4 * BN + col];
-      const double s2 = sh[BN + col] + sh[2 * BN + BN + col] + sh[4 * BN + BN + col];
+    for (int col = threadIdx.x; col < BN; col += kFusedThreads) {
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int gq = 0; gq < kGroups; ++gq) {                 // fixed group order
+        s1 += sh[gq * 2 * BN + col];
+        s2 += sh[gq * 2 * BN + BN + col];
+      }
       const double mu = s1 / n;
       double var = s2 / n - mu * mu;
       if (var < 0.0) var = 0.0;
@@ -1387,7 +1412,7 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (p.b_sign != nullptr && (p.sign_loss || p.sign_acc) && (int)blockIdx.x == grid - 1) {
       __syncthreads();                                       // sh is about to be reused
       double h = 0.0, r = 0.0, a = 0.0;
-      for (int o = threadIdx.x; o < g.Nout; o += kThreads) {
+      for (int o = threadIdx.x; o < g.Nout; o += kFusedThreads) {
         const float gm = p.w_oihw ? __ldcg(p.gamma_out + o) : (p.gamma_in ? __ldg(p.gamma_in + o) : 1.0f);
         const float bb = __ldg(p.b_sign + o);
         const float hinge = fmaxf(-bb * gm + 0.1f, 0.0f);
@@ -1398,12 +1423,14 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         a += (sb == sg) ? 1.0 : 0.0;
       }
       sh[threadIdx.x] = h;
-      sh[kThreads + threadIdx.x] = r;
-      sh[2 * kThreads + threadIdx.x] = a;
+      sh[kFusedThreads + threadIdx.x] = r;
+      sh[2 * kFusedThreads + threadIdx.x] = a;
       __syncthreads();
       if (threadIdx.x == 0) {
         double hs = 0.0, rs = 0.0, as = 0.0;
-        for (int i = 0; i < kThreads; ++i) { hs += sh[i]; rs += sh[kThreads + i]; as += sh[2 * kThreads + i]; }
+        for (int i = 0; i < kFusedThreads; ++i) {
+          hs += sh[i]; rs += sh[kFusedThreads + i]; as += sh[2 * kFusedThreads + i];
+        }
         if (p.sign_loss) *p.sign_loss = (float)(hs + 0.00001 * rs);
         if (p.sign_acc) *p.sign_acc = (float)(as / (double)g.Nout);
       }
@@ -1411,11 +1438,13 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncthreads();
   }
 
-  // (d) pass 2: y = relu(a z + b) straight from the resident accumulators
+  // (d) pass 2: y = relu(a z + b) straight from the resident accumulators — eight warps, four column chunks each
   if (warp >= 2) {
     const int ew = warp - 2;
+    const int half = ew >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    uint8_t* my_stage = half == 0 ? s_stage + (ew & 3) * 4096 : stage_base + 32768 + (ew & 3) * 4096;
     for (int s = 0; s < nlocal; ++s) {
       const int tile = (int)blockIdx.x + s * grid;
       const int m_tile = tile / g.num_n_tiles;
@@ -1425,7 +1454,7 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const long long out_row = (long long)m;
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + s * BN;
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int j = half * 4; j < half * 4 + 4; ++j) {
         uint32_t raw[32];
         tmem_ld_32x32(taddr + j * 32, raw);
         tmem_ld_wait();
@@ -1436,7 +1465,7 @@ passport_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
-        uint4* st = reinterpret_cast<uint4*>(s_stage + ew * 4096);
+        uint4* st = reinterpret_cast<uint4*>(my_stage);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 u;
@@ -1538,7 +1567,7 @@ int passport_fused_tcgen05(const TapGemm& g, const void* act, const void* B, con
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kFusedThreads);
   cfg.dynamicSmemBytes = kFusedSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];

@@ -331,9 +331,22 @@ __device__ __forceinline__ bool reduce_partials_32x32(const float* __restrict__ 
   const int slice = threadIdx.y;
   double a1 = 0.0, a2 = 0.0;
   if (o < O) {
-    for (int i = slice; i < num; i += 32) {
-      a1 += (double)partial[(size_t)i * 2 * O + o];
-      a2 += (double)partial[(size_t)i * 2 * O + O + o];
+    // four rows in flight per trip (eight independent loads), summed in a fixed order: with up to 592 partial rows a
+    // one-load-at-a-time loop is a chain of 18 L2 round trips, which is what these tiny kernels cost
+    const size_t rs = (size_t)2 * O;
+    const float* p = partial + o;
+    int i = slice;
+    for (; i + 96 < num; i += 128) {
+      const float u0 = __ldg(p + (size_t)i * rs), v0 = __ldg(p + (size_t)i * rs + O);
+      const float u1 = __ldg(p + (size_t)(i + 32) * rs), v1 = __ldg(p + (size_t)(i + 32) * rs + O);
+      const float u2 = __ldg(p + (size_t)(i + 64) * rs), v2 = __ldg(p + (size_t)(i + 64) * rs + O);
+      const float u3 = __ldg(p + (size_t)(i + 96) * rs), v3 = __ldg(p + (size_t)(i + 96) * rs + O);
+      a1 += (double)u0; a1 += (double)u1; a1 += (double)u2; a1 += (double)u3;
+      a2 += (double)v0; a2 += (double)v1; a2 += (double)v2; a2 += (double)v3;
+    }
+    for (; i < num; i += 32) {
+      a1 += (double)__ldg(p + (size_t)i * rs);
+      a2 += (double)__ldg(p + (size_t)i * rs + O);
     }
   }
   sh1[slice][threadIdx.x] = a1;
@@ -482,12 +495,33 @@ int launch_affine_coef(int O, const float* gamma, const float* beta, const float
 }
 
 // ---------------------------------------------------------------------------------------------
-// affine + ReLU pass: y[r, o] = relu(a[o]*z[r,o] + b[o]); 8 channels (one 128-bit bf16 vector) per thread
+// affine + ReLU pass: y[r, o] = relu(a[o]*z[r,o] + b[o]); 8 channels (one 128-bit bf16 vector) per thread.
+// RES: the residual join of a basic block folded in, y = bf16(relu(a z + b)) + res — the block output is rounded to
+// bf16 first, exactly as if it had been stored and re-read by a separate add pass, so results do not depend on
+// whether the join is fused.  (The reference's join is relu(out + shortcut) with BOTH summands already >= 0 — every
+// block of its ResNets, convbn_2 and the shortcut included, ends in a ReLU: resnet_passport_private.py:26-30,78-85 —
+// so the outer ReLU is the identity and is not applied here; callers pass `res` only under that guarantee.)
 // ---------------------------------------------------------------------------------------------
-template <bool AF32>
+template <bool AF32, bool RES>
+__device__ __forceinline__ void affine8(float (&v)[8], const float (&ca)[8], const float (&cb)[8], int relu,
+                                        const __nv_bfloat16* __restrict__ res, size_t i) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = fmaf(v[k], ca[k], cb[k]);
+    if (relu) v[k] = fmaxf(v[k], 0.0f);
+  }
+  if (RES) {
+    float r[8];
+    load8_bf16(res, i, r);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = bf16_round(v[k]) + r[k];
+  }
+}
+
+template <bool AF32, bool RES>
 __global__ void affine_apply_kernel(const void* __restrict__ z, int z_f32, size_t nvec, int O,
                                     const float* __restrict__ a, const float* __restrict__ b, int relu,
-                                    void* __restrict__ y) {
+                                    const __nv_bfloat16* __restrict__ res, void* __restrict__ y) {
   const int vec_per_row = O >> 3;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -503,23 +537,15 @@ __global__ void affine_apply_kernel(const void* __restrict__ z, int z_f32, size_
       float v0[8], v1[8];
       load8(z, z_f32, i, v0);
       load8(z, z_f32, i + stride, v1);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        v0[k] = fmaf(v0[k], ca[k], cb[k]);
-        v1[k] = fmaf(v1[k], ca[k], cb[k]);
-        if (relu) { v0[k] = fmaxf(v0[k], 0.0f); v1[k] = fmaxf(v1[k], 0.0f); }
-      }
+      affine8<AF32, RES>(v0, ca, cb, relu, res, i);
+      affine8<AF32, RES>(v1, ca, cb, relu, res, i + stride);
       store8(y, AF32, i, v0);
       store8(y, AF32, i + stride, v1);
     }
     if (i < nvec) {
       float v[8];
       load8(z, z_f32, i, v);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        v[k] = fmaf(v[k], ca[k], cb[k]);
-        if (relu) v[k] = fmaxf(v[k], 0.0f);
-      }
+      affine8<AF32, RES>(v, ca, cb, relu, res, i);
       store8(y, AF32, i, v);
     }
     return;
@@ -530,26 +556,27 @@ __global__ void affine_apply_kernel(const void* __restrict__ z, int z_f32, size_
     load8(z, z_f32, i, v);
     load8_coef(a, ch, ca);
     load8_coef(b, ch, cb);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      v[k] = fmaf(v[k], ca[k], cb[k]);
-      if (relu) v[k] = fmaxf(v[k], 0.0f);
-    }
+    affine8<AF32, RES>(v, ca, cb, relu, res, i);
     store8(y, AF32, i, v);
   }
 }
 
 int launch_affine_apply(const void* z, int z_f32, size_t rows, int O, const float* a, const float* b, int relu,
-                        void* y, int y_f32, cudaStream_t s) {
+                        void* y, int y_f32, const void* res, cudaStream_t s) {
   PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "affine pass needs O%%8==0 (O=%d)", O);
+  PP_REQUIRE(!(res && y_f32), PP_EUNSUPPORTED, "the fused residual join is bf16-only");
   const size_t nvec = rows * (size_t)(O / 8);
-  static int occ[2] = {0, 0};
+  static int occ[3] = {0, 0, 0};
+  const __nv_bfloat16* r = (const __nv_bfloat16*)res;
   if (y_f32)
-    affine_apply_kernel<true><<<streaming_grid(affine_apply_kernel<true>, &occ[1], nvec, 256, O / 8), 256, 0, s>>>(
-        z, z_f32, nvec, O, a, b, relu, y);
+    affine_apply_kernel<true, false><<<streaming_grid(affine_apply_kernel<true, false>, &occ[1], nvec, 256, O / 8), 256,
+                                       0, s>>>(z, z_f32, nvec, O, a, b, relu, nullptr, y);
+  else if (res)
+    affine_apply_kernel<false, true><<<streaming_grid(affine_apply_kernel<false, true>, &occ[2], nvec, 256, O / 8), 256,
+                                       0, s>>>(z, z_f32, nvec, O, a, b, relu, r, y);
   else
-    affine_apply_kernel<false><<<streaming_grid(affine_apply_kernel<false>, &occ[0], nvec, 256, O / 8), 256, 0, s>>>(
-        z, z_f32, nvec, O, a, b, relu, y);
+    affine_apply_kernel<false, false><<<streaming_grid(affine_apply_kernel<false, false>, &occ[0], nvec, 256, O / 8),
+                                        256, 0, s>>>(z, z_f32, nvec, O, a, b, relu, nullptr, y);
   PP_POST_LAUNCH();
   return PP_OK;
 }
@@ -565,9 +592,13 @@ int bwd_reduce_max_partials() { return kRedMaxBlocks; }
 // Shared skeleton of the per-channel column reductions: each thread owns one 8-channel vector column
 // and a row lane; rows are strided over (row lanes x blocks); row lanes are combined through shared
 // memory in a fixed order.  MODE 0: (sum z, sum z^2).  MODE 1: (sum dy_m, sum dy_m*z).
+// MODE 1 derives the ReLU-mask coefficients a = gamma * invstd, b = beta - a * mean itself when `mean` is given (the
+// same two fp32 operations bn_finalize_kernel performed in the forward pass, so the mask is the forward's), which
+// saves the separate coefficient launch; with mean == NULL, a and b are read as given.
 template <int MODE, bool AF32>
 __global__ void column_reduce_kernel(const void* __restrict__ dy, const void* __restrict__ z, int z_f32,
                                      size_t rows, int O, const float* __restrict__ a, const float* __restrict__ b,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                      int relu, float* __restrict__ partial) {
   extern __shared__ float s_part[];  // [row_lanes][2][O]
   const int vec_per_row = O >> 3;
@@ -580,8 +611,18 @@ __global__ void column_reduce_kernel(const void* __restrict__ dy, const void* __
   if (rl < row_lanes) {
     float ca[8], cb[8];
     if (MODE == 1 && relu) {
-      load8_coef(a, col * 8, ca);
-      load8_coef(b, col * 8, cb);
+      if (mean != nullptr) {          // a = gamma, b = beta here
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int o = col * 8 + k;
+          const float av = (a ? __ldg(a + o) : 1.0f) * __ldg(invstd + o);
+          ca[k] = av;
+          cb[k] = (b ? __ldg(b + o) : 0.0f) - av * __ldg(mean + o);
+        }
+      } else {
+        load8_coef(a, col * 8, ca);
+        load8_coef(b, col * 8, cb);
+      }
     }
     const size_t rstride = (size_t)gridDim.x * row_lanes;
     size_t r = (size_t)blockIdx.x * row_lanes + rl;
@@ -661,7 +702,8 @@ __global__ void column_reduce_kernel(const void* __restrict__ dy, const void* __
 
 template <int MODE, bool AF32>
 static int column_reduce_launch_t(const void* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
-                                  const float* b, int relu, float* partial, int* num_partials, cudaStream_t s) {
+                                  const float* b, const float* mean, const float* invstd, int relu, float* partial,
+                                  int* num_partials, cudaStream_t s) {
   const int vec_per_row = O / 8;
   const int row_lanes = kRedThreads / vec_per_row;
   const size_t smem = (size_t)row_lanes * 2 * O * sizeof(float);
@@ -681,7 +723,8 @@ static int column_reduce_launch_t(const void* dy, const void* z, int z_f32, size
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   PP_SET_MAX_SMEM_ONCE((column_reduce_kernel<MODE, AF32>), 64 * 1024);
-  column_reduce_kernel<MODE, AF32><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, relu, partial);
+  column_reduce_kernel<MODE, AF32><<<(int)blocks, kRedThreads, smem, s>>>(dy, z, z_f32, rows, O, a, b, mean, invstd,
+                                                                          relu, partial);
   PP_POST_LAUNCH();
   *num_partials = (int)blocks;
   return PP_OK;
@@ -690,14 +733,20 @@ static int column_reduce_launch_t(const void* dy, const void* z, int z_f32, size
 int launch_col_stats(const void* z, int z_f32, size_t rows, int O, float* partial, int* num_partials,
                      cudaStream_t s) {
   PP_REQUIRE(O % 8 == 0 && O / 8 <= kRedThreads, PP_EBADSHAPE, "column reduce needs O%%8==0 and O<=2048 (O=%d)", O);
-  return column_reduce_launch_t<0, false>(nullptr, z, z_f32, rows, O, nullptr, nullptr, 0, partial, num_partials, s);
+  return column_reduce_launch_t<0, false>(nullptr, z, z_f32, rows, O, nullptr, nullptr, nullptr, nullptr, 0, partial,
+                                          num_partials, s);
 }
 
-int launch_bwd_reduce(const void* dy, int dy_f32, const void* z, int z_f32, size_t rows, int O, const float* a,
-                      const float* b, int relu, float* partial, int* num_partials, cudaStream_t s) {
+int launch_bwd_reduce(const void* dy, int dy_f32, const void* z, int z_f32, size_t rows, int O, const float* gamma,
+                      const float* beta, const float* mean, const float* invstd, int relu, float* partial,
+                      int* num_partials, cudaStream_t s) {
   PP_REQUIRE(O % 8 == 0 && O / 8 <= kRedThreads, PP_EBADSHAPE, "column reduce needs O%%8==0 and O<=2048 (O=%d)", O);
-  if (dy_f32) return column_reduce_launch_t<1, true>(dy, z, z_f32, rows, O, a, b, relu, partial, num_partials, s);
-  return column_reduce_launch_t<1, false>(dy, z, z_f32, rows, O, a, b, relu, partial, num_partials, s);
+  PP_REQUIRE(mean && invstd, PP_EBADARG, "backward reduce needs the saved statistics");
+  if (dy_f32)
+    return column_reduce_launch_t<1, true>(dy, z, z_f32, rows, O, gamma, beta, mean, invstd, relu, partial,
+                                           num_partials, s);
+  return column_reduce_launch_t<1, false>(dy, z, z_f32, rows, O, gamma, beta, mean, invstd, relu, partial,
+                                          num_partials, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -708,13 +757,20 @@ int launch_bwd_reduce(const void* dy, int dy_f32, const void* z, int z_f32, size
 //   none / BN(eval):  dz = a*dy_m
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) bwd_coef_kernel(int norm, double n, const float* __restrict__ partial, int num,
-                                const float* __restrict__ gamma, const float* __restrict__ mean,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ mean,
                                 const float* __restrict__ invstd, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2,
-                                float* __restrict__ k3, int O, int flags) {
+                                float* __restrict__ k3, float* __restrict__ ca, float* __restrict__ cb, int O,
+                                int flags) {
   const int o = blockIdx.x * 32 + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
   if (!reduce_partials_32x32(partial, num, O, o, s1, s2)) return;
+  {   // ReLU-mask coefficients for the dz pass: the forward's a = gamma * invstd, b = beta - a * mean
+    const float av = (gamma ? gamma[o] : 1.0f) * invstd[o];
+    ca[o] = av;
+    cb[o] = (beta ? beta[o] : 0.0f) - av * mean[o];
+  }
   const double mu = mean[o], is = invstd[o];
   const double g = gamma ? (double)gamma[o] : 1.0;
   const double dg = is * (s2 - mu * s1);
@@ -734,10 +790,11 @@ __global__ void __launch_bounds__(1024) bwd_coef_kernel(int norm, double n, cons
 }
 
 int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int num_partials, const float* gamma,
-                    const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* k1,
-                    float* k2, float* k3, cudaStream_t s) {
-  bwd_coef_kernel<<<(d.O + 31) / 32, dim3(32, 32), 0, s>>>(d.norm, (double)rows, partial, num_partials, gamma, save_mean,
-                                                save_invstd, dgamma, dbeta, k1, k2, k3, d.O, d.flags);
+                    const float* beta, const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                    float* k1, float* k2, float* k3, float* ca, float* cb, cudaStream_t s) {
+  bwd_coef_kernel<<<(d.O + 31) / 32, dim3(32, 32), 0, s>>>(d.norm, (double)rows, partial, num_partials, gamma, beta,
+                                                save_mean, save_invstd, dgamma, dbeta, k1, k2, k3, ca, cb, d.O,
+                                                d.flags);
   PP_POST_LAUNCH();
   return PP_OK;
 }
@@ -1111,6 +1168,121 @@ int launch_pad_rows(const void* src, void* dst, int rows, int K, int Kpad, int f
   else
     pad_rows_kernel<__nv_bfloat16><<<grid_for((size_t)rows * Kpad, 256, 1024), 256, 0, s>>>(
         (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, rows, K, Kpad);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// nn.MaxPool2d(k, s, p) on NHWC tensors (models/resnet_passport*.py: MaxPool2d(3, 2, 1) behind the ImageNet stem;
+// models/alexnet_passport.py:37-38: MaxPool2d(2, 2)), bf16 or fp32, 8 channels per thread.
+// Forward keeps, per output element, the position of its maximum inside the window (one byte, first maximum in
+// (kh, kw) scan order — the rule of ATen's max_pool2d on both CPU and CUDA: `val > maxval`), so the backward is a
+// gather without atomics: every input element adds the gradients of the (at most ceil(k/s)^2) windows that elected it.
+// HBM-bound: forward reads x once and writes y + 1 byte/element, backward reads dy + the bytes and writes dx once
+// (ATen's kernels for this layout took 0.75 ms / 1.73 ms at the ImageNet stem, 9x / 17x those bytes).
+// ---------------------------------------------------------------------------------------------
+template <bool F32>
+__global__ void maxpool_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, uint8_t* __restrict__ idx, int N,
+                                   int H, int W, int C, int k, int s, int p, int P, int Q) {
+  const int c8n = C >> 3;
+  const size_t total = (size_t)N * P * Q * c8n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    const size_t pix = i / c8n;
+    const int q = (int)(pix % Q);
+    const int pp_ = (int)((pix / Q) % P);
+    const size_t n = pix / ((size_t)P * Q);
+    const int h0 = pp_ * s - p, w0 = q * s - p;
+    float best[8];
+    uint8_t bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    bool first = true;
+    for (int r = 0; r < k; ++r) {
+      const int h = h0 + r;
+      if (h < 0 || h >= H) continue;
+      for (int t = 0; t < k; ++t) {
+        const int w = w0 + t;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        load8(x, F32 ? 1 : 0, ((n * H + h) * W + w) * c8n + c8, v);
+        const uint8_t li = (uint8_t)(r * k + t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (first || v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; bi[j] = li; }
+        }
+        first = false;
+      }
+    }
+    store8(y, F32 ? 1 : 0, i, best);
+    uint2 packed;
+    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    reinterpret_cast<uint2*>(idx)[i] = packed;
+  }
+}
+
+template <bool F32>
+__global__ void maxpool_bwd_kernel(const void* __restrict__ dy, const uint8_t* __restrict__ idx, void* __restrict__ dx,
+                                   int N, int H, int W, int C, int k, int s, int p, int P, int Q) {
+  const int c8n = C >> 3;
+  const size_t total = (size_t)N * H * W * c8n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    const size_t pix = i / c8n;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const size_t n = pix / ((size_t)H * W);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    // windows (ph, pw) with ph*s - p <= h <= ph*s - p + k - 1
+    int ph_lo = (h + p - k + 1 + s - 1) / s;      // ceil, arguments may be negative only when the result is <= 0
+    if (h + p - k + 1 < 0) ph_lo = 0;
+    int ph_hi = (h + p) / s;
+    if (ph_hi > P - 1) ph_hi = P - 1;
+    int pw_lo = (w + p - k + 1 + s - 1) / s;
+    if (w + p - k + 1 < 0) pw_lo = 0;
+    int pw_hi = (w + p) / s;
+    if (pw_hi > Q - 1) pw_hi = Q - 1;
+    for (int ph = ph_lo; ph <= ph_hi; ++ph) {
+      const int r = h - (ph * s - p);
+      for (int pw = pw_lo; pw <= pw_hi; ++pw) {
+        const int t = w - (pw * s - p);
+        const uint32_t li = (uint32_t)(r * k + t);
+        const size_t o = ((n * P + ph) * Q + pw) * c8n + c8;
+        const uint2 packed = __ldg(reinterpret_cast<const uint2*>(idx) + o);
+        float g[8];
+        load8(dy, F32 ? 1 : 0, o, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t e = ((j < 4 ? packed.x : packed.y) >> (8 * (j & 3))) & 0xffu;
+          if (e == li) acc[j] += g[j];
+        }
+      }
+    }
+    store8(dx, F32 ? 1 : 0, i, acc);
+  }
+}
+
+int launch_maxpool_fwd(int N, int H, int W, int C, int k, int s, int p, const void* x, int f32, void* y, uint8_t* idx,
+                       cudaStream_t st) {
+  const int P = (H + 2 * p - k) / s + 1, Q = (W + 2 * p - k) / s + 1;
+  const size_t total = (size_t)N * P * Q * (C / 8);
+  const int grid = grid_for(total, 256, 148 * 16);
+  if (f32) maxpool_fwd_kernel<true><<<grid, 256, 0, st>>>(x, y, idx, N, H, W, C, k, s, p, P, Q);
+  else maxpool_fwd_kernel<false><<<grid, 256, 0, st>>>(x, y, idx, N, H, W, C, k, s, p, P, Q);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
+int launch_maxpool_bwd(int N, int H, int W, int C, int k, int s, int p, const void* dy, const uint8_t* idx, int f32,
+                       void* dx, cudaStream_t st) {
+  const int P = (H + 2 * p - k) / s + 1, Q = (W + 2 * p - k) / s + 1;
+  const size_t total = (size_t)N * H * W * (C / 8);
+  const int grid = grid_for(total, 256, 148 * 16);
+  if (f32) maxpool_bwd_kernel<true><<<grid, 256, 0, st>>>(dy, idx, dx, N, H, W, C, k, s, p, P, Q);
+  else maxpool_bwd_kernel<false><<<grid, 256, 0, st>>>(dy, idx, dx, N, H, W, C, k, s, p, P, Q);
   PP_POST_LAUNCH();
   return PP_OK;
 }

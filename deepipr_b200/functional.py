@@ -388,7 +388,7 @@ class _ConvBlockFn(torch.autograd.Function):
     (reference: passportconv2d.py:218-222, passportconv2d_private.py:215-218, conv2d.py:29-36)."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, prepared: PreparedWeight, o: BlockOpts):
+    def forward(ctx, x, weight, gamma, beta, prepared: PreparedWeight, o: BlockOpts, residual=None):
         spec = o.spec
         N, Cx, H, W = x.shape
         if Cx != spec.C:
@@ -399,8 +399,8 @@ class _ConvBlockFn(torch.autograd.Function):
             raise RuntimeError("deepipr_b200: weight operands were prepared for another arithmetic type")
         adt = act_dtype(o.dtype)
         xc = to_nhwc(x.detach(), o.dtype)
-        need_grad = any(ctx.needs_input_grad[:4])
-        keep_z = need_grad or o.norm in (L.PP_NORM_BN_TRAIN, L.PP_NORM_GN)
+        need_grad = any(ctx.needs_input_grad[:4]) or ctx.needs_input_grad[6]
+        keep_z = need_grad or o.norm in (L.PP_NORM_BN_TRAIN, L.PP_NORM_GN) or residual is not None
         d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, dtype=o.dtype)
         y = torch.empty((N, spec.O, P, Q), dtype=adt, device=dev, memory_format=torch.channels_last)
         z = torch.empty((N, P, Q, spec.O), dtype=torch.float32 if o.z_f32 else torch.bfloat16, device=dev) \
@@ -411,10 +411,18 @@ class _ConvBlockFn(torch.autograd.Function):
         g = None if gamma is None else gamma.detach().reshape(-1).float().contiguous()
         b = None if beta is None else beta.detach().reshape(-1).float().contiguous()
         ws, nbytes = workspace(d, key, L.PP_WS_FWD, dev)
-        L.check(L.load().pp_conv_block_fwd(
+        res = None
+        if residual is not None:
+            # residual join folded into the block's last pass: y = bf16(relu(...)) + residual (see pp_conv_block_fwd_res)
+            if z is None or o.dtype != L.PP_DTYPE_BF16 or residual.shape != y.shape:
+                raise RuntimeError("deepipr_b200: fused residual join needs a bf16 block that keeps z and a residual "
+                                   "of the output's shape")
+            res = to_nhwc_bf16(residual.detach())
+        L.check(L.load().pp_conv_block_fwd_res(
             C.byref(d), L.ptr(xc), L.ptr(prepared.wf), L.ptr(g), L.ptr(b), L.ptr(o.running_mean),
-            L.ptr(o.running_var), L.ptr(z), L.ptr(y), L.ptr(save_mean), L.ptr(save_invstd), L.ptr(ws),
+            L.ptr(o.running_var), L.ptr(z), L.ptr(y), L.ptr(save_mean), L.ptr(save_invstd), L.ptr(res), L.ptr(ws),
             C.c_size_t(nbytes), _stream()), "pp_conv_block_fwd")
+        ctx.res_dtype = None if residual is None else residual.dtype
         if need_grad:
             ctx.save_for_backward(xc, z, g, b, save_mean, save_invstd)
             # gradients that can be accumulated by the kernels themselves into a flat gradient buffer
@@ -481,7 +489,9 @@ class _ConvBlockFn(torch.autograd.Function):
         for slot in (sw, sg, sb):
             if slot:
                 slot[0].direct_done(slot[1])
-        return dx, (None if sw else dw), (None if sg else gg), (None if sb else gb), None, None
+        # the join is y = block + residual: the residual receives the upstream gradient unchanged (no kernel)
+        g_res = gy.to(ctx.res_dtype) if (ctx.res_dtype is not None and ctx.needs_input_grad[6]) else None
+        return dx, (None if sw else dw), (None if sg else gg), (None if sb else gb), None, None, g_res
 
 
 @dataclass
@@ -598,10 +608,14 @@ def passport_conv(x, weight, prepared: PreparedWeight, opts: BlockOpts, pc: Pass
     return out
 
 
-def conv_block(x, weight, gamma, beta, prepared: PreparedWeight, opts: BlockOpts):
+def conv_block(x, weight, gamma, beta, prepared: PreparedWeight, opts: BlockOpts, residual=None):
+    """``residual`` (optional, >= 0 everywhere, e.g. another block's post-ReLU output): the residual join of a basic
+    unit folded into the block's last pass, y = block(x) + residual."""
     require_cuda(x, "block input")
     require_cuda(weight, "conv weight")
-    return _ConvBlockFn.apply(x, weight, gamma, beta, prepared, opts)
+    if residual is not None:
+        require_cuda(residual, "residual")
+    return _ConvBlockFn.apply(x, weight, gamma, beta, prepared, opts, residual)
 
 
 class _AddReluFn(torch.autograd.Function):
@@ -636,6 +650,52 @@ def add_relu(a, b):
             and (a.is_contiguous() or (a.dim() == 4 and a.is_contiguous(memory_format=torch.channels_last)))):
         return _AddReluFn.apply(a, b)
     return torch.relu(a + b)
+
+
+class _MaxPoolFn(torch.autograd.Function):
+    """nn.MaxPool2d(k, s, p) on a dense channels_last tensor (pp_maxpool_fwd / _bwd): the pooling layers of the
+    reference nets (resnet_passport*.py ImageNet stem, alexnet_passport.py:37-38)."""
+
+    @staticmethod
+    def forward(ctx, x, k, s, p):
+        N, Cc, H, W = x.shape
+        P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        xc = x.detach().contiguous(memory_format=torch.channels_last)
+        f32 = int(xc.dtype == torch.float32)
+        y = torch.empty((N, Cc, P, Q), dtype=xc.dtype, device=x.device, memory_format=torch.channels_last)
+        idx = torch.empty((N, P, Q, Cc), dtype=torch.uint8, device=x.device)
+        L.check(L.load().pp_maxpool_fwd(N, H, W, Cc, k, s, p, L.ptr(xc), f32, L.ptr(y), L.ptr(idx), _stream()),
+                "pp_maxpool_fwd")
+        ctx.save_for_backward(idx)
+        ctx.geom = (N, Cc, H, W, k, s, p)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (idx,) = ctx.saved_tensors
+        N, Cc, H, W, k, s, p = ctx.geom
+        g = gy.contiguous(memory_format=torch.channels_last)
+        f32 = int(g.dtype == torch.float32)
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g, f32 = g.float(), 1
+        dx = torch.empty((N, Cc, H, W), dtype=g.dtype, device=g.device, memory_format=torch.channels_last)
+        L.check(L.load().pp_maxpool_bwd(N, H, W, Cc, k, s, p, L.ptr(g), L.ptr(idx), f32, L.ptr(dx), _stream()),
+                "pp_maxpool_bwd")
+        return dx.to(gy.dtype), None, None, None
+
+
+def max_pool2d_supported(x, k, s, p):
+    return (x.is_cuda and x.dim() == 4 and x.dtype in (torch.bfloat16, torch.float32) and x.shape[1] % 8 == 0
+            and x.is_contiguous(memory_format=torch.channels_last) and 1 <= k <= 15 and 2 * p <= k
+            and x.shape[2] + 2 * p >= k and x.shape[3] + 2 * p >= k)
+
+
+def max_pool2d(x, k, s, p):
+    """F.max_pool2d(x, k, s, p) for dense channels_last bf16 / fp32 CUDA tensors with C % 8 == 0."""
+    require_cuda(x, "max-pool input")
+    if not max_pool2d_supported(x, k, s, p):
+        raise RuntimeError("deepipr_b200.max_pool2d: unsupported input (needs channels_last bf16/fp32, C % 8 == 0)")
+    return _MaxPoolFn.apply(x, int(k), int(s), int(p))
 
 
 # ---------------------------------------------------------------- raw building blocks (tests / profiling)

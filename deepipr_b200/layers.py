@@ -222,7 +222,20 @@ class ConvBlock(nn.Module, _FusedConvMixin):
     def reset_parameters(self):
         init.kaiming_normal_(self.conv.weight, mode='fan_out', nonlinearity='relu')
 
-    def forward(self, x):
+    def can_fuse_residual(self, x):
+        """True when forward(x, residual=...) can fold the residual join of a basic unit into this block's last pass
+        (bf16 arithmetic, batch-norm or no norm, a call that keeps z: training-mode BN or autograd recording)."""
+        norm = _norm_mode(self.bn)
+        if norm not in (L.PP_NORM_NONE, L.PP_NORM_BN_TRAIN, L.PP_NORM_BN_EVAL) or self.relu is None:
+            return False
+        if self._dtype(x, norm) != L.PP_DTYPE_BF16:
+            return False
+        return norm == L.PP_NORM_BN_TRAIN or torch.is_grad_enabled()
+
+    def forward(self, x, residual=None):
+        """``residual`` (extension over the reference signature, used by nets.BasicUnit): a tensor >= 0 of the output's
+        shape that is added after the ReLU, i.e. the unit's residual join folded into this block
+        (F.relu(out + shortcut) of resnet_passport_private.py:78-85 with both summands already non-negative)."""
         F_.require_cuda(x, "ConvBlock input")
         self._check_conv()
         norm = _norm_mode(self.bn)
@@ -242,7 +255,26 @@ class ConvBlock(nn.Module, _FusedConvMixin):
             gamma, beta = self.bn.weight, self.bn.bias
         o = self._bn_opts(norm, self.relu is not None, self.z_f32, x, dtype)
         o.direct_grad_ok = True      # conv.weight / bn.weight / bn.bias (or conv.bias) feed this operator only
-        return F_.conv_block(x, self.conv.weight, gamma, beta, prepared, o)
+        if residual is not None:
+            if not self.can_fuse_residual(x):
+                raise RuntimeError("deepipr_b200: this ConvBlock call cannot fuse a residual (see can_fuse_residual)")
+        return F_.conv_block(x, self.conv.weight, gamma, beta, prepared, o, residual)
+
+
+class MaxPool2d(nn.MaxPool2d):
+    """nn.MaxPool2d whose channels_last CUDA inputs take the library's NHWC kernels (pp_maxpool_fwd / _bwd: one pass
+    over the bytes each way, argmax kept as one byte per output); anything else — CPU tensors, NCHW memory, dilation,
+    ceil_mode, return_indices — is the stock module.  Same constructor, no parameters, same state_dict."""
+
+    def forward(self, x):
+        def one(v):
+            return v if isinstance(v, int) else (v[0] if v[0] == v[1] else None)
+
+        k, s, p, d = one(self.kernel_size), one(self.stride), one(self.padding), one(self.dilation)
+        if (None not in (k, s, p) and d == 1 and not self.ceil_mode and not self.return_indices
+                and F_.max_pool2d_supported(x, k, s, p)):
+            return F_.max_pool2d(x, k, s, p)
+        return super().forward(x)
 
 
 def _signature_bits(b, o):

@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as F_
-from .layers import ConvBlock, PassportBlock, PassportPrivateBlock
+from .layers import ConvBlock, MaxPool2d, PassportBlock, PassportPrivateBlock
 
 SCHEMES = ('normal', 'v1', 'private')
 
@@ -108,10 +108,43 @@ class BasicUnit(nn.Module):
         if stride != 1 or in_planes != planes:
             self.shortcut = _make_block(blocks, scheme, kw.get('shortcut'), in_planes, planes, 1, stride, 0, norm_type)
 
+    #: set by ResNet18: the unit's input is itself a post-ReLU tensor (the stem's or the previous unit's output), so
+    #: with an identity shortcut both summands of the join are >= 0 — as they always are with a projection shortcut,
+    #: whose block ends in a ReLU like every block of the reference nets.  The join relu(out + shortcut) is then a plain
+    #: sum with an identity backward, which convbn_2 folds into its last pass (ConvBlock.forward(residual=)) or, for a
+    #: passport convbn_2, one add launch computes.  Units used on their own keep the general relu(a + b) kernel.
+    input_nonneg = False
+    #: A/B switch (tests): False keeps the general relu(a + b) kernel even where the join is a plain sum
+    fuse_join = True
+
+    def _join_is_plain_sum(self):
+        if not self.fuse_join:
+            return False
+        last_relu = getattr(self.convbn_2, 'relu', None) is not None
+        if isinstance(self.shortcut, nn.Sequential):
+            return last_relu and self.input_nonneg and len(self.shortcut) == 0
+        return last_relu and getattr(self.shortcut, 'relu', None) is not None
+
     def forward(self, x, force_passport=False, ind=0):
         out = _call(self.convbnrelu_1, x, force_passport, ind)
-        out = _call(self.convbn_2, out, force_passport, ind)
-        sc = x if isinstance(self.shortcut, nn.Sequential) else _call(self.shortcut, x, force_passport, ind)
+        identity = isinstance(self.shortcut, nn.Sequential)
+        plain = self._join_is_plain_sum() and out.is_cuda
+        c2 = self.convbn_2
+        # Folding the join into convbn_2 needs the shortcut first.  Passport blocks must run in the reference's order
+        # (convbnrelu_1, convbn_2, shortcut: resnet_passport_private.py:67-85) because a block without keys draws them
+        # from numpy's global RNG on its first forward (passportconv2d_private.py:198-207) — only plain ConvBlocks,
+        # which consume nothing, are reordered.
+        if (plain and isinstance(c2, ConvBlock) and (identity or isinstance(self.shortcut, ConvBlock))
+                and c2.can_fuse_residual(out)):
+            sc = x if identity else self.shortcut(x)
+            if sc.dtype == out.dtype:
+                return c2(out, residual=sc)
+            out = c2(out)
+        else:
+            out = _call(c2, out, force_passport, ind)
+            sc = x if identity else _call(self.shortcut, x, force_passport, ind)
+        if plain:
+            return out + sc            # relu(out + sc) == out + sc for out, sc >= 0; the gradient passes unchanged
         # F.relu(out + shortcut) (resnet_passport_private.py:78-85): one fused kernel
         return F_.add_relu(out, sc)
 
@@ -146,7 +179,7 @@ class ResNet18(nn.Module):
         stem_kw = pk['convbnrelu_1']
         if num_classes == 1000 or imagenet:
             self.convbnrelu_1 = nn.Sequential(_make_block(blocks, scheme, stem_kw, 3, 64, 7, 2, 3, norm_type),
-                                              nn.MaxPool2d(3, 2, 1))
+                                              MaxPool2d(3, 2, 1))
         else:
             self.convbnrelu_1 = _make_block(blocks, scheme, stem_kw, 3, 64, 3, 1, 1, norm_type)
         in_planes = 64
@@ -154,6 +187,7 @@ class ResNet18(nn.Module):
             units = []
             for bi, st in enumerate((stride, 1)):
                 units.append(BasicUnit(scheme, in_planes, planes, st, pk[f'layer{li}'][str(bi)], norm_type, blocks))
+                units[-1].input_nonneg = True      # fed by the stem (ReLU) or by the previous unit's join
                 in_planes = planes
             setattr(self, f'layer{li}', nn.Sequential(*units))
         self.linear = nn.Linear(512, num_classes)
@@ -267,7 +301,7 @@ class AlexNetCifar(nn.Module):
         layers, inp = [], in_channels
         for idx in range(8):
             if idx in (1, 3, 7):
-                layers.append(nn.MaxPool2d(2, 2))
+                layers.append(MaxPool2d(2, 2))
                 continue
             k, p = _ALEX_KP[idx]
             layers.append(_make_block(blocks, scheme, passport_kwargs[str(idx)], inp, _ALEX_OUT[idx], k, 1, p, norm_type))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 13
+#define PP_ABI_VERSION 14
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -175,6 +175,19 @@ int pp_conv_block_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, c
                       float* save_mean, float* save_invstd, void* workspace, size_t ws_bytes,
                       void* stream);
 
+/* The same block with the residual join of a ResNet basic unit folded into its last pass
+ * (models/resnet_passport_private.py:78-85, resnet_passport.py:77-84, resnet_normal.py:24-26):
+ *   y = bf16(relu(gamma * norm(conv(x, W)) + beta)) + residual        residual: bf16, same shape and layout as y
+ * The reference computes relu(out + shortcut) where out and shortcut are both outputs of blocks that end in a ReLU
+ * (every block of its ResNets does, convbn_2 and the shortcut included), so the outer ReLU is the identity; the caller
+ * passes `residual` only when it is known to be >= 0 (a block / unit output).  The inner rounding makes the result
+ * bit-identical to the separate add pass it replaces.  residual == NULL: exactly pp_conv_block_fwd.  bf16 tensors,
+ * PP_NORM_NONE / PP_NORM_BN_* with the z buffer; other requests return PP_EUNSUPPORTED. */
+int pp_conv_block_fwd_res(const PPConvDesc* d, const void* x, const void* w_fprop, const float* gamma,
+                          const float* beta, float* running_mean, float* running_var, void* z, void* y,
+                          float* save_mean, float* save_invstd, const void* residual, void* workspace,
+                          size_t ws_bytes, void* stream);
+
 /* Backward of pp_conv_block_fwd (autograd of the same reference lines).
  *   dy bf16 [N,P,Q,O];  dx bf16 [N,H,W,C] or NULL;  dw_oihw fp32 [O,C,kh,kw] or NULL
  *   dgamma / dbeta fp32 [O] (always written; added to when d->flags has PP_FLAG_ACC_DGAMMA / _DBETA,
@@ -235,6 +248,17 @@ int pp_conv_wgrad(const PPConvDesc* d, const void* dz, const void* x, float* dw_
  * gx = gy * [y > 0] (the same gradient flows to both inputs). */
 int pp_add_relu_fwd(size_t n, const void* a, const void* b, void* y, void* stream);
 int pp_add_relu_bwd(size_t n, const void* gy, const void* y, void* gx, void* stream);
+
+/* nn.MaxPool2d(k, stride, pad) (dilation 1, floor mode) on a dense NHWC tensor, bf16 or fp32 (f32 != 0): the pooling
+ * layers between the blocks of the reference nets (models/resnet_passport.py / resnet_passport_private.py:
+ * MaxPool2d(3, 2, 1) behind the ImageNet stem; models/alexnet_passport.py:37-38: MaxPool2d(2, 2)).
+ *   y[n,ph,pw,c] = max over the window; argmax[n,ph,pw,c] = position r*k + t of the FIRST maximum in scan order
+ *   (ATen's rule), one byte per output element;  dx = gather of dy through argmax (no atomics, deterministic).
+ * C % 8 == 0.  x: [N,H,W,C], y / argmax / dy: [N,P,Q,C] with P = (H + 2 pad - k) / stride + 1, dx: [N,H,W,C]. */
+int pp_maxpool_fwd(int N, int H, int W, int C, int k, int stride, int pad, const void* x, int f32, void* y,
+                   uint8_t* argmax, void* stream);
+int pp_maxpool_bwd(int N, int H, int W, int C, int k, int stride, int pad, const void* dy, const uint8_t* argmax,
+                   int f32, void* dx, void* stream);
 
 /* Fused SGD(momentum, weight decay) step on one flat fp32 buffer (classification.py:47-50):
  *   g' = g + wd*p;  buf = mom*buf + g' (buf = g' on the first step);  p -= lr*buf */

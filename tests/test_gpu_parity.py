@@ -117,6 +117,8 @@ GEOMS = [  # N, C, H, O, k, s, p
     # 64 -> 64 channels: tap-paired weight gradient (row-shifted dz in the upper accumulator rows) at 2 / 4 / 8 image
     # rows per 64-pixel chunk, batch 1 included
     (3, 64, 16, 64, 3, 1, 1), (1, 64, 32, 64, 3, 1, 1), (5, 64, 8, 64, 3, 1, 1),
+    # ImageNet layer1: 56x56 maps, pixels-on-N tiles of 4 image rows (N = 224)
+    (2, 64, 56, 64, 3, 1, 1),
 ]
 
 
@@ -1093,3 +1095,77 @@ def test_single_kernel_block_other_geometries_vs_sequence(geom):
     assert rel_l2(a["dx"], b["dx"]) < 1e-3 and rel_l2(a["rv"], b["rv"]) < 1e-5
     for key, gref in b["grads"].items():
         assert rel_l2(a["grads"][key], gref) < 1e-3, key
+
+
+@pytest.mark.parametrize("geom", [(6, 64, 64, 1, 16), (5, 64, 128, 2, 16), (4, 256, 512, 2, 8)])
+def test_residual_join_folded_into_the_block_equals_the_separate_pass(geom):
+    """nets.BasicUnit with a post-ReLU input: relu(out + shortcut) (resnet_passport_private.py:78-85) has both summands
+    >= 0, so it is a plain sum that convbn_2's affine pass computes (pp_conv_block_fwd_res) with an identity backward.
+    Outputs and every gradient must equal, bit for bit, the general path (block, then the relu(a + b) kernel and its
+    masked backward); dx is compared where x > 0 (at x == 0 == y the general path masks what an upstream ReLU masks
+    again anyway)."""
+    N, cin, planes, stride, H = geom
+    seed_all(11)
+    unit = nets.BasicUnit('normal', cin, planes, stride, None, 'bn').cuda().train()
+    x0 = torch.relu(torch.randn(N, cin, H, H)).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    r = torch.randn(N, planes, H // stride, H // stride).to(torch.bfloat16).cuda()
+
+    def run(fuse):
+        unit.input_nonneg = True
+        unit.fuse_join = fuse
+        unit.zero_grad()
+        for m in unit.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.reset_running_stats()
+        x = x0.clone().requires_grad_(True)
+        lib = L.load()
+        lib.pp_launch_count(1)
+        y = unit(x)
+        (y.float() * r.float()).sum().backward()
+        n = lib.pp_launch_count(0)
+        return y.detach(), x.grad.detach(), {k: p.grad.detach().clone() for k, p in unit.named_parameters()}, n
+
+    y_sep, dx_sep, g_sep, n_sep = run(False)
+    y_fus, dx_fus, g_fus, n_fus = run(True)
+    assert n_fus <= n_sep                # no relu(a + b) launch forward, none backward (the separate path may use the
+                                         # single-kernel block for convbn_2 where it applies, hence not always - 2)
+    assert torch.equal(y_sep, y_fus)
+    mask = (x0 > 0)
+    assert torch.equal(dx_sep * mask, dx_fus * mask)
+    for k in g_sep:
+        assert torch.equal(g_sep[k], g_fus[k]), k
+    # and against the CPU oracle (bf16-operand model) like every other block
+    unit.input_nonneg = True
+    oracle = po.mirror(torch.nn.Sequential(unit), round_bf16=True).train()   # (a parent, so the unit itself is mirrored)
+    xo = x0.float().cpu().requires_grad_(True)
+    yo = oracle[0](xo)
+    (yo * r.float().cpu()).sum().backward()
+    assert rel_l2(y_fus, bf16r(yo)) < ACT_TOL
+    assert rel_l2(dx_fus * mask, xo.grad * mask.cpu()) < GRAD_TOL
+
+
+@pytest.mark.parametrize("case", [(2, 64, 12, 12, 3, 2, 1, torch.bfloat16), (3, 64, 9, 7, 3, 2, 1, torch.bfloat16),
+                                  (2, 192, 16, 16, 2, 2, 0, torch.float32), (1, 8, 5, 5, 3, 1, 1, torch.float32),
+                                  (4, 256, 8, 8, 2, 2, 0, torch.bfloat16)])
+def test_nhwc_max_pool_equals_aten_bit_for_bit(case):
+    """layers.MaxPool2d on channels_last tensors (pp_maxpool_fwd / _bwd) vs F.max_pool2d on the CPU — the operator
+    the reference's nn.MaxPool2d layers call (alexnet_passport.py:37-38, ImageNet stem of resnet_passport*.py).  The
+    inputs are post-ReLU (half of the elements tie at zero), so the first-maximum rule of the backward is exercised."""
+    N, C, H, W, k, s, p, dt = case
+    seed_all(5)
+    x0 = torch.relu(torch.randn(N, C, H, W)).to(dt)
+    pool = layers.MaxPool2d(k, s, p)
+    xg = x0.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    lib = L.load()
+    lib.pp_launch_count(1)
+    y = pool(xg)
+    assert lib.pp_launch_count(0) == 1 and y.is_contiguous(memory_format=torch.channels_last)
+    xc = x0.float().requires_grad_(True)
+    yc = torch.nn.functional.max_pool2d(xc, k, s, p)
+    assert torch.equal(y.float().cpu(), yc.detach())
+    r = torch.randn_like(yc).to(dt)
+    y.backward(r.cuda())
+    yc.backward(r.float())
+    assert torch.equal(xg.grad.float().cpu(), xc.grad.to(dt).float())
+    # NCHW-contiguous or CPU inputs are the stock module
+    assert torch.equal(pool(x0.float()), yc.detach())
