@@ -213,10 +213,19 @@ def reference_trainer(cfg, device, channels_last=False):
     if channels_last:
         model = model.to(memory_format=torch.channels_last)
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0001)
-    if cfg["scheme"] == "private":
-        trainer = mods["experiments.trainer_private"].TrainerPrivate(model, opt, None, device)
-    else:
-        trainer = mods["experiments.trainer"].Trainer(model, opt, None, device)
+    # The reference's trainers wrap the model in nn.DataParallel whenever torch.cuda.device_count() > 1
+    # (experiments/trainer.py:92-93, trainer_private.py:110-111) — also for a CPU model, which then fails.  This arm is
+    # one process on one device (the CPU, or one GPU): construct the trainer the way CUDA_VISIBLE_DEVICES=<one device>
+    # would make it see the machine.  Nothing in the reference is modified.
+    real_count = torch.cuda.device_count
+    torch.cuda.device_count = lambda: min(1, real_count())
+    try:
+        if cfg["scheme"] == "private":
+            trainer = mods["experiments.trainer_private"].TrainerPrivate(model, opt, None, device)
+        else:
+            trainer = mods["experiments.trainer"].Trainer(model, opt, None, device)
+    finally:
+        torch.cuda.device_count = real_count
     return model, trainer
 
 
@@ -293,12 +302,23 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=5)
-    ap.add_argument("--graph", action="store_true", help="run the value / e2e legs through the CUDA-graph step")
+    ap.add_argument("--graph", action="store_true", help="(default) value / e2e legs replay the step as one CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches (~540 per step) instead of the graph replay")
     ap.add_argument("--legs", default="value,e2e,roofline,eager,dropin,small_batch,configs,shared",
                     help="comma list: value (always), e2e, roofline, eager (the reference on this GPU), dropin (the "
                          "reference's trainer on the patched blocks), small_batch (batch 64 / 256, eager vs CUDA "
                          "graph), configs (short lines of the other BASELINE configs), shared (trunk CSE)")
     args = ap.parse_args()
+
+    # stdout carries exactly ONE JSON line.  Native libraries write to file descriptor 1 behind Python's back (NCCL
+    # prints its version banner there): keep the real stdout aside for the JSON line and point fd 1 at stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -324,7 +344,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -380,6 +400,7 @@ def main():
         if graph:
             graphed = GraphedStepRunner(runner, *data[0])
             step = graphed.step
+            runner.graphed = graphed
         return model, opt, runner, data, step
 
     def timed(step, data, steps, warmup):
@@ -395,7 +416,9 @@ def main():
         return max_over_ranks(e0.elapsed_time(e1))
 
     # ---------------- leg 1 (`value`): inputs resident in HBM
-    use_graph = args.graph and world == 1
+    # The step (zero_grad, forward(s), losses, backward, bucketed NCCL all-reduces when N > 1, fused SGD) is captured
+    # once and replayed: trainer.GraphedStepRunner.  --no-graph runs the same step eagerly.
+    use_graph = not args.no_graph
     model, opt, runner, dev_batches, step = make_runner(args.config, B, graph=use_graph)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -416,8 +439,8 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     value = args.steps * per_step * world / (ms_total * 1e-3)
-    if use_graph:       # a replay launches the captured kernels without passing through the library's counter
-        launches = None
+    if use_graph:       # a replay re-launches the kernels counted while the step was captured
+        launches = runner.graphed.launches_per_replay * args.steps
 
     # ---------------- leg 2 (`e2e`): the public trainer API on HOST buffers.  deepipr_b200.trainer.TrainerPrivate.train
     # (the call a user makes, same signature as experiments/trainer_private.py:118) over a loader of pinned host
@@ -453,14 +476,14 @@ def main():
 
     # ---------------- leg 3 (`roofline`): per-kernel CUDA-event timing on the kernels' own stream
     roof = roof_w = roof_hbm = roof_fused = None
-    if "roofline" in legs and not use_graph:
+    if "roofline" in legs:                   # (eager steps: the per-kernel event instrumentation wraps real launches)
         if rank == 0:
             lib.pp_profile_enable(1)
         for i in range(3):
             runner.step(*dev_batches[i % 4])
         barrier()
         lib.pp_profile_enable(0)
-    if rank == 0 and "roofline" in legs and not use_graph:
+    if rank == 0 and "roofline" in legs:
         def read(kind, c=0, nout=0, taps=0):
             ms, fl, n = C.c_double(0), C.c_double(0), C.c_int(0)
             lib.pp_profile_read(kind, c, nout, taps, C.byref(ms), C.byref(fl), C.byref(n))
@@ -533,6 +556,8 @@ def main():
 
     sig = test_signature(model) if rank == 0 else {}
     model.train()
+    if getattr(runner, "graphed", None) is not None:
+        runner.graphed.release()
     del model, opt, runner, dev_batches, step
     torch.cuda.empty_cache()
 
@@ -545,10 +570,12 @@ def main():
                 continue
             c = CONFIGS[name]
             try:
-                m2, o2, r2, d2, s2 = make_runner(name, c["batch"], ddp=False)
+                m2, o2, r2, d2, s2 = make_runner(name, c["batch"], graph=use_graph, ddp=False)
                 n2 = 8
                 ms2 = timed(s2, d2, n2, 3)
                 v2 = n2 * c["batch"] / (ms2 * 1e-3)
+                if getattr(r2, "graphed", None) is not None:
+                    r2.graphed.release()
                 configs_out[name] = {"value": v2, "unit": UNIT, "ms_per_step": ms2 / n2, "per_gpu_batch": c["batch"],
                                      "dtype": c["dtype"], "workload": c["workload"],
                                      "conv_roofline_frac_whole_step":
@@ -638,9 +665,23 @@ def main():
                 "cpu_baseline": cpu_baseline, "torch_eager_gpu": eager, "reference_trainer_on_patched_blocks": dropin,
                 "small_batch": small, "configs": configs_out, "value_shared_trunk": shared,
                 "sign_bit_accuracy": (sum(sig.values()) / len(sig)) if sig else None, "last_step": last}
-        print(json.dumps(line))
+        emit(line)
+    # teardown: captured graphs hold references into the NCCL communicator, so they go first; and a communicator
+    # teardown that does not return must not turn a finished measurement into a hung process
+    for holder in (locals().get("trainer"), locals().get("runner")):
+        g = getattr(holder, "_graphed", None) or getattr(holder, "graphed", None)
+        if g is not None:
+            g.release()
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     if world > 1:
+        bail = threading.Timer(45.0, lambda: os._exit(0))
+        bail.daemon = True
+        bail.start()
+        dist.barrier()
         dist.destroy_process_group()
+        bail.cancel()
 
 
 def dropin_run(cfg, B, dev, steps):

@@ -225,12 +225,13 @@ struct FwdCfg {
   static constexpr int kStageBytes = RESB ? kStageA : kStageA + kStageB;
   static constexpr int kResBytes = RESB ? kResMaxSteps * kStageB : 0;
   static constexpr int kStages = RESB ? 8 : ((BN == 64) ? 8 : (BN == 128 ? 6 : 4));
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
+  static constexpr int kTmemCols = BN == 192 ? 512 : 2 * BN;  // two accumulator buffers (allocations are powers of 2)
   static constexpr int kScratch = 2 * BN * 4 /*a,b*/ + 4 * 2 * BN * 4 /*per-warp column sums*/ +
                                   2 * kMaxStatsN * 4 /*per-CTA running column sums*/ +
                                   4 * 4096 /*per-warp store staging tiles*/;
   static constexpr int kSmemBytes =
       1024 /*align slack*/ + kResBytes + kStages * kStageBytes + kScratch + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 232448, "tapgemm stage configuration exceeds the 227 KiB of shared memory per CTA");
 };
 
 // TF32: activations and weights are fp32 in memory and enter the tensor core as TF32 (tcgen05.mma kind::tf32, K = 8
@@ -243,6 +244,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ TapGemmDev p) {
   using Cfg = FwdCfg<BN, RESB>;
   constexpr int kBKe = TF32 ? 32 : kBK;        // channels (elements) per pipeline stage
+  constexpr int kAccStride = BN == 192 ? 256 : BN;   // TMEM column distance of the two accumulator buffers
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_base = smem;                       // [ksteps][BN x 64] resident weight blocks (RESB only)
@@ -356,7 +358,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full[stage], phase, 300 + stage);
         tc_fence_after();
@@ -425,7 +427,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
       mbar_wait(&tfull[acc], acc_phase, 400 + acc);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * kAccStride;
 #pragma unroll 1
       for (int j = 0; j < BN / 32; ++j) {
         uint32_t raw[32];
@@ -553,6 +555,8 @@ static int pick_bn(const TapGemm& g) {
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
   if (g.Nout % 256 == 0 && m_tiles * (g.Nout / 256) >= sms) return 256;
+  // 192 / 384 output channels (AlexNet): 192-wide tiles instead of 3 x 64 / 3 x 128
+  if (g.Nout % 192 == 0 && g.Nout % 256 != 0 && m_tiles * (g.Nout / 192) >= sms) return 192;
   if (g.Nout % 128 == 0) return 128;
   return 64;
 }
@@ -1019,12 +1023,14 @@ int tapgemm_tcgen05(const TapGemm& g, const void* act, const void* B, const TapE
   if (g.tf32) {
     switch (pick_bn(g)) {
       case 256: return launch_tapgemm<256, false, true>(g, act, B, e, s);
+      case 192: return launch_tapgemm<192, false, true>(g, act, B, e, s);
       case 128: return launch_tapgemm<128, false, true>(g, act, B, e, s);
       default: return launch_tapgemm<64, false, true>(g, act, B, e, s);
     }
   }
   switch (pick_bn(g)) {
     case 256: return launch_tapgemm<256, false>(g, act, B, e, s);
+    case 192: return launch_tapgemm<192, false>(g, act, B, e, s);
     case 128: return launch_tapgemm<128, false>(g, act, B, e, s);
     default:
       if (g.Nout == 64 && g.ntaps * (g.C / kBK) <= kResMaxSteps) return launch_tapgemm<64, true>(g, act, B, e, s);
@@ -1611,10 +1617,11 @@ struct WgCfg {
   static constexpr int kStageA = kSlabsA * kSlabBytes;   // 16 KiB
   static constexpr int kStageB = kSlabsB * kSlabBytes;   // 8 / 16 / 32 KiB
   static constexpr int kStageBytes = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
   static constexpr int kPixPerMma = TF32 ? 8 : 16;
-  static constexpr int kTmemCols = BN;
+  static constexpr int kTmemCols = BN == 192 ? 256 : BN;   // allocations are powers of 2
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+  static_assert(kSmemBytes <= 232448, "wgrad stage configuration exceeds the 227 KiB of shared memory per CTA");
 };
 
 struct WgradDev {
@@ -1792,7 +1799,11 @@ bool wgrad_tcgen05_supported(const TapGemm& g, int O) {
   return true;
 }
 
-static int wgrad_bn(int O) { return (O % 256 == 0) ? 256 : ((O % 128 == 0) ? 128 : 64); }
+static int wgrad_bn(int O) {
+  if (O % 256 == 0) return 256;
+  if (O % 192 == 0) return 192;      // AlexNet: 192 / 384 output channels
+  return (O % 128 == 0) ? 128 : 64;
+}
 
 static bool wgrad_om_applies(const TapGemm& g, int O);
 static bool wgrad_om_paired(const TapGemm& g, int O);
@@ -2105,6 +2116,7 @@ int wgrad_tcgen05(const TapGemm& g, const void* x, const void* dz, int O, float*
   if (g.tf32) {
     switch (wgrad_bn(O)) {
       case 256: return launch_wgrad<256, true>(g, x, dz, O, partial, splits, s);
+      case 192: return launch_wgrad<192, true>(g, x, dz, O, partial, splits, s);
       case 128: return launch_wgrad<128, true>(g, x, dz, O, partial, splits, s);
       default: return launch_wgrad<64, true>(g, x, dz, O, partial, splits, s);
     }
@@ -2112,6 +2124,7 @@ int wgrad_tcgen05(const TapGemm& g, const void* x, const void* dz, int O, float*
   if (wgrad_om_applies(g, O)) return launch_wgrad_om(g, x, dz, O, partial, splits, s);
   switch (wgrad_bn(O)) {
     case 256: return launch_wgrad<256>(g, x, dz, O, partial, splits, s);
+    case 192: return launch_wgrad<192>(g, x, dz, O, partial, splits, s);
     case 128: return launch_wgrad<128>(g, x, dz, O, partial, splits, s);
     default: return launch_wgrad<64>(g, x, dz, O, partial, splits, s);
   }

@@ -2,6 +2,8 @@
 // GEMV that yields gamma/beta (+ SignLoss), BatchNorm statistics finalisation, the affine+ReLU pass,
 // the two backward passes (per-channel reductions, dz), the split-K weight-gradient reduction and SGD.
 // All reductions are fixed-order (no float atomics) so results are run-to-run deterministic.
+#include <stdlib.h>
+
 #include "common.h"
 #include "vec8.cuh"
 
@@ -1137,8 +1139,92 @@ __global__ void im2col_small_f32_kernel(const float* __restrict__ x, float* __re
   }
 }
 
+// Row-tiled variant: one block per (image, output row).  The kh input rows the output row reads (W*C contiguous
+// elements each in NHWC) are staged in shared memory with their zero padding by coalesced 128-bit loads, and the Q
+// rows of `col` are then written as whole 128-bit vectors — for a fixed filter row the kw*C patch entries of an output
+// pixel are CONTIGUOUS in the staged row (they start at q*stride*C).  The element-wise gather of the kernels above
+// (one 2-byte global load per entry: 1.1 ms for the 7x7/s2 ImageNet stem at batch 256) becomes a write-bound pass.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const T* __restrict__ x, T* __restrict__ col, int H, int W,
+                                                          int C, int kh, int kw, int stride, int pad, int P, int Q,
+                                                          int Kpad) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const int rowlen = (W + 2 * pad) * C;                  // staged row incl. padding
+  int* s_off = reinterpret_cast<int*>(s_raw);            // [Kpad]: offset into the staged rows, or -1 (zero column)
+  T* s_x = reinterpret_cast<T*>(s_raw + ((Kpad * 4 + 15) & ~15));
+  const int n = blockIdx.x / P, p = blockIdx.x - n * P;
+  const int K = kh * kw * C, kwC = kw * C;
+  for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+    int v = -1;
+    if (k < K) { const int r = k / kwC; v = r * rowlen + (k - r * kwC); }
+    s_off[k] = v;
+  }
+  // stage the kh rows (zeros outside the image)
+  const int h0 = p * stride - pad;
+  const int WC = W * C;
+  for (int r = 0; r < kh; ++r) {
+    const int h = h0 + r;
+    T* dst = s_x + r * rowlen;
+    if (h < 0 || h >= H) {
+      for (int i = threadIdx.x; i < rowlen; i += blockDim.x) dst[i] = T(0.0f);
+      continue;
+    }
+    for (int i = threadIdx.x; i < pad * C; i += blockDim.x) { dst[i] = T(0.0f); dst[pad * C + WC + i] = T(0.0f); }
+    const T* src = x + ((size_t)n * H + h) * WC;
+    if ((WC % VEC) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      for (int i = threadIdx.x; i < WC / VEC; i += blockDim.x) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) dst[pad * C + i * VEC + j] = e[j];
+      }
+    } else {
+      for (int i = threadIdx.x; i < WC; i += blockDim.x) dst[pad * C + i] = src[i];
+    }
+  }
+  __syncthreads();
+  const int groups = Kpad / VEC;
+  const int total = Q * groups;
+  T* out = col + ((size_t)n * P + p) * Q * Kpad;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int q = i / groups, kg = i - q * groups;
+    const int base = q * stride * C;
+    __align__(16) T v[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int o = s_off[kg * VEC + j];
+      v[j] = o >= 0 ? s_x[o + base] : T(0.0f);
+    }
+    reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+template <typename T>
+static bool try_im2col_rows(const PPConvDesc& d, const void* x, void* col, int P, int Q, int Kpad, cudaStream_t s,
+                            int* rc) {
+  const size_t smem = (((size_t)Kpad * 4 + 15) & ~size_t(15)) + (size_t)d.kh * (d.W + 2 * d.pad) * d.C * sizeof(T);
+  if (smem > 48 * 1024 || (Kpad % (16 / (int)sizeof(T))) != 0) return false;
+  im2col_rows_kernel<T><<<d.N * P, 256, smem, s>>>((const T*)x, (T*)col, d.H, d.W, d.C, d.kh, d.kw, d.stride, d.pad, P,
+                                                  Q, Kpad);
+  count_launch();
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("im2col_rows_kernel: %s", cudaGetErrorString(e)); *rc = PP_ELAUNCH; }
+  else *rc = PP_OK;
+  return true;
+}
+
 int launch_im2col_small(const PPConvDesc& d, const void* x, void* col, size_t rows, int P, int Q, int Kpad,
                         cudaStream_t s) {
+  {
+    static int rows_on = -1;      // PP_IM2COL_ROWS=0 restores the element-wise gather (A/B comparison)
+    if (rows_on < 0) { const char* e = getenv("PP_IM2COL_ROWS"); rows_on = (e && e[0] == '0') ? 0 : 1; }
+    int rc = PP_OK;
+    if (rows_on && (size_t)d.N * P * Q == rows &&
+        (d.dtype == PP_DTYPE_TF32 ? try_im2col_rows<float>(d, x, col, P, Q, Kpad, s, &rc)
+                                  : try_im2col_rows<__nv_bfloat16>(d, x, col, P, Q, Kpad, s, &rc)))
+      return rc;
+  }
   if (d.dtype == PP_DTYPE_TF32) {
     const size_t total = rows * (size_t)(Kpad / 4);
     im2col_small_f32_kernel<<<grid_for(total, 256, 148 * 16), 256, 0, s>>>(

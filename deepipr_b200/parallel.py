@@ -17,6 +17,8 @@ per-rank (what DataParallel does too).
 import ctypes as C
 import weakref
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -106,7 +108,9 @@ class FlatParams:
 class GradBuckets:
     """Size-bounded buckets over FlatParams.flat_grad, all-reduced (mean) asynchronously as they fill."""
 
-    def __init__(self, flat: FlatParams, bucket_bytes=25 << 20, process_group=None, overlap=True):
+    def __init__(self, flat: FlatParams, bucket_bytes=None, process_group=None, overlap=True):
+        if bucket_bytes is None:      # PP_BUCKET_MB: A/B runs of the bucket size without touching the callers
+            bucket_bytes = int(float(os.environ.get("PP_BUCKET_MB", "25")) * (1 << 20))
         self.flat = flat
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1

@@ -10,6 +10,7 @@ import time
 import torch
 import torch.nn.functional as F
 
+from . import _lib as L_
 from . import functional as F_
 from .layers import PassportBlock, PassportPrivateBlock, SignLoss
 from .parallel import GradBuckets
@@ -131,15 +132,16 @@ class GraphedStepRunner:
     one launch.  What makes the step capturable: the library allocates nothing and never synchronises, TMA descriptors
     and kernel arguments are plain launch parameters, the operand / key-pool caches take the same branches every step,
     and the SGD hyper-parameters live in device memory (pp_sgd_step_dev), so a learning-rate schedule needs no
-    re-capture.  Single process only (the NCCL bucket launches of GradBuckets stay eager); batch shape is fixed.
+    re-capture.  Batch shape is fixed.  Under DDP the bucketed NCCL all-reduces that GradBuckets launches from the
+    backward hooks are captured with the step (they fork from / join the capturing stream like any side-stream work):
+    every rank replays the same graph, so the collectives stay matched; the warm-up steps create the communicator
+    eagerly, and pending eager work is drained before the capture starts.
 
     The warm-up steps capture needs are rolled back (parameters, momentum, buffers), so a graphed run follows exactly
     the trajectory of the eager one."""
 
     def __init__(self, runner: StepRunner, data, target, warmup=2):
         from .parallel import FlatSGD
-        if runner.buckets is not None:
-            raise RuntimeError("GraphedStepRunner: gradient buckets (multi-process) are not captured; use StepRunner")
         if not isinstance(runner.optimizer, FlatSGD):
             raise RuntimeError("GraphedStepRunner needs parallel.FlatSGD (its update is one capturable launch)")
         F_.require_cuda(data, "graph input")
@@ -154,12 +156,21 @@ class GraphedStepRunner:
             for _ in range(max(1, warmup)):
                 runner.step(self.x, self.t)
         torch.cuda.current_stream().wait_stream(side)
+        if runner.buckets is not None and runner.buckets.world > 1:
+            import torch.distributed as dist
+            torch.cuda.synchronize()            # no eager collective may still be in flight when the capture starts
+            dist.barrier(group=runner.buckets.group)
+            torch.cuda.synchronize()
         # everything the captured kernels point at that was allocated BEFORE the capture must outlive the graph
         self._keep = [m.__dict__.get('_pp_keypool') for m in model.modules()] + list(F_._workspace.values())
         self.graph = torch.cuda.CUDAGraph()
+        lib = L_.load()
+        before = int(lib.pp_launch_count(0))
         with torch.cuda.graph(self.graph):
             self.out = runner.step(self.x, self.t)
             self.metrics = runner.metrics
+        #: kernels of libpassport_sm100 inside the captured step (a replay re-launches exactly these)
+        self.launches_per_replay = int(lib.pp_launch_count(0)) - before
         with torch.no_grad():                              # roll the warm-up back
             flat.flat.copy_(saved[0])
             opt._buf.copy_(saved[1])
@@ -169,7 +180,17 @@ class GraphedStepRunner:
         F_.bump_weight_epoch()
 
     def matches(self, data, target):
-        return data.shape == self.x.shape and target.shape == self.t.shape and data.dtype == self.x.dtype
+        return (self.graph is not None and data.shape == self.x.shape and target.shape == self.t.shape
+                and data.dtype == self.x.dtype)
+
+    def release(self):
+        """Destroy the captured graph (call before tearing down a process group whose collectives it captured: NCCL
+        does not finish destroying a communicator while graphs that reference it are alive)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph = None
+            self.out = self.metrics = None
+            self._keep = []
 
     def step(self, data, target):
         if data.data_ptr() != self.x.data_ptr():

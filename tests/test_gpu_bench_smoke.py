@@ -38,14 +38,14 @@ def test_bench_contract_small_batch():
 def test_bench_other_configs_and_graph_mode():
     """BASELINE configs 2, 3 and 5 through --config, and the CUDA-graph step through --graph, at tiny batches."""
     for extra in (["--config", "v1_alexnet"], ["--config", "v2_cifar100"], ["--config", "v1_imagenet", "--batch", "4"],
-                  ["--graph"]):
+                  ["--no-graph"]):
         p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--batch", "16", "--steps", "2", "--warmup",
                             "3", "--no-cpu-baseline", "--legs", "value,e2e", *extra], capture_output=True, text=True,
                            timeout=600, cwd=ROOT)
         assert p.returncode == 0, (extra, p.stderr[-2000:])
         d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][0])
         assert d["value"] > 0 and d["e2e"]["value"] > 0, extra
-        assert d["cuda_graph"] == ("--graph" in extra)
+        assert d["cuda_graph"] == ("--no-graph" not in extra)
 
 
 def test_reference_arm_line():

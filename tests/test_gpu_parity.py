@@ -119,6 +119,8 @@ GEOMS = [  # N, C, H, O, k, s, p
     (3, 64, 16, 64, 3, 1, 1), (1, 64, 32, 64, 3, 1, 1), (5, 64, 8, 64, 3, 1, 1),
     # ImageNet layer1: 56x56 maps, pixels-on-N tiles of 4 image rows (N = 224)
     (2, 64, 56, 64, 3, 1, 1),
+    # AlexNet channel counts at a batch with >= one 192-wide tile per SM (fprop 64 -> 192, dgrad 384 -> 192)
+    (80, 64, 16, 192, 3, 1, 1), (160, 192, 8, 384, 3, 1, 1),
 ]
 
 

@@ -54,6 +54,7 @@ GEOMS = [  # N, C, H, O, k, s, p
     (2, 64, 8, 128, 3, 2, 1),      # strided: phase-decomposed data gradient
     (16, 512, 4, 512, 3, 1, 1),    # ResNet layer4 geometry: 256-wide tiles
     (2, 64, 8, 64, 1, 1, 0),       # 1x1
+    (80, 64, 16, 192, 3, 1, 1),    # enough tiles for the 192-wide conv tile (features.2 at training batch sizes)
 ]
 
 

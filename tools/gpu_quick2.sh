@@ -19,6 +19,6 @@ for k, v in (d.get("configs") or {}).items():
     print(k, v.get("value"), v.get("ms_per_step"), v.get("conv_roofline_frac_whole_step"), v.get("error"))
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
-   --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 1 --legs value --no-cpu-baseline \
+   --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 1 --legs value --no-cpu-baseline --no-graph \
    > $OUT/${TAG}_launches_bench.log 2>&1
 python tools/launch_summary.py $OUT/${TAG}_launches_bench.csv 3 | head -24

@@ -30,7 +30,7 @@ PY
 fi
 if [ -z "$SKIP_LAUNCHES" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
-   --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 1 --legs value --no-cpu-baseline \
+   --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 2 --warmup 1 --legs value --no-cpu-baseline --no-graph \
    > $OUT/${TAG}_launches_bench.log 2>&1
 echo "launch list exit $?"
 python tools/launch_summary.py $OUT/${TAG}_launches_bench.csv 3 | head -40

@@ -11,7 +11,7 @@ echo "bench tf32 exit $?"; tail -c 400 $OUT/${TAG}_bench_alexnet_tf32.err; head 
 timeout 600 python bench.py --config v1_alexnet_bf16 --legs value --no-cpu-baseline > $OUT/${TAG}_bench_alexnet_bf16.json 2> $OUT/${TAG}_bench_alexnet_bf16.err
 echo "bench bf16 exit $?"; head -c 400 $OUT/${TAG}_bench_alexnet_bf16.json; echo
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv \
-   --log-file $OUT/${TAG}_launches_alexnet_tf32.csv python bench.py --config v1_alexnet --steps 2 --warmup 1 --legs value --no-cpu-baseline \
+   --log-file $OUT/${TAG}_launches_alexnet_tf32.csv python bench.py --config v1_alexnet --steps 2 --warmup 1 --legs value --no-cpu-baseline --no-graph \
    > $OUT/${TAG}_launches_alexnet_tf32.log 2>&1
 echo "launch list exit $?"
 python tools/launch_summary.py $OUT/${TAG}_launches_alexnet_tf32.csv 3 | head -30

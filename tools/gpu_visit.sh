@@ -18,7 +18,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:'pxn
    > $OUT/${TAG}_ncu_pxn_layer1.log 2>&1
 echo "ncu pxn exit $?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
-   --log-file $OUT/${TAG}_launches_imagenet.csv python bench.py --config v1_imagenet --steps 2 --warmup 1 --legs value --no-cpu-baseline \
+   --log-file $OUT/${TAG}_launches_imagenet.csv python bench.py --config v1_imagenet --steps 2 --warmup 1 --legs value --no-cpu-baseline --no-graph \
    > $OUT/${TAG}_launches_imagenet.log 2>&1
 python tools/launch_summary.py $OUT/${TAG}_launches_imagenet.csv 3 | head -24
 ls -la $OUT/${TAG}_* | head -30
