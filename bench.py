@@ -545,7 +545,7 @@ def main():
 
     # ---------------- optional: public/private passes share the passport-free trunk (reported separately)
     shared = None
-    if "shared" in legs and private and cfg["net"] == "resnet18" and not use_graph:
+    if "shared" in legs and private and cfg["net"] == "resnet18":
         model.share_trunk = True
         ms_sh = timed(runner.step, dev_batches, max(5, args.steps // 2), 3)
         n_sh = max(5, args.steps // 2)
