@@ -10,18 +10,18 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpassport_sm100.so")
 
-PP_ABI_VERSION = 14
+PP_ABI_VERSION = 15
 PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL, PP_NORM_GN = 0, 1, 2, 3
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1
 PP_DTYPE_BF16, PP_DTYPE_TF32 = 0, 1
-PP_FLAG_ACC_DW, PP_FLAG_ACC_DGAMMA, PP_FLAG_ACC_DBETA = 1, 2, 4
+PP_FLAG_ACC_DW, PP_FLAG_ACC_DGAMMA, PP_FLAG_ACC_DBETA, PP_FLAG_SHARE_SM = 1, 2, 4, 8
 
 #: every symbol include/passport_sm100.h declares (tests check the .so exports all of them)
 EXPORTS = (
     "pp_version", "pp_last_error", "pp_device_info", "pp_workspace_bytes", "pp_weight_prep", "pp_key_pool",
     "pp_passport_affine_fwd", "pp_passport_affine_bwd", "pp_sign_loss_fwd", "pp_sign_loss_bwd",
-    "pp_conv_block_fwd", "pp_conv_block_fwd_res", "pp_conv_block_bwd", "pp_maxpool_fwd", "pp_maxpool_bwd", "pp_conv_fwd_raw", "pp_conv_dgrad", "pp_conv_wgrad",
+    "pp_conv_block_fwd", "pp_conv_block_fwd_res", "pp_conv_block_bwd", "pp_conv_block_bwd_dz", "pp_maxpool_fwd", "pp_maxpool_bwd", "pp_conv_fwd_raw", "pp_conv_dgrad", "pp_conv_wgrad",
     "pp_sgd_step", "pp_debug_last_timeout", "pp_launch_count", "pp_profile_enable", "pp_profile_read",
     "pp_add_relu_fwd", "pp_add_relu_bwd", "pp_passport_key_grad", "pp_signature_verify",
     "pp_sgd_step_dev", "pp_ce_top1", "pp_passport_conv_fwd", "pp_passport_conv_bwd",
@@ -68,6 +68,7 @@ _PROTOS = {
     "pp_signature_verify": (C.c_int, [_i, C.POINTER(PPSigLayer), _vp, _fp, _vp]),
     "pp_sign_loss_fwd": (C.c_int, [_i, _fp, _fp, _f, _fp, _fp, _vp]),
     "pp_sign_loss_bwd": (C.c_int, [_i, _fp, _fp, _f, _fp, _fp, _vp]),
+    "pp_conv_block_bwd_dz": (C.c_int, [_desc, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _vp, _vp, _sz, _vp]),
     "pp_maxpool_fwd": (C.c_int, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "pp_maxpool_bwd": (C.c_int, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "pp_conv_block_fwd": (C.c_int, [_desc, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp, _sz, _vp]),

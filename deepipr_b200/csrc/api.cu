@@ -597,10 +597,14 @@ int pp_conv_block_fwd_res(const PPConvDesc* d, const void* x, const void* w_fpro
   return rc;
 }
 
-int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad, const void* z,
-                      const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
-                      void* dx, float* dw_oihw, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
-                      void* stream) {
+}  // extern "C"
+
+// dz_ext != NULL: dz goes to that caller-owned buffer instead of the workspace and the weight gradient is NOT computed
+// (the caller runs pp_conv_wgrad on it, possibly on another stream: pp_conv_block_bwd_dz).
+static int conv_block_bwd_impl(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad, const void* z,
+                               const float* gamma, const float* beta, const float* save_mean,
+                               const float* save_invstd, void* dx, float* dw_oihw, float* dgamma, float* dbeta,
+                               void* dz_ext, void* workspace, size_t ws_bytes, void* stream) {
   Geo geo;
   PP_TRY(geo_of(d, &geo));
   PP_TRY(check_device());
@@ -616,6 +620,8 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
   BwdWs ws = carve_bwd(*d, geo, workspace, splits);
   PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "bwd workspace too small: need %zu, got %zu", ws.total,
              ws_bytes);
+  PP_REQUIRE(!dz_ext || d->norm != PP_NORM_GN, PP_EUNSUPPORTED, "the split backward is not built for group / instance norm");
+  if (dz_ext) ws.dz = dz_ext;
   if (d->norm == PP_NORM_GN) {
     const int HW = geo.P * geo.Q;
     PP_TRY(launch_gn_bwd_reduce(*d, HW, (const __nv_bfloat16*)dy, z, gamma, beta, save_mean, save_invstd, ws.ca, ws.cb,
@@ -631,22 +637,41 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
   int num_partials = 0;
   const double zb = d->z_f32 ? 4.0 : 2.0;
   prof_begin(PROF_REDUCE, (double)geo.rows * d->O * (zb + ab), d->C, d->O, geo.T, s);   // read dy + z
+  const int share = (d->flags & PP_FLAG_SHARE_SM) ? 1 : 0;
   const int rc_red = launch_bwd_reduce(dy, af32, z, d->z_f32, geo.rows, d->O, gamma, beta, save_mean, save_invstd,
-                                       d->relu, ws.partial, &num_partials, s);
+                                       d->relu, ws.partial, &num_partials, s, share);
   prof_end(PROF_REDUCE, s);
   PP_TRY(rc_red);
   PP_TRY(launch_bwd_coef(*d, geo.rows, ws.partial, num_partials, gamma, beta, save_mean, save_invstd, dgamma, dbeta,
                          ws.k1, ws.k2, ws.k3, ws.ca, ws.cb, s));
-  if (!dx && !dw_oihw) return PP_OK;
+  if (!dx && !dw_oihw && !dz_ext) return PP_OK;
   prof_begin(PROF_DZ, (double)geo.rows * d->O * (zb + 2.0 * ab), d->C, d->O, geo.T, s);   // read dy + z, write dz
   const int rc_dz = launch_bwd_dz(dy, af32, z, d->z_f32, geo.rows, d->O, ws.ca, ws.cb, d->relu, ws.k1, ws.k2, ws.k3,
-                                  ws.dz, s);
+                                  ws.dz, s, share);
   prof_end(PROF_DZ, s);
   PP_TRY(rc_dz);
   if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));
-  if (dw_oihw)
+  if (dw_oihw && !dz_ext)
     PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s, d->flags & PP_FLAG_ACC_DW));
   return PP_OK;
+}
+
+extern "C" {
+
+int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad, const void* z,
+                      const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                      void* dx, float* dw_oihw, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
+                      void* stream) {
+  return conv_block_bwd_impl(d, dy, x, w_dgrad, z, gamma, beta, save_mean, save_invstd, dx, dw_oihw, dgamma, dbeta,
+                             nullptr, workspace, ws_bytes, stream);
+}
+
+int pp_conv_block_bwd_dz(const PPConvDesc* d, const void* dy, const void* w_dgrad, const void* z, const float* gamma,
+                         const float* beta, const float* save_mean, const float* save_invstd, void* dx,
+                         float* dgamma, float* dbeta, void* dz_out, void* workspace, size_t ws_bytes, void* stream) {
+  PP_REQUIRE(dz_out != nullptr, PP_EBADARG, "conv block bwd (split): dz_out is NULL");
+  return conv_block_bwd_impl(d, dy, nullptr, w_dgrad, z, gamma, beta, save_mean, save_invstd, dx, nullptr, dgamma,
+                             dbeta, dz_out, workspace, ws_bytes, stream);
 }
 
 int pp_passport_conv_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, const float* w_oihw,
@@ -739,7 +764,8 @@ int pp_conv_wgrad(const PPConvDesc* d, const void* dz, const void* x, float* dw_
   BwdWs ws = carve_bwd(*d, geo, workspace, splits);
   PP_REQUIRE(workspace && ws_bytes >= ws.total, PP_EWORKSPACE, "wgrad workspace too small: need %zu, got %zu",
              ws.total, ws_bytes);
-  return run_wgrad(*d, geo, dz, x, dw_oihw, ws.wpartial, ws.col, splits, tc, (cudaStream_t)stream);
+  return run_wgrad(*d, geo, dz, x, dw_oihw, ws.wpartial, ws.col, splits, tc, (cudaStream_t)stream,
+                   d->flags & PP_FLAG_ACC_DW);
 }
 
 int pp_sgd_step(size_t n, float* param, const float* grad, float* momentum_buf, float lr, float momentum,

@@ -175,7 +175,7 @@ int launch_col_stats(const void* z, int z_f32, size_t rows, int O, float* partia
                      cudaStream_t s);
 int launch_bwd_reduce(const void* dy, int dy_f32, const void* z, int z_f32, size_t rows, int O, const float* gamma,
                       const float* beta, const float* mean, const float* invstd, int relu, float* partial,
-                      int* num_partials, cudaStream_t s);   // the mask coefficients are derived in the kernel
+                      int* num_partials, cudaStream_t s, int share_sm = 0);   // mask coefficients derived in the kernel
 int bwd_reduce_max_partials();
 int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int num_partials, const float* gamma,
                     const float* beta, const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
@@ -183,7 +183,7 @@ int launch_bwd_coef(const PPConvDesc& d, size_t rows, const float* partial, int 
                     cudaStream_t s);
 int launch_bwd_dz(const void* dy, int act_f32 /*dy and dz*/, const void* z, int z_f32, size_t rows, int O, const float* a,
                   const float* b, int relu, const float* k1, const float* k2, const float* k3, void* dz,
-                  cudaStream_t s);
+                  cudaStream_t s, int share_sm = 0);
 int launch_wgrad_finalize(const PPConvDesc& d, const float* partial, int splits, int kstride, float* dw_oihw,
                           cudaStream_t s, int accumulate = 0);
 int launch_im2col_small(const PPConvDesc& d, const void* x, void* col, size_t rows, int P, int Q, int Kpad,

@@ -20,7 +20,8 @@ static inline int grid_for(size_t work_items, int threads, int max_blocks) {
 // that grid*threads is a whole number of `vec_per_row`-vector rows whenever possible (the kernels then keep their
 // per-channel coefficients in registers).
 template <typename Kern>
-static int streaming_grid(Kern kernel, int* cached_occ, size_t work_items, int threads, int vec_per_row) {
+static int streaming_grid(Kern kernel, int* cached_occ, size_t work_items, int threads, int vec_per_row,
+                          int max_per_sm = 0 /*0: every resident slot; else at most this many CTAs per SM*/) {
   if (*cached_occ <= 0) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) {
@@ -31,7 +32,8 @@ static int streaming_grid(Kern kernel, int* cached_occ, size_t work_items, int t
   }
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  int grid = grid_for(work_items, threads, sms * *cached_occ);
+  const int per_sm = (max_per_sm > 0 && max_per_sm < *cached_occ) ? max_per_sm : *cached_occ;
+  int grid = grid_for(work_items, threads, sms * per_sm);
   int a = vec_per_row, b = threads;   // q = vec_per_row / gcd(vec_per_row, threads)
   while (b) { const int t = a % b; a = b; b = t; }
   const int q = vec_per_row / (a > 0 ? a : 1);
@@ -602,7 +604,7 @@ __global__ void column_reduce_kernel(const void* __restrict__ dy, const void* __
                                      size_t rows, int O, const float* __restrict__ a, const float* __restrict__ b,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      int relu, float* __restrict__ partial) {
-  extern __shared__ float s_part[];  // [row_lanes][2][O]
+  extern __shared__ float s_part[];  // [row_lanes][O]
   const int vec_per_row = O >> 3;
   const int row_lanes = kRedThreads / vec_per_row > 0 ? kRedThreads / vec_per_row : 1;
   const int col = threadIdx.x % vec_per_row;
@@ -688,27 +690,33 @@ __global__ void column_reduce_kernel(const void* __restrict__ dy, const void* __
         }
       }
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s_part[(rl * 2 + 0) * O + col * 8 + k] = s1[k];
-      s_part[(rl * 2 + 1) * O + col * 8 + k] = s2[k];
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * O; i += blockDim.x) {
-    float acc = 0.0f;
-    for (int l = 0; l < row_lanes; ++l) acc += s_part[l * 2 * O + i];
-    partial[(size_t)blockIdx.x * 2 * O + i] = acc;
+  // the row lanes are combined in two rounds (first sums, then second sums) through ONE [row_lanes][O] buffer: 8 KiB
+  // instead of 16, so that three of these blocks still fit beside a weight-gradient CTA that holds ~198 KiB of the SM's
+  // shared memory (functional._SideStream runs them concurrently)
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    if (rl < row_lanes) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_part[rl * O + col * 8 + k] = half == 0 ? s1[k] : s2[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < O; i += blockDim.x) {
+      float acc = 0.0f;
+      for (int l = 0; l < row_lanes; ++l) acc += s_part[l * O + i];
+      partial[(size_t)blockIdx.x * 2 * O + half * O + i] = acc;
+    }
+    __syncthreads();
   }
 }
 
 template <int MODE, bool AF32>
 static int column_reduce_launch_t(const void* dy, const void* z, int z_f32, size_t rows, int O, const float* a,
                                   const float* b, const float* mean, const float* invstd, int relu, float* partial,
-                                  int* num_partials, cudaStream_t s) {
+                                  int* num_partials, cudaStream_t s, int share_sm = 0) {
   const int vec_per_row = O / 8;
   const int row_lanes = kRedThreads / vec_per_row;
-  const size_t smem = (size_t)row_lanes * 2 * O * sizeof(float);
+  const size_t smem = (size_t)row_lanes * O * sizeof(float);
   // one wave: every block gets the same share of rows, so a partial second wave would cost a full one
   static int occ = 0;
   if (occ <= 0) {
@@ -719,7 +727,7 @@ static int column_reduce_launch_t(const void* dy, const void* z, int z_f32, size
   }
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
-  size_t max_blocks = (size_t)sms * occ;
+  size_t max_blocks = (size_t)sms * ((share_sm && occ > 2) ? 2 : occ);
   if (max_blocks > (size_t)kRedMaxBlocks) max_blocks = kRedMaxBlocks;
   size_t blocks = (rows + row_lanes - 1) / row_lanes;
   if (blocks > max_blocks) blocks = max_blocks;
@@ -741,14 +749,14 @@ int launch_col_stats(const void* z, int z_f32, size_t rows, int O, float* partia
 
 int launch_bwd_reduce(const void* dy, int dy_f32, const void* z, int z_f32, size_t rows, int O, const float* gamma,
                       const float* beta, const float* mean, const float* invstd, int relu, float* partial,
-                      int* num_partials, cudaStream_t s) {
+                      int* num_partials, cudaStream_t s, int share_sm) {
   PP_REQUIRE(O % 8 == 0 && O / 8 <= kRedThreads, PP_EBADSHAPE, "column reduce needs O%%8==0 and O<=2048 (O=%d)", O);
   PP_REQUIRE(mean && invstd, PP_EBADARG, "backward reduce needs the saved statistics");
   if (dy_f32)
     return column_reduce_launch_t<1, true>(dy, z, z_f32, rows, O, gamma, beta, mean, invstd, relu, partial,
-                                           num_partials, s);
+                                           num_partials, s, share_sm);
   return column_reduce_launch_t<1, false>(dy, z, z_f32, rows, O, gamma, beta, mean, invstd, relu, partial,
-                                          num_partials, s);
+                                          num_partials, s, share_sm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -872,15 +880,15 @@ __global__ void bwd_dz_kernel(const void* __restrict__ dy, const void* __restric
 
 int launch_bwd_dz(const void* dy, int act_f32, const void* z, int z_f32, size_t rows, int O, const float* a,
                   const float* b, int relu, const float* k1, const float* k2, const float* k3, void* dz,
-                  cudaStream_t s) {
+                  cudaStream_t s, int share_sm) {
   PP_REQUIRE(O % 8 == 0, PP_EBADSHAPE, "dz pass needs O%%8==0 (O=%d)", O);
   const size_t nvec = rows * (size_t)(O / 8);
   static int occ[2] = {0, 0};
   if (act_f32)
-    bwd_dz_kernel<true><<<streaming_grid(bwd_dz_kernel<true>, &occ[1], nvec, 256, O / 8), 256, 0, s>>>(
+    bwd_dz_kernel<true><<<streaming_grid(bwd_dz_kernel<true>, &occ[1], nvec, 256, O / 8, share_sm ? 2 : 0), 256, 0, s>>>(
         dy, z, z_f32, nvec, O, a, b, relu, k1, k2, k3, dz);
   else
-    bwd_dz_kernel<false><<<streaming_grid(bwd_dz_kernel<false>, &occ[0], nvec, 256, O / 8), 256, 0, s>>>(
+    bwd_dz_kernel<false><<<streaming_grid(bwd_dz_kernel<false>, &occ[0], nvec, 256, O / 8, share_sm ? 2 : 0), 256, 0, s>>>(
         dy, z, z_f32, nvec, O, a, b, relu, k1, k2, k3, dz);
   PP_POST_LAUNCH();
   return PP_OK;

@@ -80,8 +80,9 @@ def make_desc(spec: ConvSpec, N, H, W, norm=L.PP_NORM_NONE, relu=0, z_f32=0, eps
     return d, key
 
 
-def workspace(desc, key, which, device):
-    """Grow-only per-device scratch buffer (fwd and bwd share it: they are stream-ordered)."""
+def workspace(desc, key, which, device, slot=0):
+    """Grow-only per-device scratch buffer (fwd and bwd share it: they are stream-ordered).  slot 1 is the scratch of
+    the weight-gradient launches that run on the side stream (see _SideStream)."""
     ck = (key, which)
     nbytes = _ws_bytes_cache.get(ck)
     if nbytes is None:
@@ -89,11 +90,57 @@ def workspace(desc, key, which, device):
         L.check(L.load().pp_workspace_bytes(C.byref(desc), which, C.byref(out)), "pp_workspace_bytes")
         nbytes = int(out.value)
         _ws_bytes_cache[ck] = nbytes
-    buf = _workspace.get(device)
+    wk = device if slot == 0 else (device, slot)
+    buf = _workspace.get(wk)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None and slot != 0:
+            join_side(device)             # the old side buffer may still be in use by a launch in flight
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspace[device] = buf
+        _workspace[wk] = buf
     return buf, nbytes
+
+
+# ---------------------------------------------------------------- weight gradients on a second stream
+#: The weight gradient of a block is a tensor-core kernel that nothing later in the backward pass depends on, while the
+#: next block's backward starts with two HBM-bound passes (reduce, dz).  Where the gradient is accumulated by the
+#: kernels themselves into a flat gradient buffer (FlatParams, direct accumulation: autograd never sees it), it is
+#: launched on a side stream so that the two overlap (measured: 50-70 % of the shorter kernel is hidden).  Everything
+#: that reads the gradients joins first: the end of the backward pass (autograd engine callback), a bucket all-reduce,
+#: the optimizer step.  PP_NO_WGRAD_OVERLAP=1 (or functional.OVERLAP_WGRAD = False) keeps everything on one stream.
+import os as _os
+OVERLAP_WGRAD = _os.environ.get("PP_NO_WGRAD_OVERLAP", "0") != "1"
+
+
+class _SideStream:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.pending = False        # launches since the last join
+        self.keep = []              # tensors the side launches read / write, kept alive until the join
+        self.cb_queued = False
+
+
+_side = {}
+
+
+def _side_for(device):
+    st = _side.get(device)
+    if st is None:
+        st = _side[device] = _SideStream(device)
+    return st
+
+
+def join_side(device=None):
+    """Make the current stream wait for the weight-gradient launches in flight on the side stream of `device` (all
+    devices if None) and release the tensors they used."""
+    for dev, st in list(_side.items()):
+        if device is not None and dev != device:
+            continue
+        st.cb_queued = False
+        if st.pending:
+            with torch.cuda.device(dev):
+                torch.cuda.current_stream(dev).wait_stream(st.stream)
+            st.pending = False
+        st.keep.clear()
 
 
 def to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -477,10 +524,31 @@ class _ConvBlockFn(torch.autograd.Function):
         if need_dx and ctx.prepared.wd is None:
             raise RuntimeError("deepipr_b200: dgrad weights were not prepared")
         ws, nbytes = workspace(d, key, L.PP_WS_BWD, dev)
-        L.check(L.load().pp_conv_block_bwd(
-            C.byref(d), L.ptr(gyc), L.ptr(xc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(g), L.ptr(b), L.ptr(save_mean),
-            L.ptr(save_invstd), L.ptr(dx), L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), C.c_size_t(nbytes),
-            _stream()), "pp_conv_block_bwd")
+        if OVERLAP_WGRAD and sw and need_dw and o.norm != L.PP_NORM_GN:
+            # dgamma / dbeta / dz / dx here; the weight gradient on the side stream, straight into the flat buffer
+            if _side_for(dev).pending:      # a weight gradient is in flight: share the SMs with it (PP_FLAG_SHARE_SM)
+                d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups,
+                                   flags | L.PP_FLAG_SHARE_SM, o.dtype)
+            dzbuf = torch.empty((N,) + spec.out_hw(H, W) + (spec.O,), dtype=adt, device=dev)
+            L.check(L.load().pp_conv_block_bwd_dz(
+                C.byref(d), L.ptr(gyc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(g), L.ptr(b), L.ptr(save_mean),
+                L.ptr(save_invstd), L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dzbuf), L.ptr(ws),
+                C.c_size_t(nbytes), _stream()), "pp_conv_block_bwd_dz")
+            side = _side_for(dev)
+            ws2, nbytes2 = workspace(d, key, L.PP_WS_BWD, dev, slot=1)
+            side.stream.wait_stream(torch.cuda.current_stream(dev))
+            L.check(L.load().pp_conv_wgrad(C.byref(d), L.ptr(dzbuf), L.ptr(xc), L.ptr(dw), L.ptr(ws2),
+                                           C.c_size_t(nbytes2), C.c_void_p(side.stream.cuda_stream)), "pp_conv_wgrad")
+            side.pending = True
+            side.keep.append((dzbuf, xc, dw))
+            if not side.cb_queued:           # whoever reads gradients after this backward pass finds them complete
+                side.cb_queued = True
+                torch.autograd.Variable._execution_engine.queue_callback(lambda: join_side(dev))
+        else:
+            L.check(L.load().pp_conv_block_bwd(
+                C.byref(d), L.ptr(gyc), L.ptr(xc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(g), L.ptr(b),
+                L.ptr(save_mean), L.ptr(save_invstd), L.ptr(dx), L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws),
+                C.c_size_t(nbytes), _stream()), "pp_conv_block_bwd")
         if dx is not None and ctx.x_dtype != adt:
             dx = dx.to(ctx.x_dtype)
         gg = dgamma.reshape(ctx.gshape).to(ctx.gdtype) if (ctx.gshape is not None and ctx.needs_input_grad[2]) else None

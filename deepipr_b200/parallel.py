@@ -97,6 +97,8 @@ class FlatParams:
                 p.grad = view
 
     def zero_grad(self):
+        if self.flat_grad.is_cuda:
+            F_.join_side(self.flat_grad.device)
         self.flat_grad.zero_()
         self.ensure_grad_views()
         # forwards whose backward never ran (evaluation with grad enabled, an aborted step) must not leak into the
@@ -206,6 +208,7 @@ class GradBuckets:
     def _launch(self, b):
         start, end, _ = self.buckets[b]
         chunk = self.flat.flat_grad[start:end]
+        F_.join_side(chunk.device if chunk.is_cuda else None)   # weight gradients still in flight on the side stream
         if self.world > 1:
             if self._avg_op is not None:     # NCCL: the mean is taken inside the collective (no pre-scaling launch)
                 self._works.append(dist.all_reduce(chunk, op=self._avg_op, group=self.group, async_op=True))
@@ -320,6 +323,7 @@ class FlatSGD(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         F_.require_cuda(self.flat.flat, "FlatSGD parameters")
+        F_.join_side(self.flat.flat.device)
         self.flat.ensure_grad_views()
         if len(self.param_groups) != 1:
             raise ValueError("FlatSGD supports exactly one param group")

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 14
+#define PP_ABI_VERSION 15
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -51,7 +51,12 @@ enum { PP_ALGO_AUTO = 0, PP_ALGO_TCGEN05 = 1, PP_ALGO_SIMT = 2 };
  * (what autograd's AccumulateGrad does with `param.grad += g`, one launch per parameter and pass; here it is the
  * last store of the producing kernel, so the gradients of a two-pass V2 step land in a flat gradient buffer with
  * no extra launches). */
-enum { PP_FLAG_ACC_DW = 1, PP_FLAG_ACC_DGAMMA = 2, PP_FLAG_ACC_DBETA = 4 };
+enum { PP_FLAG_ACC_DW = 1, PP_FLAG_ACC_DGAMMA = 2, PP_FLAG_ACC_DBETA = 4,
+       /* the HBM-bound passes of this backward call will share the SMs with a tensor-core kernel running on another
+        * stream (the previous block's weight gradient): size their grids to two resident CTAs per SM, which still
+        * saturates HBM and leaves registers / shared memory for that kernel's CTA, instead of every slot of an idle
+        * chip (a statically partitioned grid that is only partly resident runs in two waves) */
+       PP_FLAG_SHARE_SM = 8 };
 enum { PP_WS_FWD = 0, PP_WS_BWD = 1 };
 /* PPConvDesc.dtype — the arithmetic type of the contractions and the element type of every activation-shaped tensor
  * that crosses this boundary (x, y, dy, dx; the weight operand copies of pp_weight_prep):
@@ -236,7 +241,18 @@ int pp_passport_conv_bwd(const PPConvDesc* d, const void* dy, const void* x, con
                          const float* g_sign_loss, void* dx, float* dw_oihw, float* dgamma, float* dbeta,
                          void* workspace, size_t ws_bytes, void* stream);
 
-/* Building blocks exposed for tests / profiling (same kernels the two calls above use). */
+/* The block backward WITHOUT its weight gradient: dgamma, dbeta, dx as pp_conv_block_bwd, and dz (the gradient w.r.t.
+ * the conv output, [N*P*Q, O] in the activation type) written to the caller's buffer dz_out instead of the workspace.
+ * The weight gradient is then pp_conv_wgrad(d, dz_out, x, dw, ...) — a tensor-core kernel nothing downstream in the
+ * backward pass depends on, which the caller may launch on a second stream so that it overlaps the HBM-bound passes
+ * of the next block's backward (deepipr_b200.functional does, into a flat gradient buffer with PP_FLAG_ACC_DW).
+ * Batch-norm / plain blocks only (PP_NORM_GN: PP_EUNSUPPORTED). */
+int pp_conv_block_bwd_dz(const PPConvDesc* d, const void* dy, const void* w_dgrad, const void* z, const float* gamma,
+                         const float* beta, const float* save_mean, const float* save_invstd, void* dx,
+                         float* dgamma, float* dbeta, void* dz_out, void* workspace, size_t ws_bytes, void* stream);
+
+/* Building blocks exposed for tests / profiling (same kernels the two calls above use).  pp_conv_wgrad honours
+ * PP_FLAG_ACC_DW in d->flags (adds into dw_oihw). */
 int pp_conv_fwd_raw(const PPConvDesc* d, const void* x, const void* w_fprop, void* z, void* workspace,
                     size_t ws_bytes, void* stream); /* z = conv(x,W), dtype per z_f32 */
 int pp_conv_dgrad(const PPConvDesc* d, const void* dz, const void* w_dgrad, void* dx, void* stream);
