@@ -477,12 +477,17 @@ def main():
     # ---------------- leg 3 (`roofline`): per-kernel CUDA-event timing on the kernels' own stream
     roof = roof_w = roof_hbm = roof_fused = None
     if "roofline" in legs:                   # (eager steps: the per-kernel event instrumentation wraps real launches)
+        # one stream for these steps: a kernel that shares the SMs with another stream's kernel (the side-stream weight
+        # gradients) would be charged the other one's time by the per-launch events
+        from deepipr_b200 import functional as _F
+        overlap_was, _F.OVERLAP_WGRAD = _F.OVERLAP_WGRAD, False
         if rank == 0:
             lib.pp_profile_enable(1)
         for i in range(3):
             runner.step(*dev_batches[i % 4])
         barrier()
         lib.pp_profile_enable(0)
+        _F.OVERLAP_WGRAD = overlap_was
     if rank == 0 and "roofline" in legs:
         def read(kind, c=0, nout=0, taps=0):
             ms, fl, n = C.c_double(0), C.c_double(0), C.c_int(0)

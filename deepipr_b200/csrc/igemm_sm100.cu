@@ -988,7 +988,11 @@ static int launch_pxn(const TapGemm& g, PxnPlan& pl, const void* act, const void
   {
     static int dbg = -1, m64 = -1;
     if (dbg < 0) { const char* ev = getenv("PP_DEBUG"); dbg = ev ? atoi(ev) : 0; }
-    if (m64 < 0) { const char* ev = getenv("PP_M64"); m64 = ev ? atoi(ev) : 0; }
+    // 64 output channels: M = 64 instructions (accumulator row r in TMEM lane 32*(r/16) + r%16) instead of M = 128 with
+    // the upper 64 rows multiplying don't-care data.  Per launch the two cost the same time, but the chip runs this
+    // workload at its power cap and the narrower instruction draws less: +0.9 % on the whole step (1905 -> 1953 MHz).
+    // PP_M64=0 restores M = 128.
+    if (m64 < 0) { const char* ev = getenv("PP_M64"); m64 = ev ? atoi(ev) : 2; }
     d.dbg = dbg;
     d.m64 = (g.Nout == 64) ? m64 : 0;
   }

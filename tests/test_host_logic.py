@@ -187,3 +187,59 @@ def test_config_helpers():
     leaf = kw['layer4']['1']['convbn_2']
     assert leaf['flag'] is True and leaf['b'] == "this is my signature" and leaf['key_type'] == 'shuffle'
     assert nets.alexnet_passport_config() == {'0': False, '2': False, '4': True, '5': True, '6': True}
+
+
+def test_precision_switch_selects_the_arithmetic_per_call(monkeypatch):
+    """layers.set_precision / a block's own `precision`: TF32 applies to fp32 inputs outside autocast on batch-norm /
+    plain blocks only; everything else keeps the bf16 path (DESIGN.md 'TF32')."""
+    import pytest
+    from deepipr_b200 import _lib as L
+    from deepipr_b200 import layers
+    blk = layers.ConvBlock(32, 64, 3, 1, 1, bn='bn')
+    x32, x16 = torch.zeros(1, 32, 4, 4), torch.zeros(1, 32, 4, 4, dtype=torch.bfloat16)
+    prev = layers.set_precision('bf16')
+    try:
+        assert blk._dtype(x32, L.PP_NORM_BN_TRAIN) == L.PP_DTYPE_BF16
+        assert layers.set_precision('tf32') == 'bf16' and layers.get_precision() == 'tf32'
+        assert blk._dtype(x32, L.PP_NORM_BN_TRAIN) == L.PP_DTYPE_TF32
+        assert blk._dtype(x16, L.PP_NORM_BN_TRAIN) == L.PP_DTYPE_BF16            # bf16 input
+        assert blk._dtype(x32, L.PP_NORM_GN) == L.PP_DTYPE_BF16                  # group / instance norm: bf16 kernels
+        with monkeypatch.context() as mp:                                        # inside torch.autocast('cuda', bf16)
+            mp.setattr(torch, "is_autocast_enabled", lambda *a: True)
+            assert blk._dtype(x32, L.PP_NORM_BN_TRAIN) == L.PP_DTYPE_BF16
+        blk.precision = 'bf16'                                                   # per-block override
+        assert blk._dtype(x32, L.PP_NORM_BN_TRAIN) == L.PP_DTYPE_BF16
+        with pytest.raises(ValueError):
+            layers.set_precision('fp8')
+    finally:
+        layers.set_precision(prev)
+
+
+def test_residual_join_is_folded_only_where_both_summands_are_nonnegative():
+    """nets.BasicUnit: relu(out + shortcut) is a plain sum (folded into convbn_2 / identity backward) iff convbn_2 ends
+    in a ReLU and the shortcut is a ReLU block's output or a post-ReLU unit input (set by ResNet18 for its units)."""
+    from deepipr_b200 import nets
+    ident = nets.BasicUnit('normal', 64, 64, 1, None, 'bn')
+    proj = nets.BasicUnit('normal', 64, 128, 2, None, 'bn')
+    assert not ident._join_is_plain_sum()          # stand-alone unit: nothing known about the sign of its input
+    ident.input_nonneg = True
+    assert ident._join_is_plain_sum()
+    assert proj._join_is_plain_sum()               # projection shortcut ends in a ReLU like every reference block
+    proj.fuse_join = False
+    assert not proj._join_is_plain_sum()
+    proj.fuse_join = True
+    proj.shortcut.relu = None
+    assert not proj._join_is_plain_sum()
+    ident.convbn_2.relu = None
+    assert not ident._join_is_plain_sum()
+    net = quiet(nets.ResNet18, 'private', 10, nets.passport_kwargs_from_config(nets.resnet18_passport_config(), 'bn',
+                                                                                'random', 0.1))
+    assert all(u.input_nonneg for u in net._units())
+
+
+def test_max_pool_module_is_the_stock_module_off_the_gpu():
+    from deepipr_b200 import layers
+    pool = layers.MaxPool2d(3, 2, 1)
+    x = torch.randn(2, 8, 9, 9)
+    assert torch.equal(pool(x), torch.nn.functional.max_pool2d(x, 3, 2, 1))
+    assert list(pool.state_dict().keys()) == [] and isinstance(pool, torch.nn.MaxPool2d)

