@@ -10,7 +10,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpassport_sm100.so")
 
-PP_ABI_VERSION = 15
+PP_ABI_VERSION = 16
 PP_NORM_NONE, PP_NORM_BN_TRAIN, PP_NORM_BN_EVAL, PP_NORM_GN = 0, 1, 2, 3
 PP_ALGO_AUTO, PP_ALGO_TCGEN05, PP_ALGO_SIMT = 0, 1, 2
 PP_WS_FWD, PP_WS_BWD = 0, 1
@@ -68,7 +68,7 @@ _PROTOS = {
     "pp_signature_verify": (C.c_int, [_i, C.POINTER(PPSigLayer), _vp, _fp, _vp]),
     "pp_sign_loss_fwd": (C.c_int, [_i, _fp, _fp, _f, _fp, _fp, _vp]),
     "pp_sign_loss_bwd": (C.c_int, [_i, _fp, _fp, _f, _fp, _fp, _vp]),
-    "pp_conv_block_bwd_dz": (C.c_int, [_desc, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _vp, _vp, _sz, _vp]),
+    "pp_conv_block_bwd_dz": (C.c_int, [_desc, _vp, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp, _vp, _sz, _vp]),
     "pp_maxpool_fwd": (C.c_int, [_i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "pp_maxpool_bwd": (C.c_int, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "pp_conv_block_fwd": (C.c_int, [_desc, _vp, _vp, _fp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp, _sz, _vp]),

@@ -333,7 +333,10 @@ static int run_fprop(const PPConvDesc& d, const Geo& geo, const void* x, const v
   return tapgemm_simt(g, x, wf, e2, s);
 }
 
-static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const void* wd, void* dx, cudaStream_t s) {
+// dx_add (optional, bf16 [N,H,W,C]): added to the data gradient — in the kernel's epilogue where the gradient is one
+// identity-mapped tensor-core launch (every stride-1 conv), by a separate pass otherwise.
+static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const void* wd, void* dx, cudaStream_t s,
+                     const void* dx_add = nullptr) {
   TapGemm phases[64];
   int nph = 0;
   bool any_empty = false;
@@ -344,10 +347,14 @@ static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
       if (plan_dgrad_phase(d, geo, ph, pw, phases[nph])) ++nph; else any_empty = true;
     }
   if (any_empty) PP_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)d.N * d.H * d.W * d.C * act_esz(d), s));
+  PP_REQUIRE(!dx_add || !is_tf32(d), PP_EUNSUPPORTED, "dx_add is bf16-only");
+  const bool fuse_add = dx_add && nph == 1 && !any_empty && phases[0].out_identity &&
+                        use_tcgen05(d, tapgemm_tcgen05_supported(phases[0]));
   for (int i = 0; i < nph; ++i) {
     TapEpilogue e;
     e.out = dx; e.out_f32 = is_tf32(d) ? 1 : 0; e.scale = nullptr; e.shift = nullptr; e.relu = 0;
     e.stats_partial = nullptr;
+    e.add_src = fuse_add ? dx_add : nullptr;
     const bool tc = use_tcgen05(d, tapgemm_tcgen05_supported(phases[i]));
     PP_REQUIRE(tc || !is_tf32(d), PP_EUNSUPPORTED, "PP_DTYPE_TF32 data gradient needs O%%32==0 and C%%64==0 (C=%d O=%d)",
                d.C, d.O);
@@ -356,6 +363,8 @@ static int run_dgrad(const PPConvDesc& d, const Geo& geo, const void* dz, const 
     if (tc) PP_TRY(tapgemm_tcgen05(phases[i], dz, wd, e, s));
     else PP_TRY(tapgemm_simt(phases[i], dz, wd, e, s));
   }
+  if (dx_add && !fuse_add)
+    PP_TRY(launch_add_inplace((__nv_bfloat16*)dx, (const __nv_bfloat16*)dx_add, (size_t)d.N * d.H * d.W * d.C, s));
   return PP_OK;
 }
 
@@ -604,7 +613,7 @@ int pp_conv_block_fwd_res(const PPConvDesc* d, const void* x, const void* w_fpro
 static int conv_block_bwd_impl(const PPConvDesc* d, const void* dy, const void* x, const void* w_dgrad, const void* z,
                                const float* gamma, const float* beta, const float* save_mean,
                                const float* save_invstd, void* dx, float* dw_oihw, float* dgamma, float* dbeta,
-                               void* dz_ext, void* workspace, size_t ws_bytes, void* stream) {
+                               void* dz_ext, const void* dx_add, void* workspace, size_t ws_bytes, void* stream) {
   Geo geo;
   PP_TRY(geo_of(d, &geo));
   PP_TRY(check_device());
@@ -650,7 +659,7 @@ static int conv_block_bwd_impl(const PPConvDesc* d, const void* dy, const void* 
                                   ws.dz, s, share);
   prof_end(PROF_DZ, s);
   PP_TRY(rc_dz);
-  if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s));
+  if (dx) PP_TRY(run_dgrad(*d, geo, ws.dz, w_dgrad, dx, s, dx_add));
   if (dw_oihw && !dz_ext)
     PP_TRY(run_wgrad(*d, geo, ws.dz, x, dw_oihw, ws.wpartial, ws.col, splits, wg_tc, s, d->flags & PP_FLAG_ACC_DW));
   return PP_OK;
@@ -663,15 +672,17 @@ int pp_conv_block_bwd(const PPConvDesc* d, const void* dy, const void* x, const 
                       void* dx, float* dw_oihw, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
                       void* stream) {
   return conv_block_bwd_impl(d, dy, x, w_dgrad, z, gamma, beta, save_mean, save_invstd, dx, dw_oihw, dgamma, dbeta,
-                             nullptr, workspace, ws_bytes, stream);
+                             nullptr, nullptr, workspace, ws_bytes, stream);
 }
 
 int pp_conv_block_bwd_dz(const PPConvDesc* d, const void* dy, const void* w_dgrad, const void* z, const float* gamma,
                          const float* beta, const float* save_mean, const float* save_invstd, void* dx,
-                         float* dgamma, float* dbeta, void* dz_out, void* workspace, size_t ws_bytes, void* stream) {
+                         const void* dx_add, float* dgamma, float* dbeta, void* dz_out, void* workspace,
+                         size_t ws_bytes, void* stream) {
   PP_REQUIRE(dz_out != nullptr, PP_EBADARG, "conv block bwd (split): dz_out is NULL");
+  PP_REQUIRE(!dx_add || dx, PP_EBADARG, "conv block bwd (split): dx_add without dx");
   return conv_block_bwd_impl(d, dy, nullptr, w_dgrad, z, gamma, beta, save_mean, save_invstd, dx, nullptr, dgamma,
-                             dbeta, dz_out, workspace, ws_bytes, stream);
+                             dbeta, dz_out, dx_add, workspace, ws_bytes, stream);
 }
 
 int pp_passport_conv_fwd(const PPConvDesc* d, const void* x, const void* w_fprop, const float* w_oihw,

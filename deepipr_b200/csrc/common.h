@@ -91,6 +91,10 @@ struct TapEpilogue {
   const float* shift;    // per-n affine b[n] (NULL => 0)
   int relu;
   float* stats_partial;  // NULL or [tapgemm_tcgen05_grid()][2][Nout]: per-CTA sum z, sum z^2 (fp32 accumulators)
+  // NULL, or a bf16 tensor of the output's shape and pixel mapping that is added to the (bf16-rounded) result before
+  // it is stored: out = bf16(bf16(acc) + add_src) — the gradient sum autograd performs where a tensor forks
+  // (dx = dgrad + gradient of the residual path), folded into the data-gradient kernel.  bf16 outputs only.
+  const void* add_src = nullptr;
 };
 
 void count_launch();
@@ -193,6 +197,7 @@ int launch_maxpool_fwd(int N, int H, int W, int C, int k, int s, int p, const vo
                        cudaStream_t st);
 int launch_maxpool_bwd(int N, int H, int W, int C, int k, int s, int p, const void* dy, const uint8_t* idx, int f32,
                        void* dx, cudaStream_t st);
+int launch_add_inplace(__nv_bfloat16* y, const __nv_bfloat16* a, size_t n, cudaStream_t s);   // y += a
 int launch_add_relu_fwd(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, size_t n, cudaStream_t s);
 int launch_add_relu_bwd(const __nv_bfloat16* g, const __nv_bfloat16* y, __nv_bfloat16* gx, size_t n, cudaStream_t s);
 // --- groupnorm.cu (GroupNorm / InstanceNorm: per-(sample, group) statistics, per-(sample, channel) coefficients) ---

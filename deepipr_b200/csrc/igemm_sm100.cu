@@ -185,6 +185,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// 8 bf16 + 8 bf16 -> 8 bf16 (fp32 add, round to nearest)
+__device__ __forceinline__ uint4 add_bf16x8(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __bfloat1622float2(pa[i]), fb = __bfloat1622float2(pb[i]);
+    pr[i] = __floats2bfloat162_rn(fa.x + fb.x, fa.y + fb.y);
+  }
+  return r;
+}
+
 struct TapGemmDev {
   int M;            // N * P * Q
   int P, Q, PQ;
@@ -206,6 +220,7 @@ struct TapGemmDev {
   const float* shift;
   int relu;
   float* stats_partial;
+  const __nv_bfloat16* add_src;   // see TapEpilogue::add_src
 };
 
 constexpr int kBM = 128;       // output pixels per tile (UMMA M)
@@ -492,12 +507,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           __syncwarp();
           __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + n0 + j * 32 + (lane & 3) * 8;
+          const __nv_bfloat16* abase = p.add_src ? p.add_src + n0 + j * 32 + (lane & 3) * 8 : nullptr;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int r = it * 8 + (lane >> 2);
-            const uint4 val = st[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
+            uint4 val = st[r * 4 + ((lane & 3) ^ ((r >> 1) & 3))];
             const long long orow = __shfl_sync(0xffffffffu, (long long)out_row, r);
-            if ((valid_mask >> r) & 1u) *reinterpret_cast<uint4*>(obase + (size_t)orow * p.Nout) = val;
+            if ((valid_mask >> r) & 1u) {
+              if (abase) val = add_bf16x8(val, __ldg(reinterpret_cast<const uint4*>(abase + (size_t)orow * p.Nout)));
+              *reinterpret_cast<uint4*>(obase + (size_t)orow * p.Nout) = val;
+            }
           }
           __syncwarp();
         }
@@ -592,6 +611,8 @@ static int launch_tapgemm(const TapGemm& g, const void* act, const void* B, cons
   }
   p.out = e.out; p.out_f32 = e.out_f32; p.scale = e.scale; p.shift = e.shift; p.relu = e.relu;
   p.stats_partial = e.stats_partial;
+  p.add_src = (const __nv_bfloat16*)e.add_src;
+  PP_REQUIRE(!e.add_src || !e.out_f32, PP_EUNSUPPORTED, "add_src needs a bf16 output");
 
   PP_SET_MAX_SMEM_ONCE((tapgemm_kernel<BN, RESB, TF32>), Cfg::kSmemBytes);
   PP_REQUIRE(e.stats_partial == nullptr || g.Nout <= kMaxStatsN, PP_EUNSUPPORTED,
@@ -644,6 +665,7 @@ struct PxnDev {
   const float* shift;
   int relu;
   float* stats_partial;
+  const __nv_bfloat16* add_src;   // see TapEpilogue::add_src
   int dbg;
   int m64;   // Nout == 64: issue M=64 MMAs; 1 = accumulator row r in TMEM lane r, 2 = lane 32*(r/16) + r%16
 };
@@ -864,8 +886,17 @@ pxn_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CU
             for (int i = 0; i < 32; ++i) out[base8[i >> 3] + (size_t)(i & 7) * step] = v[i];
           } else {
             __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+            if (p.add_src) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) out[base8[i >> 3] + (size_t)(i & 7) * step] = __float2bfloat16_rn(v[i]);
+              for (int i = 0; i < 32; ++i) {
+                const size_t idx = base8[i >> 3] + (size_t)(i & 7) * step;
+                const float r = __bfloat162float(__float2bfloat16_rn(v[i])) + __bfloat162float(p.add_src[idx]);
+                out[idx] = __float2bfloat16_rn(r);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) out[base8[i >> 3] + (size_t)(i & 7) * step] = __float2bfloat16_rn(v[i]);
+            }
           }
         }
       }
@@ -985,6 +1016,8 @@ static int launch_pxn(const TapGemm& g, PxnPlan& pl, const void* act, const void
   PxnDev& d = pl.dev;
   d.out = e.out; d.out_f32 = e.out_f32; d.scale = e.scale; d.shift = e.shift; d.relu = e.relu;
   d.stats_partial = e.stats_partial;
+  d.add_src = (const __nv_bfloat16*)e.add_src;
+  PP_REQUIRE(!e.add_src || !e.out_f32, PP_EUNSUPPORTED, "add_src needs a bf16 output");
   {
     static int dbg = -1, m64 = -1;
     if (dbg < 0) { const char* ev = getenv("PP_DEBUG"); dbg = ev ? atoi(ev) : 0; }

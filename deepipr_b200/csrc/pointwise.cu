@@ -1420,6 +1420,29 @@ __global__ void add_relu_bwd_kernel(const __nv_bfloat16* __restrict__ g, const _
   }
 }
 
+// y += a (bf16, fp32 add, round to nearest): fallback of the data-gradient epilogue add (TapEpilogue::add_src)
+__global__ void add_inplace_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ a, size_t n) {
+  const size_t nvec = n >> 3;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    float vy[8], va[8];
+    load8_bf16(y, i, vy);
+    load8_bf16(a, i, va);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vy[k] += va[k];
+    store8_bf16(y, i, vy);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (nvec << 3) + threadIdx.x;
+    y[i] = __float2bfloat16_rn(__bfloat162float(y[i]) + __bfloat162float(a[i]));
+  }
+}
+
+int launch_add_inplace(__nv_bfloat16* y, const __nv_bfloat16* a, size_t n, cudaStream_t s) {
+  add_inplace_kernel<<<grid_for((n >> 3) + 1, 256, 148 * 8), 256, 0, s>>>(y, a, n);
+  PP_POST_LAUNCH();
+  return PP_OK;
+}
+
 int launch_add_relu_fwd(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, size_t n, cudaStream_t s) {
   add_relu_fwd_kernel<<<grid_for(n / 8 + 1, 256, 148 * 8), 256, 0, s>>>(a, b, y, n);
   PP_POST_LAUNCH();

@@ -409,10 +409,33 @@ class BlockOpts:
     algo: Optional[int] = None
     groups: int = 0           # PP_NORM_GN: number of groups (== O for InstanceNorm)
     dtype: int = L.PP_DTYPE_BF16   # PP_DTYPE_*: bf16 tensors / kind::f16, or fp32 tensors / kind::tf32
+    #: (ResidualLink, 'stash' | 'add') or None — see ResidualLink
+    link: Optional[tuple] = None
     #: the block's weight / gamma / beta are Parameters that receive gradients from this operator ONLY (ConvBlock):
     #: when they live in a parallel.FlatParams their gradients are accumulated straight into the flat buffer by
     #: the producing kernels (PP_FLAG_ACC_*), and autograd sees no gradient for them
     direct_grad_ok: bool = False
+
+
+#: PP_RESIDUAL_LINK=1 folds the gradient sum at the input of a residual unit into conv1's data-gradient epilogue
+#: (ResidualLink below).  OFF by default: measured on B200 the epilogue's loads of the second summand are exposed
+#: (the 32 loads of a chunk are ordered behind the chunk's stores and a chunk's latency is not hidden by the next
+#: tile's main loop at the 64-channel geometry), which costs far more than the 0.3 ms of autograd's add launches it
+#: removes — 29.3 ms per step against 15.2 ms.  Kept for the parity tests that pin its numerics (bit-identical sums).
+RESIDUAL_LINK = _os.environ.get("PP_RESIDUAL_LINK", "0") == "1"
+
+
+class ResidualLink:
+    """Carries the gradient of a unit's residual path from the block that closes the unit to the block that opens it.
+
+    x -> conv1 -> conv2(+ x) -> y: autograd would hand `gy` to x twice — through conv1's data gradient and through the
+    residual — and sum the two in a separate pass.  With a link, conv2's backward (role 'stash') parks gy here and
+    reports no gradient for the residual; conv1's backward (role 'add'), which always runs later, has it added in its
+    data-gradient kernel's epilogue (pp_conv_block_bwd_dz dx_add) and returns the complete gradient of x."""
+    __slots__ = ("g",)
+
+    def __init__(self):
+        self.g = None
 
 
 def _flat_slot(t):
@@ -470,6 +493,7 @@ class _ConvBlockFn(torch.autograd.Function):
             L.ptr(o.running_var), L.ptr(z), L.ptr(y), L.ptr(save_mean), L.ptr(save_invstd), L.ptr(res), L.ptr(ws),
             C.c_size_t(nbytes), _stream()), "pp_conv_block_fwd")
         ctx.res_dtype = None if residual is None else residual.dtype
+        ctx.link = o.link
         if need_grad:
             ctx.save_for_backward(xc, z, g, b, save_mean, save_invstd)
             # gradients that can be accumulated by the kernels themselves into a flat gradient buffer
@@ -511,6 +535,10 @@ class _ConvBlockFn(torch.autograd.Function):
         gyc = to_nhwc(gy, o.dtype)
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         sw, sg, sb = ctx.slots
+        link, role = ctx.link if ctx.link is not None else (None, None)
+        dx_add = None
+        if role == 'add' and link.g is not None:          # the residual path's gradient, parked by the closing block
+            dx_add, link.g = link.g, None
         flags = (L.PP_FLAG_ACC_DW if sw else 0) | (L.PP_FLAG_ACC_DGAMMA if sg else 0) | (L.PP_FLAG_ACC_DBETA if sb else 0)
         d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups, flags, o.dtype)
         dx = torch.empty((N, Cx, H, W), dtype=adt, device=dev, memory_format=torch.channels_last) \
@@ -530,9 +558,12 @@ class _ConvBlockFn(torch.autograd.Function):
                 d, key = make_desc(spec, N, H, W, o.norm, o.relu, o.z_f32, o.eps, o.momentum, o.algo, o.groups,
                                    flags | L.PP_FLAG_SHARE_SM, o.dtype)
             dzbuf = torch.empty((N,) + spec.out_hw(H, W) + (spec.O,), dtype=adt, device=dev)
+            fused_add = None
+            if dx_add is not None and dx is not None and adt == torch.bfloat16 and dx_add.shape == dx.shape:
+                fused_add, dx_add = to_nhwc_bf16(dx_add), None          # summed in the dgrad epilogue
             L.check(L.load().pp_conv_block_bwd_dz(
                 C.byref(d), L.ptr(gyc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(g), L.ptr(b), L.ptr(save_mean),
-                L.ptr(save_invstd), L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dzbuf), L.ptr(ws),
+                L.ptr(save_invstd), L.ptr(dx), L.ptr(fused_add), L.ptr(dgamma), L.ptr(dbeta), L.ptr(dzbuf), L.ptr(ws),
                 C.c_size_t(nbytes), _stream()), "pp_conv_block_bwd_dz")
             side = _side_for(dev)
             ws2, nbytes2 = workspace(d, key, L.PP_WS_BWD, dev, slot=1)
@@ -549,6 +580,8 @@ class _ConvBlockFn(torch.autograd.Function):
                 C.byref(d), L.ptr(gyc), L.ptr(xc), L.ptr(ctx.prepared.wd), L.ptr(z), L.ptr(g), L.ptr(b),
                 L.ptr(save_mean), L.ptr(save_invstd), L.ptr(dx), L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws),
                 C.c_size_t(nbytes), _stream()), "pp_conv_block_bwd")
+        if dx_add is not None:                 # not summed by the kernel (other path / no dx of our own): one torch add
+            dx = dx_add.to(adt) if dx is None else dx + dx_add.to(dx.dtype)
         if dx is not None and ctx.x_dtype != adt:
             dx = dx.to(ctx.x_dtype)
         gg = dgamma.reshape(ctx.gshape).to(ctx.gdtype) if (ctx.gshape is not None and ctx.needs_input_grad[2]) else None
@@ -559,6 +592,8 @@ class _ConvBlockFn(torch.autograd.Function):
                 slot[0].direct_done(slot[1])
         # the join is y = block + residual: the residual receives the upstream gradient unchanged (no kernel)
         g_res = gy.to(ctx.res_dtype) if (ctx.res_dtype is not None and ctx.needs_input_grad[6]) else None
+        if g_res is not None and role == 'stash' and gy.dtype == torch.bfloat16 and ctx.res_dtype == torch.bfloat16:
+            link.g, g_res = gyc, None          # the opening block of the unit adds it to its data gradient
         return dx, (None if sw else dw), (None if sg else gg), (None if sb else gb), None, None, g_res
 
 

@@ -232,10 +232,12 @@ class ConvBlock(nn.Module, _FusedConvMixin):
             return False
         return norm == L.PP_NORM_BN_TRAIN or torch.is_grad_enabled()
 
-    def forward(self, x, residual=None):
+    def forward(self, x, residual=None, _link=None):
         """``residual`` (extension over the reference signature, used by nets.BasicUnit): a tensor >= 0 of the output's
         shape that is added after the ReLU, i.e. the unit's residual join folded into this block
-        (F.relu(out + shortcut) of resnet_passport_private.py:78-85 with both summands already non-negative)."""
+        (F.relu(out + shortcut) of resnet_passport_private.py:78-85 with both summands already non-negative).
+        ``_link``: (functional.ResidualLink, role) — the two ConvBlocks of a unit hand the residual path's gradient
+        from one backward to the other instead of leaving the sum to autograd."""
         F_.require_cuda(x, "ConvBlock input")
         self._check_conv()
         norm = _norm_mode(self.bn)
@@ -255,6 +257,7 @@ class ConvBlock(nn.Module, _FusedConvMixin):
             gamma, beta = self.bn.weight, self.bn.bias
         o = self._bn_opts(norm, self.relu is not None, self.z_f32, x, dtype)
         o.direct_grad_ok = True      # conv.weight / bn.weight / bn.bias (or conv.bias) feed this operator only
+        o.link = _link
         if residual is not None:
             if not self.can_fuse_residual(x):
                 raise RuntimeError("deepipr_b200: this ConvBlock call cannot fuse a residual (see can_fuse_residual)")

@@ -126,10 +126,20 @@ class BasicUnit(nn.Module):
         return last_relu and getattr(self.shortcut, 'relu', None) is not None
 
     def forward(self, x, force_passport=False, ind=0):
-        out = _call(self.convbnrelu_1, x, force_passport, ind)
         identity = isinstance(self.shortcut, nn.Sequential)
+        c1, c2 = self.convbnrelu_1, self.convbn_2
+        # identity unit made of two ConvBlocks whose join will be folded: the residual path's gradient travels from
+        # convbn_2's backward to convbnrelu_1's (functional.ResidualLink) instead of being summed by autograd
+        link = None
+        if (F_.RESIDUAL_LINK and identity and x.is_cuda and x.requires_grad and torch.is_grad_enabled()
+                and self._join_is_plain_sum()
+                and isinstance(c1, ConvBlock) and isinstance(c2, ConvBlock) and c2.can_fuse_residual(x)
+                and c1.conv.stride == (1, 1)):
+            link = F_.ResidualLink()
+            out = c1(x, _link=(link, 'add'))
+        else:
+            out = _call(c1, x, force_passport, ind)
         plain = self._join_is_plain_sum() and out.is_cuda
-        c2 = self.convbn_2
         # Folding the join into convbn_2 needs the shortcut first.  Passport blocks must run in the reference's order
         # (convbnrelu_1, convbn_2, shortcut: resnet_passport_private.py:67-85) because a block without keys draws them
         # from numpy's global RNG on its first forward (passportconv2d_private.py:198-207) — only plain ConvBlocks,
@@ -138,7 +148,7 @@ class BasicUnit(nn.Module):
                 and c2.can_fuse_residual(out)):
             sc = x if identity else self.shortcut(x)
             if sc.dtype == out.dtype:
-                return c2(out, residual=sc)
+                return c2(out, residual=sc, _link=None if link is None else (link, 'stash'))
             out = c2(out)
         else:
             out = _call(c2, out, force_passport, ind)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 15
+#define PP_ABI_VERSION 16
 
 typedef enum PPStatus {
   PP_OK = 0,
@@ -246,10 +246,14 @@ int pp_passport_conv_bwd(const PPConvDesc* d, const void* dy, const void* x, con
  * The weight gradient is then pp_conv_wgrad(d, dz_out, x, dw, ...) — a tensor-core kernel nothing downstream in the
  * backward pass depends on, which the caller may launch on a second stream so that it overlaps the HBM-bound passes
  * of the next block's backward (deepipr_b200.functional does, into a flat gradient buffer with PP_FLAG_ACC_DW).
- * Batch-norm / plain blocks only (PP_NORM_GN: PP_EUNSUPPORTED). */
+ * Batch-norm / plain blocks only (PP_NORM_GN: PP_EUNSUPPORTED).
+ * dx_add (optional, bf16, the shape of dx): a gradient that reaches the block's input by another route (the residual
+ * path of a ResNet unit, resnet_passport_private.py:78-85) and is added to the data gradient in the dgrad kernel's
+ * epilogue, dx = bf16(bf16(dgrad) + dx_add) — the sum autograd would otherwise form in a separate pass. */
 int pp_conv_block_bwd_dz(const PPConvDesc* d, const void* dy, const void* w_dgrad, const void* z, const float* gamma,
                          const float* beta, const float* save_mean, const float* save_invstd, void* dx,
-                         float* dgamma, float* dbeta, void* dz_out, void* workspace, size_t ws_bytes, void* stream);
+                         const void* dx_add, float* dgamma, float* dbeta, void* dz_out, void* workspace,
+                         size_t ws_bytes, void* stream);
 
 /* Building blocks exposed for tests / profiling (same kernels the two calls above use).  pp_conv_wgrad honours
  * PP_FLAG_ACC_DW in d->flags (adds into dw_oihw). */

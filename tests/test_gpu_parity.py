@@ -1129,6 +1129,16 @@ def test_residual_join_folded_into_the_block_equals_the_separate_pass(geom):
 
     y_sep, dx_sep, g_sep, n_sep = run(False)
     y_fus, dx_fus, g_fus, n_fus = run(True)
+    # the (off by default) residual-gradient link: conv1's dgrad epilogue adds the residual path's gradient
+    # (functional.ResidualLink, pp_conv_block_bwd_dz dx_add) — the same sums again, bit for bit
+    was, F_.RESIDUAL_LINK = F_.RESIDUAL_LINK, True
+    try:
+        y_lnk, dx_lnk, g_lnk, _ = run(True)
+    finally:
+        F_.RESIDUAL_LINK = was
+    assert torch.equal(y_lnk, y_fus) and torch.equal(dx_lnk * (x0 > 0), dx_fus * (x0 > 0))
+    for k in g_fus:
+        assert torch.equal(g_lnk[k], g_fus[k]), k
     assert n_fus <= n_sep                # no relu(a + b) launch forward, none backward (the separate path may use the
                                          # single-kernel block for convbn_2 where it applies, hence not always - 2)
     assert torch.equal(y_sep, y_fus)
