@@ -170,8 +170,6 @@ int launch_sign_loss_bwd(int O, const float* gamma, const float* b, float alpha,
 int launch_bn_finalize(const PPConvDesc& d, int n_per_channel, const float* stats_partial, int num_tiles,
                        const float* gamma, const float* beta, float* running_mean, float* running_var,
                        float* save_mean, float* save_invstd, float* coef_a, float* coef_b, cudaStream_t s);
-int launch_affine_coef(int O, const float* gamma, const float* beta, const float* mean, const float* invstd,
-                       float* ca, float* cb, cudaStream_t s);
 int launch_affine_apply(const void* z, int z_f32, size_t rows, int O, const float* a, const float* b, int relu,
                         void* y, int y_f32, const void* res /*bf16 residual added after the ReLU, or NULL*/,
                         cudaStream_t s);

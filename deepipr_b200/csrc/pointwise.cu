@@ -480,24 +480,6 @@ int launch_bn_finalize(const PPConvDesc& d, int n, const float* partial, int num
   return PP_OK;
 }
 
-// a = gamma*invstd, b = beta - a*mean from the statistics the forward saved (backward re-derives them)
-__global__ void affine_coef_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const float* __restrict__ mean, const float* __restrict__ invstd,
-                                   float* __restrict__ ca, float* __restrict__ cb, int O) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= O) return;
-  const float a = (gamma ? gamma[o] : 1.0f) * invstd[o];
-  ca[o] = a;
-  cb[o] = (beta ? beta[o] : 0.0f) - a * mean[o];
-}
-
-int launch_affine_coef(int O, const float* gamma, const float* beta, const float* mean, const float* invstd,
-                       float* ca, float* cb, cudaStream_t s) {
-  affine_coef_kernel<<<(O + 63) / 64, 64, 0, s>>>(gamma, beta, mean, invstd, ca, cb, O);
-  PP_POST_LAUNCH();
-  return PP_OK;
-}
-
 // ---------------------------------------------------------------------------------------------
 // affine + ReLU pass: y[r, o] = relu(a[o]*z[r,o] + b[o]); 8 channels (one 128-bit bf16 vector) per thread.
 // RES: the residual join of a basic block folded in, y = bf16(relu(a z + b)) + res — the block output is rounded to
